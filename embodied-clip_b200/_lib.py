@@ -1,0 +1,82 @@
+"""ctypes binding of libembclip_b200.so (C ABI: include/embclip_b200.h).
+
+Fails loudly: a missing library is an ImportError-grade RuntimeError, never a fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libembclip_b200.so")
+
+DTYPE_F16, DTYPE_F32 = 0, 1
+
+
+class RN50Cfg(C.Structure):
+    _fields_ = [("layers", C.c_int32 * 4), ("width", C.c_int32), ("heads", C.c_int32),
+                ("output_dim", C.c_int32), ("input_resolution", C.c_int32)]
+
+
+class ParamInfo(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("dtype", C.c_int32), ("ndim", C.c_int32),
+                ("shape", C.c_int64 * 4), ("offset", C.c_uint64), ("nbytes", C.c_uint64)]
+
+
+class ActInfo(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("dtype", C.c_int32), ("n", C.c_int32), ("h", C.c_int32),
+                ("w", C.c_int32), ("c", C.c_int32), ("offset", C.c_uint64)]
+
+
+# symbol -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
+_VP, _I, _U64, _FP = C.c_void_p, C.c_int, C.c_uint64, C.c_void_p
+SIGNATURES = {
+    "embclip_last_error": (C.c_char_p, []),
+    "embclip_abi_version": (_I, []),
+    "embclip_rn50_create": (_I, [C.POINTER(RN50Cfg), C.POINTER(_VP)]),
+    "embclip_rn50_destroy": (_I, [_VP]),
+    "embclip_rn50_num_params": (_I, [_VP]),
+    "embclip_rn50_param_info": (_I, [_VP, _I, C.POINTER(ParamInfo)]),
+    "embclip_rn50_blob_bytes": (_U64, [_VP]),
+    "embclip_rn50_bind_weights": (_I, [_VP, _VP, _U64]),
+    "embclip_rn50_workspace_bytes": (_U64, [_VP, _I]),
+    "embclip_rn50_forward": (_I, [_VP, _FP, _I, _FP, _FP, _FP, _VP, _U64, _VP]),
+    "embclip_rn50_num_acts": (_I, [_VP]),
+    "embclip_rn50_act_info": (_I, [_VP, _I, _I, C.POINTER(ActInfo)]),
+    "embclip_rn50_profile": (_I, [_VP, _FP, _I, _FP, _FP, _FP, _VP, _U64, _VP, _VP, _VP, _I]),
+    "embclip_rn50_launches_per_forward": (_I, [_VP, _I, _I, _I]),
+    "embclip_gemm_f16": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
+    "embclip_gemm_grouped_f16": (_I, [_VP, _I, _VP, _I, _I, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP]),
+    "embclip_conv3x3_f16": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
+    "embclip_avgpool2_f16": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
+    "embclip_stem_conv1": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"embclip_b200: {LIB_PATH} is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU / PyTorch fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)       # AttributeError here = header / library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class EmbclipError(RuntimeError):
+    pass
+
+
+def check(rc: int) -> int:
+    if rc < 0:
+        raise EmbclipError(f"embclip_b200 error {rc}: {load().embclip_last_error().decode()}")
+    return rc

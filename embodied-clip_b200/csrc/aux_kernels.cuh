@@ -1,0 +1,296 @@
+// Non-GEMM kernels of the encoder path: HBM-bound vectorised / warp-shuffle work.
+//   stem_conv1_kernel     3->C 3x3 stride-2 conv + folded BN + ReLU straight from the fp32 NHWC frames
+//   avgpool2_kernel       nn.AvgPool2d(2), NHWC fp16
+//   attnpool_tokens       mean token + positional embedding  -> fp16 tokens [B, HW+1, C]
+//   attnpool_core         single-query softmax attention over HW+1 keys, per head, warp-shuffle
+//   avg_head / nhwc_to_nchw   the two trivial output heads
+#pragma once
+#include "ptx.cuh"
+
+namespace embclip {
+
+// ------------------------------------------------------------------------------------------------
+// Stem conv1 (clip/model.py ModifiedResNet.conv1+bn1+relu): K = 27 is too thin for the tensor pipe and the
+// layer is bound by the fp32 frame read, so it runs on CUDA cores: one thread = one output pixel x COUT
+// channels, weights broadcast from shared memory.
+// ------------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(128)
+stem_conv1_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                  __half* __restrict__ y, int B, int R) {
+  __shared__ float sw[27 * COUT];
+  __shared__ float sb[COUT];
+  for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias[i];
+  __syncthreads();
+  const int Ro = R / 2;
+  const long long total = (long long)B * Ro * Ro;
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= total) return;
+  const int ow = int(pix % Ro);
+  const int oh = int((pix / Ro) % Ro);
+  const int b = int(pix / ((long long)Ro * Ro));
+  float acc[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc[c] = sb[c];
+  const float* xb = x + (size_t)b * R * R * 3;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    const int ih = 2 * oh - 1 + kh;
+    if (ih < 0 || ih >= R) continue;
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int iw = 2 * ow - 1 + kw;
+      if (iw < 0 || iw >= R) continue;
+      const float* px = xb + ((size_t)ih * R + iw) * 3;
+      const float v0 = __ldg(px), v1 = __ldg(px + 1), v2 = __ldg(px + 2);
+      const float4* w0 = reinterpret_cast<const float4*>(sw + ((kh * 3 + kw) * 3 + 0) * COUT);
+      const float4* w1 = reinterpret_cast<const float4*>(sw + ((kh * 3 + kw) * 3 + 1) * COUT);
+      const float4* w2 = reinterpret_cast<const float4*>(sw + ((kh * 3 + kw) * 3 + 2) * COUT);
+#pragma unroll
+      for (int c4 = 0; c4 < COUT / 4; ++c4) {
+        const float4 a = w0[c4], bq = w1[c4], cq = w2[c4];
+        acc[4 * c4 + 0] += v0 * a.x + v1 * bq.x + v2 * cq.x;
+        acc[4 * c4 + 1] += v0 * a.y + v1 * bq.y + v2 * cq.y;
+        acc[4 * c4 + 2] += v0 * a.z + v1 * bq.z + v2 * cq.z;
+        acc[4 * c4 + 3] += v0 * a.w + v1 * bq.w + v2 * cq.w;
+      }
+    }
+  }
+  uint4* out = reinterpret_cast<uint4*>(y + (size_t)pix * COUT);
+#pragma unroll
+  for (int i = 0; i < COUT / 8; ++i) {
+    uint4 o;
+    o.x = pack_half2(fmaxf(acc[8 * i + 0], 0.f), fmaxf(acc[8 * i + 1], 0.f));
+    o.y = pack_half2(fmaxf(acc[8 * i + 2], 0.f), fmaxf(acc[8 * i + 3], 0.f));
+    o.z = pack_half2(fmaxf(acc[8 * i + 4], 0.f), fmaxf(acc[8 * i + 5], 0.f));
+    o.w = pack_half2(fmaxf(acc[8 * i + 6], 0.f), fmaxf(acc[8 * i + 7], 0.f));
+    out[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// nn.AvgPool2d(2) on NHWC fp16; one thread = 8 channels of one output pixel (16-B vectors).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void acc8(float (&a)[8], const uint4 v) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    a[2 * i] += f.x;
+    a[2 * i + 1] += f.y;
+  }
+}
+__global__ void __launch_bounds__(256)
+avgpool2_kernel(const __half* __restrict__ x, __half* __restrict__ y, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
+  const long long total = (long long)B * Ho * Wo * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = int(i % C8);
+    long long r = i / C8;
+    const int ow = int(r % Wo);
+    r /= Wo;
+    const int oh = int(r % Ho);
+    const int b = int(r / Ho);
+    const uint4* p = reinterpret_cast<const uint4*>(x + (((size_t)b * H + 2 * oh) * W + 2 * ow) * C) + c8;
+    const size_t rowstride = (size_t)W * C8;
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    acc8(a, __ldg(p));
+    acc8(a, __ldg(p + C8));
+    acc8(a, __ldg(p + rowstride));
+    acc8(a, __ldg(p + rowstride + C8));
+    uint4 o;
+    o.x = pack_half2(a[0] * .25f, a[1] * .25f);
+    o.y = pack_half2(a[2] * .25f, a[3] * .25f);
+    o.z = pack_half2(a[4] * .25f, a[5] * .25f);
+    o.w = pack_half2(a[6] * .25f, a[7] * .25f);
+    reinterpret_cast<uint4*>(y)[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// AttentionPool2d front end: tokens[b,0,:] = mean_p x[b,p,:] + pos[0];  tokens[b,1+p,:] = x[b,p,:] + pos[1+p].
+// x is the fp32 NHWC trunk output [B, P, C]; one thread = 4 channels.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+attnpool_tokens_kernel(const float* __restrict__ x, const float* __restrict__ pos, __half* __restrict__ tok,
+                       int P, int C) {
+  const int b = blockIdx.y;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= C) return;
+  const float* xb = x + (size_t)b * P * C + c;
+  __half* tb = tok + (size_t)b * (P + 1) * C + c;
+  float4 s = make_float4(0, 0, 0, 0);
+  for (int p = 0; p < P; ++p) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)p * C));
+    const float4 e = __ldg(reinterpret_cast<const float4*>(pos + (size_t)(p + 1) * C + c));
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    uint2 o;
+    o.x = pack_half2(v.x + e.x, v.y + e.y);
+    o.y = pack_half2(v.z + e.z, v.w + e.w);
+    *reinterpret_cast<uint2*>(tb + (size_t)(p + 1) * C) = o;
+  }
+  const float inv = 1.f / float(P);
+  const float4 e0 = __ldg(reinterpret_cast<const float4*>(pos + c));
+  uint2 o;
+  o.x = pack_half2(s.x * inv + e0.x, s.y * inv + e0.y);
+  o.y = pack_half2(s.z * inv + e0.z, s.w * inv + e0.w);
+  *reinterpret_cast<uint2*>(tb) = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// AttentionPool2d core.  Only query row 0 is consumed downstream, and
+//   q_h . (Wk_h t_j + bk_h) = (Wk_h^T q_h) . t_j + const_h        (const_h drops out of the softmax)
+//   sum_j p_j (Wv_h t_j + bv_h) = Wv_h (sum_j p_j t_j) + bv_h     (sum_j p_j = 1)
+// so per (image, head) this kernel takes the folded query qt = Wk_h^T q_h (length C) and the L = HW+1 tokens,
+// computes s_j = qt . t_j, p = softmax(s) and the head's token average  xbar_h = sum_j p_j t_j  (length C).
+// The two remaining contractions (with Wk^T before, Wv after) are grouped GEMMs on the tensor pipe.
+// Grid (B, heads/HG); 256 threads.  Requires C == 2048 * (C/2048) multiple of 2048? no: C % 256*8 == 0.
+// ------------------------------------------------------------------------------------------------
+template <int HG>
+__global__ void __launch_bounds__(256)
+attnpool_core_kernel(const __half* __restrict__ qt,   // [B, heads, C]
+                     const __half* __restrict__ tok,  // [B, L, C]
+                     __half* __restrict__ xbar,       // [B, heads, C]
+                     int heads, int L, int C) {
+  extern __shared__ uint8_t smem[];
+  __half* sq = reinterpret_cast<__half*>(smem);                        // [HG][C]
+  float* sp = reinterpret_cast<float*>(smem + (size_t)HG * C * 2);     // [HG][64]
+  const int b = blockIdx.x;
+  const int h0 = blockIdx.y * HG;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C8 = C / 8;
+
+  const uint4* gq = reinterpret_cast<const uint4*>(qt + ((size_t)b * heads + h0) * C);
+  for (int i = tid; i < HG * C8; i += 256) reinterpret_cast<uint4*>(sq)[i] = __ldg(gq + i);
+  __syncthreads();
+
+  // scores: warp <-> token, lanes stride the channel dimension in 16-B pieces
+  const __half* tb = tok + (size_t)b * L * C;
+  for (int j = warp; j < L; j += 8) {
+    float part[HG];
+#pragma unroll
+    for (int h = 0; h < HG; ++h) part[h] = 0.f;
+    const uint4* tj = reinterpret_cast<const uint4*>(tb + (size_t)j * C);
+    for (int i = lane; i < C8; i += 32) {
+      const uint4 tv = __ldg(tj + i);
+      const __half2* t2 = reinterpret_cast<const __half2*>(&tv);
+      float tf[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(t2[k]);
+        tf[2 * k] = f.x;
+        tf[2 * k + 1] = f.y;
+      }
+#pragma unroll
+      for (int h = 0; h < HG; ++h) {
+        const uint4 qv = reinterpret_cast<const uint4*>(sq + (size_t)h * C)[i];
+        const __half2* q2 = reinterpret_cast<const __half2*>(&qv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(q2[k]);
+          part[h] += f.x * tf[2 * k] + f.y * tf[2 * k + 1];
+        }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < HG; ++h) {
+      float v = part[h];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) sp[h * 64 + j] = v;
+    }
+  }
+  __syncthreads();
+
+  // softmax over the L keys: warp <-> head
+  if (warp < HG) {
+    const float v0 = lane < L ? sp[warp * 64 + lane] : -INFINITY;
+    const float v1 = lane + 32 < L ? sp[warp * 64 + lane + 32] : -INFINITY;
+    float m = fmaxf(v0, v1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float e0 = lane < L ? __expf(v0 - m) : 0.f;
+    const float e1 = lane + 32 < L ? __expf(v1 - m) : 0.f;
+    float s = e0 + e1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float inv = 1.f / s;
+    if (lane < L) sp[warp * 64 + lane] = e0 * inv;
+    if (lane + 32 < L) sp[warp * 64 + lane + 32] = e1 * inv;
+  }
+  __syncthreads();
+
+  // weighted token average: thread <-> 8 channels, all HG heads
+  for (int i = tid; i < C8; i += 256) {
+    float acc[HG][8];
+#pragma unroll
+    for (int h = 0; h < HG; ++h)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[h][k] = 0.f;
+    for (int j = 0; j < L; ++j) {
+      const uint4 tv = __ldg(reinterpret_cast<const uint4*>(tb + (size_t)j * C) + i);
+      const __half2* t2 = reinterpret_cast<const __half2*>(&tv);
+      float tf[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(t2[k]);
+        tf[2 * k] = f.x;
+        tf[2 * k + 1] = f.y;
+      }
+#pragma unroll
+      for (int h = 0; h < HG; ++h) {
+        const float pj = sp[h * 64 + j];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[h][k] += pj * tf[k];
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < HG; ++h) {
+      uint4 o;
+      o.x = pack_half2(acc[h][0], acc[h][1]);
+      o.y = pack_half2(acc[h][2], acc[h][3]);
+      o.z = pack_half2(acc[h][4], acc[h][5]);
+      o.w = pack_half2(acc[h][6], acc[h][7]);
+      reinterpret_cast<uint4*>(xbar + ((size_t)b * heads + h0 + h) * C)[i] = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Output heads from the fp32 NHWC trunk result [B, P, C].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+avg_head_kernel(const float* __restrict__ x, float* __restrict__ y, int P, int C) {
+  const int b = blockIdx.y;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= C) return;
+  const float* xb = x + (size_t)b * P * C + c;
+  float4 s = make_float4(0, 0, 0, 0);
+  for (int p = 0; p < P; ++p) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)p * C));
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  const float inv = 1.f / float(P);
+  *reinterpret_cast<float4*>(y + (size_t)b * C + c) = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
+}
+
+// [B, P, C] -> [B, C, P]; one block = 32 channels of one image, out slab [32][P] is contiguous.
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int P, int C) {
+  extern __shared__ float tile[];   // [P][33]
+  const int b = blockIdx.y, c0 = blockIdx.x * 32;
+  const float* xb = x + (size_t)b * P * C + c0;
+  for (int i = threadIdx.x; i < P * 32; i += blockDim.x) {
+    const int p = i >> 5, c = i & 31;
+    tile[p * 33 + c] = __ldg(xb + (size_t)p * C + c);
+  }
+  __syncthreads();
+  float* yb = y + ((size_t)b * C + c0) * P;
+  for (int i = threadIdx.x; i < P * 32; i += blockDim.x) {
+    const int c = i / P, p = i - c * P;
+    yb[i] = tile[p * 33 + c];
+  }
+}
+
+}  // namespace embclip

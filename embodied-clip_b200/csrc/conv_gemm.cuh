@@ -1,0 +1,292 @@
+// conv_gemm: the one tensor-core kernel of the encoder path.
+//
+//   C[m, n] = epilogue( sum_k A[m, k] * W[n, k] )      fp16 x fp16 -> fp32 (TMEM) -> fp16 / fp32
+//
+// * A is an NHWC fp16 activation seen through a 4-D TMA tensor map {C, W, H, N}; a 1x1 conv / linear
+//   layer is the degenerate case {K, M, 1, 1}.  A 3x3 (pad 1, stride 1) conv is an implicit GEMM: the
+//   M-tile is a box of box_w x box_h x box_n pixels, and each of the 9 taps is the same box loaded at a
+//   shifted (w, h) coordinate -- TMA's out-of-bounds zero fill IS the conv padding, nothing is materialised.
+// * An optional second A source (2-D) is concatenated along K: this fuses a bottleneck's downsample 1x1
+//   conv into its conv3 ( [W3 | Wd] . [t ; x] ), so the identity tensor never touches HBM.
+// * "Grouped" mode offsets the K window per N-group (per attention head), which is how AttentionPool2d's
+//   per-head contractions run on the same kernel.
+// * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread tcgen05.mma
+//   issuer, warps 2..5 = epilogue (TMEM -> regs -> +bias (+residual) -> ReLU -> fp16 -> swizzled smem -> TMA
+//   store).  smem stages are handed over with full/empty mbarriers; the accumulator is double-buffered
+//   in TMEM (2 x BN columns) so tile i's epilogue overlaps tile i+1's MMAs.  Persistent grid.
+#pragma once
+#include "ptx.cuh"
+
+namespace embclip {
+
+struct ConvGemmParams {
+  int num_m_blks, num_n_blks;
+  int tiles_w, tiles_h;         // M-tile grid inside one image group (2-D mode: tiles_w = num_m_blks, tiles_h = 1)
+  int box_w, box_h, box_n;      // pixels per M-tile = box_w * box_h * box_n <= 128 (2-D mode: 128, 1, 1)
+  int taps;                     // 1 or 9
+  int kb_per_tap;               // Cin / BK of source 0
+  int kb_src0;                  // k-blocks read from A0 (= taps * kb_per_tap); the rest come from A1
+  int kb_total;
+  uint32_t a0_box_bytes;        // bytes one A0 box load delivers (box may hold fewer than 128 rows)
+  int relu;
+  int out_f32;                  // 1: epilogue stores fp32 rows straight to `out_f32_ptr` (2-D mode only)
+  int M, N;                     // logical GEMM extents (rows valid for residual / fp32 stores)
+  const float* bias;            // [N] or nullptr
+  const __half* residual;       // [M, ldr] or nullptr (2-D mode only)
+  int ldr;
+  float* out_f32_ptr;           // [M, ldo]
+  int ldo;
+  // grouped mode (0 = off): N-group g = n0 / grp_n reads A at k + g*grp_a_koff, W at k + g*grp_b_koff,
+  // and W rows n0 % grp_b_nmod (if grp_b_nmod != 0)
+  int grp_n, grp_a_koff, grp_b_koff, grp_b_nmod;
+};
+
+template <int BN, int BK>
+struct ConvGemmCfg {
+  static constexpr int BM = 128;
+  static constexpr int kSwz = BK * 2;                          // operand swizzle span (bytes)
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kCS = BN < 64 ? BN : 64;                // channels per C staging chunk / TMA store box
+  static constexpr int kCSwz = kCS * 2;
+  static constexpr int kCChunkBytes = BM * kCS * 2;
+  static constexpr int kCBytes = BM * BN * 2;
+  static constexpr int kBudget = 200 * 1024;
+  static constexpr int kStagesRaw = (kBudget - kCBytes) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int kBarBytes = 256;                        // mbarriers + tmem ptr
+  static constexpr int kBiasBytes = BN * 4;
+  static constexpr size_t kSmemBytes = 1024 /*align slack*/ + size_t(kStages) * kStageBytes + kCBytes + kBiasBytes + kBarBytes;
+  static_assert(kStages >= 2, "pipeline needs at least two stages");
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
+  static_assert(kABytes % 1024 == 0 && kBBytes % 1024 == 0, "stage tiles must keep 1024-B alignment");
+};
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(192, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                 const ConvGemmParams p) {
+  using Cfg = ConvGemmCfg<BN, BK>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + S * Cfg::kABytes;
+  const uint32_t sC = sB + S * Cfg::kBBytes;
+  const uint32_t sBias = sC + Cfg::kCBytes;
+  const uint32_t sBar = sBias + Cfg::kBiasBytes;
+  const uint32_t bar_full = sBar;                 // S x 8 B
+  const uint32_t bar_empty = sBar + 8 * S;        // S x 8 B
+  const uint32_t bar_tfull = sBar + 16 * S;       // 2 x 8 B
+  const uint32_t bar_tempty = bar_tfull + 16;     // 2 x 8 B
+  const uint32_t tmem_slot = bar_tempty + 16;     // 4 B
+  uint8_t* const gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  float* const sBias_ptr = reinterpret_cast<float*>(gen_base + (sBias - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_blks * p.num_n_blks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    if (p.kb_src0 < p.kb_total) tma_prefetch_desc(&tmA1);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 4);           // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int n_blk = t % p.num_n_blks;
+        const int m_blk = t / p.num_n_blks;
+        const int tw = m_blk % p.tiles_w;
+        const int th = (m_blk / p.tiles_w) % p.tiles_h;
+        const int ng = m_blk / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.box_w, h0 = th * p.box_h, i0 = ng * p.box_n;
+        const int n0 = n_blk * BN;
+        int a_koff = 0, b_koff = 0, b_row = n0;
+        if (p.grp_n) {
+          const int g = n0 / p.grp_n;
+          a_koff = g * p.grp_a_koff;
+          b_koff = g * p.grp_b_koff;
+          if (p.grp_b_nmod) b_row = n0 % p.grp_b_nmod;
+        }
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+          const uint32_t full = bar_full + 8 * stage;
+          if (kb < p.kb_src0) {
+            mbar_arrive_expect_tx(full, p.a0_box_bytes + Cfg::kBBytes);
+            const int tap = kb / p.kb_per_tap;
+            const int c0 = (kb - tap * p.kb_per_tap) * BK;
+            int dw = 0, dh = 0;
+            if (p.taps == 9) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+            tma_load_4d(&tmA0, full, sA + stage * Cfg::kABytes, c0 + a_koff, w0 + dw, h0 + dh, i0);
+          } else {
+            mbar_arrive_expect_tx(full, Cfg::kABytes + Cfg::kBBytes);
+            tma_load_4d(&tmA1, full, sA + stage * Cfg::kABytes, (kb - p.kb_src0) * BK, w0, 0, 0);
+          }
+          tma_load_2d(&tmB, full, sB + stage * Cfg::kBBytes, kb * BK + b_koff, b_row);
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16_f32(128, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);       // epilogue has drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tcgen05_fence_after();
+          const uint64_t a_desc = make_kmajor_desc<Cfg::kSwz>(sA + stage * Cfg::kABytes);
+          const uint64_t b_desc = make_kmajor_desc<Cfg::kSwz>(sB + stage * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the swizzle span: +2 in the (addr >> 4) field
+            umma_f16_ss(d_tmem, a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc, uint32_t((kb | k) != 0));
+          }
+          umma_commit(bar_empty + 8 * stage);                  // smem stage free once these MMAs retire
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(bar_tfull + 8 * acc);                      // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================ epilogue (warps 2..5) ============================
+    const int q = warp & 3;                                    // TMEM lane quarter this warp may touch
+    const int row = q * 32 + lane;                             // row of the 128-row tile
+    const int epi_tid = threadIdx.x - 64;
+    const bool store_leader = (threadIdx.x == 64);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int n_blk = t % p.num_n_blks;
+      const int m_blk = t / p.num_n_blks;
+      const int tw = m_blk % p.tiles_w;
+      const int th = (m_blk / p.tiles_w) % p.tiles_h;
+      const int ng = m_blk / (p.tiles_w * p.tiles_h);
+      const int w0 = tw * p.box_w, h0 = th * p.box_h, i0 = ng * p.box_n;
+      const int n0 = n_blk * BN;
+      const int grow = w0 + row;                               // global row (2-D mode)
+      const bool row_ok = grow < p.M;
+
+      // staging smem + bias tile are reused: previous tile's TMA store must have read them
+      if (store_leader) tma_store_wait_read0();
+      for (int i = epi_tid; i < BN; i += 128) sBias_ptr[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+      named_bar_sync(1, 128);
+
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + c * 32), v);
+        uint4 rres[4];
+        const bool has_res = (p.residual != nullptr) && row_ok;
+        if (has_res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + size_t(grow) * p.ldr + n0 + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rres[i] = __ldg(rp + i);
+        }
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + sBias_ptr[c * 32 + i];
+        if (has_res) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const __half2* h = reinterpret_cast<const __half2*>(&rres[i]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 r2 = __half22float2(h[j]);
+              f[i * 8 + j * 2] += r2.x;
+              f[i * 8 + j * 2 + 1] += r2.y;
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        if (p.out_f32) {
+          if (row_ok) {
+            float4* op = reinterpret_cast<float4*>(p.out_f32_ptr + size_t(grow) * p.ldo + n0 + c * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          }
+        } else {
+          // chunk of kCS channels = one TMA store box; 16-B pieces land at their swizzled slot
+          const int col = c * 32;
+          const uint32_t chunk_base = sC + uint32_t(col / Cfg::kCS) * Cfg::kCChunkBytes;
+          const int piece0 = (col % Cfg::kCS) / 8;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t a = chunk_base + swizzle_off<Cfg::kCSwz>(uint32_t(row), uint32_t(piece0 + i));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
+                         "r"(pack_half2(f[8 * i], f[8 * i + 1])), "r"(pack_half2(f[8 * i + 2], f[8 * i + 3])),
+                         "r"(pack_half2(f[8 * i + 4], f[8 * i + 5])), "r"(pack_half2(f[8 * i + 6], f[8 * i + 7]))
+                         : "memory");
+          }
+        }
+      }
+      // accumulator drained -> MMA warp may overwrite it
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+
+      // all epilogue threads are done with sBias / have written their staging rows
+      if (!p.out_f32) fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (!p.out_f32) {
+        if (store_leader) {
+#pragma unroll
+          for (int cc = 0; cc < BN / Cfg::kCS; ++cc)
+            tma_store_4d(&tmC, sC + cc * Cfg::kCChunkBytes, n0 + cc * Cfg::kCS, w0, h0, i0);
+          tma_store_commit();
+        }
+      }
+    }
+    if (store_leader) tma_store_wait_all0();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace embclip

@@ -1,0 +1,687 @@
+// libembclip_b200.so -- host side of the C ABI declared in include/embclip_b200.h:
+// tensor-map construction, kernel launchers, and the ModifiedResNet (CLIP-RN50) execution plan.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/embclip_b200.h"
+#include "aux_kernels.cuh"
+#include "conv_gemm.cuh"
+
+using namespace embclip;
+
+// =============================================================================================
+// errors
+// =============================================================================================
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess) return fail(EMBCLIP_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" const char* embclip_last_error(void) { return g_err.c_str(); }
+extern "C" int embclip_abi_version(void) { return 1; }
+
+// =============================================================================================
+// TMA descriptors (driver entry point resolved at run time: the library links only against cudart)
+// =============================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+static CUtensorMapSwizzle swizzle_for_bytes(int inner_bytes) {
+  return inner_bytes >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : (inner_bytes >= 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+// fp16 tensor, dims fastest-first, `pitch[i]` = byte stride of dim i+1.
+static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* pitch,
+                    const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(EMBCLIP_ECUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = pitch[i];
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(int(box[0]) * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(EMBCLIP_ECUDA, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu box %u %u %u %u", int(r), rank,
+                (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), (unsigned long long)(rank > 2 ? dims[2] : 0),
+                (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+  return 0;
+}
+// activation / output [n, h, w, c] with pixel pitch `ldc` elements (>= c; lets a GEMM view a K window of a wider row)
+static int make_map_nhwc(CUtensorMap* m, const void* base, int n, int h, int w, int c, int ldc, int box_c, int box_w,
+                         int box_h, int box_n) {
+  const uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+  const uint64_t pitch[3] = {(uint64_t)ldc * 2, (uint64_t)ldc * 2 * w, (uint64_t)ldc * 2 * w * h};
+  const uint32_t box[4] = {(uint32_t)box_c, (uint32_t)box_w, (uint32_t)box_h, (uint32_t)box_n};
+  return make_map(m, base, 4, dims, pitch, box);
+}
+static int make_map_2d(CUtensorMap* m, const void* base, int rows, int cols, int ld, int box_cols, int box_rows) {
+  const uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
+  const uint64_t pitch[1] = {(uint64_t)ld * 2};
+  const uint32_t box[2] = {(uint32_t)box_cols, (uint32_t)box_rows};
+  return make_map(m, base, 2, dims, pitch, box);
+}
+
+// =============================================================================================
+// conv_gemm launcher
+// =============================================================================================
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+struct GemmOp {
+  // A0: NHWC view
+  const void* a0 = nullptr;
+  int n = 1, h = 1, w = 1, c0 = 0, lda0 = 0;   // c0 = channels of source 0 (K per tap); lda0 pixel pitch (elements)
+  int taps = 1;
+  // A1: optional 2-D source [M, c1]
+  const void* a1 = nullptr;
+  int c1 = 0;
+  // weights [w_rows, ldw] (row n holds K values), bias
+  const void* wgt = nullptr;
+  int ldw = 0, w_rows = 0;
+  const float* bias = nullptr;
+  const void* residual = nullptr;   // fp16 [M, cout]
+  void* out = nullptr;              // fp16 NHWC [n,h,w,cout] or fp32 [M, cout]
+  int cout = 0;
+  int relu = 0, out_f32 = 0;
+  int grp_n = 0, grp_a_koff = 0, grp_b_koff = 0, grp_b_nmod = 0;
+  int a_cols = 0;                   // logical width of an A0 row for the tensor map (>= c0; grouped mode: full row)
+};
+
+static void choose_box(int H, int W, int B, int* bw, int* bh, int* bn) {
+  if (W * H <= 64) { *bw = W; *bh = H; *bn = 128 / (W * H); if (*bn > B) *bn = B; if (*bn < 1) *bn = 1; return; }
+  double best = -1;
+  int bbw = 1, bbh = 1;
+  for (int w = 1; w <= W && w <= 128; ++w) {
+    int h = 128 / w;
+    if (h > H) h = H;
+    if (h < 1) continue;
+    const double tiles = double((W + w - 1) / w) * double((H + h - 1) / h);
+    const double eff = double(W) * H / (tiles * 128.0);
+    if (eff > best + 1e-9 || (eff > best - 1e-9 && w > bbw)) { best = eff; bbw = w; bbh = h; }
+  }
+  *bw = bbw; *bh = bbh; *bn = 1;
+}
+
+template <int BN, int BK>
+static int launch_cfg(const GemmOp& op, cudaStream_t st) {
+  using Cfg = ConvGemmCfg<BN, BK>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  ConvGemmParams p;
+  memset(&p, 0, sizeof p);
+  CUtensorMap tmA0, tmA1, tmB, tmC;
+  const long long M = (long long)op.n * op.h * op.w;
+  const bool conv = op.taps == 9;
+  int rc;
+  if (conv) {
+    choose_box(op.h, op.w, op.n, &p.box_w, &p.box_h, &p.box_n);
+    p.tiles_w = (op.w + p.box_w - 1) / p.box_w;
+    p.tiles_h = (op.h + p.box_h - 1) / p.box_h;
+    p.num_m_blks = p.tiles_w * p.tiles_h * ((op.n + p.box_n - 1) / p.box_n);
+    if ((rc = make_map_nhwc(&tmA0, op.a0, op.n, op.h, op.w, op.c0, op.lda0, BK, p.box_w, p.box_h, p.box_n))) return rc;
+    if (!op.out_f32 &&
+        (rc = make_map_nhwc(&tmC, op.out, op.n, op.h, op.w, op.cout, op.cout, Cfg::kCS, p.box_w, p.box_h, p.box_n)))
+      return rc;
+  } else {
+    if (M > 0x7fffffffLL) return fail(EMBCLIP_EINVAL, "M too large");
+    p.box_w = 128; p.box_h = 1; p.box_n = 1;
+    p.num_m_blks = int((M + 127) / 128);
+    p.tiles_w = p.num_m_blks; p.tiles_h = 1;
+    const int acols = op.a_cols ? op.a_cols : op.c0;
+    if ((rc = make_map_nhwc(&tmA0, op.a0, 1, 1, (int)M, acols, op.lda0, BK, 128, 1, 1))) return rc;
+    if (!op.out_f32 && (rc = make_map_nhwc(&tmC, op.out, 1, 1, (int)M, op.cout, op.cout, Cfg::kCS, 128, 1, 1))) return rc;
+  }
+  if (op.out_f32) tmC = tmA0;
+  if (op.a1) {
+    if ((rc = make_map_nhwc(&tmA1, op.a1, 1, 1, (int)M, op.c1, op.c1, BK, 128, 1, 1))) return rc;
+  } else {
+    tmA1 = tmA0;
+  }
+  if ((rc = make_map_2d(&tmB, op.wgt, op.w_rows, op.ldw, op.ldw, BK, BN))) return rc;
+  p.num_n_blks = op.cout / BN;
+  p.taps = op.taps;
+  p.kb_per_tap = op.c0 / BK;
+  p.kb_src0 = op.taps * p.kb_per_tap;
+  p.kb_total = p.kb_src0 + op.c1 / BK;
+  p.a0_box_bytes = uint32_t(p.box_w * p.box_h * p.box_n) * BK * 2;
+  p.relu = op.relu;
+  p.out_f32 = op.out_f32;
+  p.M = (int)M;
+  p.N = op.cout;
+  p.bias = op.bias;
+  p.residual = reinterpret_cast<const __half*>(op.residual);
+  p.ldr = op.cout;
+  p.out_f32_ptr = reinterpret_cast<float*>(op.out);
+  p.ldo = op.cout;
+  p.grp_n = op.grp_n; p.grp_a_koff = op.grp_a_koff; p.grp_b_koff = op.grp_b_koff; p.grp_b_nmod = op.grp_b_nmod;
+  const long long tiles = (long long)p.num_m_blks * p.num_n_blks;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  if (grid <= 0) return 0;
+  conv_gemm_kernel<BN, BK><<<grid, 192, Cfg::kSmemBytes, st>>>(tmA0, tmA1, tmB, tmC, p);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int pick_bn(int cout) {
+  if (cout % 128 == 0) return 128;
+  if (cout % 64 == 0) return 64;
+  if (cout % 32 == 0) return 32;
+  return 0;
+}
+
+static int launch_gemm(const GemmOp& op, cudaStream_t st, int force_bn = 0) {
+  if (op.c0 % 32 || op.c1 % 32 || op.cout % 32) return fail(EMBCLIP_EINVAL, "channels must be multiples of 32 (c0 %d c1 %d cout %d)", op.c0, op.c1, op.cout);
+  if (op.taps != 1 && op.taps != 9) return fail(EMBCLIP_EINVAL, "taps must be 1 or 9");
+  if (op.taps == 9 && (op.a1 || op.residual || op.out_f32 || op.grp_n)) return fail(EMBCLIP_EINVAL, "3x3 mode supports bias+relu only");
+  const int bk = (op.c0 % 64 == 0 && op.c1 % 64 == 0) ? 64 : 32;
+  int bn = force_bn ? force_bn : pick_bn(op.cout);
+  if (op.grp_n && op.grp_n % bn) bn = op.grp_n % 64 == 0 ? 64 : 32;
+  if (op.cout % bn) return fail(EMBCLIP_EINVAL, "cout %d not a multiple of tile N %d", op.cout, bn);
+  if (bk == 64) {
+    switch (bn) {
+      case 256: return launch_cfg<256, 64>(op, st);
+      case 128: return launch_cfg<128, 64>(op, st);
+      case 64: return launch_cfg<64, 64>(op, st);
+      case 32: return launch_cfg<32, 64>(op, st);
+    }
+  } else {
+    switch (bn) {
+      case 128: return launch_cfg<128, 32>(op, st);
+      case 64: return launch_cfg<64, 32>(op, st);
+      case 32: return launch_cfg<32, 32>(op, st);
+    }
+  }
+  return fail(EMBCLIP_EINVAL, "no kernel for tile N %d K %d", bn, bk);
+}
+
+// =============================================================================================
+// primitive-op entry points
+// =============================================================================================
+extern "C" int embclip_gemm_f16(const void* a0, const void* a1, const void* w, const float* bias, const void* residual,
+                                void* out, int M, int N, int K0, int K1, int relu, int out_f32, void* stream) {
+  if (!a0 || !w || !out || M <= 0) return fail(EMBCLIP_EINVAL, "gemm: null pointer or empty M");
+  GemmOp op;
+  op.a0 = a0; op.n = 1; op.h = 1; op.w = M; op.c0 = K0; op.lda0 = K0;
+  op.a1 = K1 ? a1 : nullptr; op.c1 = K1;
+  op.wgt = w; op.ldw = K0 + K1; op.w_rows = N;
+  op.bias = bias; op.residual = residual; op.out = out; op.cout = N; op.relu = relu; op.out_f32 = out_f32;
+  return launch_gemm(op, (cudaStream_t)stream);
+}
+
+extern "C" int embclip_gemm_grouped_f16(const void* a, int lda, const void* w, int ldw, int w_rows, const float* bias,
+                                        void* out, int M, int N, int K, int grp_n, int grp_a_koff, int grp_b_koff,
+                                        int grp_b_nmod, int relu, int out_f32, void* stream) {
+  if (!a || !w || !out || M <= 0) return fail(EMBCLIP_EINVAL, "gemm_grouped: null pointer or empty M");
+  GemmOp op;
+  op.a0 = a; op.n = 1; op.h = 1; op.w = M; op.c0 = K; op.lda0 = lda; op.a_cols = lda;
+  op.wgt = w; op.ldw = ldw; op.w_rows = w_rows;
+  op.bias = bias; op.out = out; op.cout = N; op.relu = relu; op.out_f32 = out_f32;
+  op.grp_n = grp_n; op.grp_a_koff = grp_a_koff; op.grp_b_koff = grp_b_koff; op.grp_b_nmod = grp_b_nmod;
+  return launch_gemm(op, (cudaStream_t)stream);
+}
+
+extern "C" int embclip_conv3x3_f16(const void* in, const void* w, const float* bias, void* out, int B, int H, int W,
+                                   int Cin, int Cout, int relu, void* stream) {
+  if (!in || !w || !out || B <= 0) return fail(EMBCLIP_EINVAL, "conv3x3: null pointer or empty batch");
+  GemmOp op;
+  op.a0 = in; op.n = B; op.h = H; op.w = W; op.c0 = Cin; op.lda0 = Cin; op.taps = 9;
+  op.wgt = w; op.ldw = 9 * Cin; op.w_rows = Cout;
+  op.bias = bias; op.out = out; op.cout = Cout; op.relu = relu;
+  return launch_gemm(op, (cudaStream_t)stream);
+}
+
+static int launch_avgpool2(const void* in, void* out, int B, int H, int W, int C, cudaStream_t st) {
+  if (H % 2 || W % 2 || C % 8) return fail(EMBCLIP_EINVAL, "avgpool2: H, W must be even and C a multiple of 8");
+  const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks <= 0) return 0;
+  avgpool2_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), B, H, W, C);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+extern "C" int embclip_avgpool2_f16(const void* in, void* out, int B, int H, int W, int C, void* stream) {
+  if (!in || !out) return fail(EMBCLIP_EINVAL, "avgpool2: null pointer");
+  return launch_avgpool2(in, out, B, H, W, C, (cudaStream_t)stream);
+}
+
+static int launch_stem_conv1(const float* x, const float* w, const float* b, void* y, int B, int R, int Cout, cudaStream_t st) {
+  if (R % 2) return fail(EMBCLIP_EINVAL, "stem: resolution must be even");
+  const long long total = (long long)B * (R / 2) * (R / 2);
+  const int blocks = (int)((total + 127) / 128);
+  if (blocks <= 0) return 0;
+  if (Cout == 32)
+    stem_conv1_kernel<32><<<blocks, 128, 0, st>>>(x, w, b, reinterpret_cast<__half*>(y), B, R);
+  else
+    return fail(EMBCLIP_EINVAL, "stem conv1: only Cout == 32 (width 64) is built");
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+extern "C" int embclip_stem_conv1(const float* frames, const float* w, const float* bias, void* out, int B, int R, int Cout,
+                                  void* stream) {
+  if (!frames || !w || !bias || !out) return fail(EMBCLIP_EINVAL, "stem_conv1: null pointer");
+  return launch_stem_conv1(frames, w, bias, out, B, R, Cout, (cudaStream_t)stream);
+}
+
+// =============================================================================================
+// ModifiedResNet plan
+// =============================================================================================
+namespace {
+
+struct Act {            // workspace tensor, NHWC; batch dim scales with B
+  std::string name;
+  int dtype;            // EMBCLIP_DTYPE_*
+  int h, w, c;          // per image
+  int rows_per_image;   // h*w, or tokens etc.
+};
+struct Param {
+  embclip_param_info info;
+};
+enum OpKind { K_STEM1, K_GEMM, K_POOL, K_TOKENS, K_ATTN_CORE, K_AVGHEAD, K_NCHW };
+enum Head { H_TRUNK_ALWAYS = 0, H_NCHW = 1, H_AVG = 2, H_ATTN = 4 };
+struct Op {
+  OpKind kind;
+  std::string name;
+  int head = H_TRUNK_ALWAYS;     // run only if this head is requested (0 = always)
+  int in0 = -1, in1 = -1, res = -1, out = -1;   // Act ids (-1: none; out -2/-3/-4: external outputs)
+  int wp = -1, bp = -1;          // Param ids
+  int taps = 1, c0 = 0, c1 = 0, cout = 0, relu = 0, out_f32 = 0;
+  int rows_mode = 0;             // 0: M = B*h*w of in0;  1: M = B (one row per image)
+  int lda0 = 0, a_cols = 0, ldw = 0, w_rows = 0;
+  int grp_n = 0, grp_a_koff = 0, grp_b_koff = 0, grp_b_nmod = 0;
+  int force_bn = 0;
+};
+
+}  // namespace
+
+struct embclip_rn50 {
+  embclip_rn50_cfg cfg;
+  std::vector<Act> acts;
+  std::vector<Param> params;
+  std::vector<Op> ops;
+  uint64_t blob_bytes = 0;
+  const uint8_t* blob = nullptr;
+  int embed = 0, fres = 0, tokens = 0;
+  int act_trunk_f32 = -1;
+};
+
+static int add_act(embclip_rn50* m, const std::string& name, int dtype, int h, int w, int c) {
+  m->acts.push_back(Act{name, dtype, h, w, c, h * w});
+  return (int)m->acts.size() - 1;
+}
+static int add_param(embclip_rn50* m, const std::string& name, int dtype, std::initializer_list<int64_t> shape) {
+  Param p;
+  memset(&p.info, 0, sizeof p.info);
+  snprintf(p.info.name, sizeof p.info.name, "%s", name.c_str());
+  p.info.dtype = dtype;
+  p.info.ndim = (int)shape.size();
+  uint64_t n = 1;
+  int i = 0;
+  for (int64_t s : shape) { p.info.shape[i++] = s; n *= (uint64_t)s; }
+  p.info.nbytes = n * (dtype == EMBCLIP_DTYPE_F16 ? 2 : 4);
+  p.info.offset = m->blob_bytes;
+  m->blob_bytes += (p.info.nbytes + 255) & ~uint64_t(255);
+  m->params.push_back(p);
+  return (int)m->params.size() - 1;
+}
+// conv (+folded BN) as GEMM: weights fp16 [cout, taps*c0 + c1], bias fp32 [cout]
+static int add_conv(embclip_rn50* m, const std::string& name, int in0, int in1, int res, int taps, int cout, int relu,
+                    int out_f32 = 0) {
+  const Act& a = m->acts[in0];
+  Op op;
+  op.kind = K_GEMM;
+  op.name = name;
+  op.in0 = in0; op.in1 = in1; op.res = res;
+  op.taps = taps; op.c0 = a.c; op.c1 = in1 >= 0 ? m->acts[in1].c : 0; op.cout = cout; op.relu = relu; op.out_f32 = out_f32;
+  op.lda0 = a.c;
+  op.ldw = taps * op.c0 + op.c1; op.w_rows = cout;
+  op.wp = add_param(m, name + ".w", EMBCLIP_DTYPE_F16, {cout, op.ldw});
+  op.bp = add_param(m, name + ".b", EMBCLIP_DTYPE_F32, {cout});
+  op.out = add_act(m, name, out_f32 ? EMBCLIP_DTYPE_F32 : EMBCLIP_DTYPE_F16, a.h, a.w, cout);
+  m->ops.push_back(op);
+  return op.out;
+}
+static int add_pool(embclip_rn50* m, const std::string& name, int in0) {
+  const Act a = m->acts[in0];
+  Op op;
+  op.kind = K_POOL;
+  op.name = name;
+  op.in0 = in0;
+  op.out = add_act(m, name, EMBCLIP_DTYPE_F16, a.h / 2, a.w / 2, a.c);
+  m->ops.push_back(op);
+  return op.out;
+}
+
+extern "C" int embclip_rn50_create(const embclip_rn50_cfg* cfg, embclip_rn50_t* out) {
+  if (!cfg || !out) return fail(EMBCLIP_EINVAL, "rn50_create: null argument");
+  const int width = cfg->width, R = cfg->input_resolution;
+  if (width != 64) return fail(EMBCLIP_EINVAL, "rn50_create: only width 64 (RN50 / RN101) is built, got %d", width);
+  if (R <= 0 || R % 32) return fail(EMBCLIP_EINVAL, "rn50_create: input_resolution must be a positive multiple of 32");
+  for (int i = 0; i < 4; ++i)
+    if (cfg->layers[i] < 1) return fail(EMBCLIP_EINVAL, "rn50_create: layers[%d] < 1", i);
+  const int embed = width * 32, fres = R / 32, L = fres * fres + 1;
+  if (cfg->heads <= 0 || embed % cfg->heads || embed / cfg->heads != 64)
+    return fail(EMBCLIP_EINVAL, "rn50_create: head dim must be 64 (embed %d heads %d)", embed, cfg->heads);
+  if (L > 64) return fail(EMBCLIP_EINVAL, "rn50_create: attention pool supports at most 64 tokens (got %d)", L);
+  if (cfg->output_dim % 32) return fail(EMBCLIP_EINVAL, "rn50_create: output_dim must be a multiple of 32");
+
+  embclip_rn50* m = new embclip_rn50();
+  m->cfg = *cfg;
+  m->embed = embed; m->fres = fres; m->tokens = L;
+
+  // ---- stem
+  {
+    Op op;
+    op.kind = K_STEM1;
+    op.name = "stem.conv1";
+    op.cout = width / 2;
+    op.wp = add_param(m, "stem.conv1.w", EMBCLIP_DTYPE_F32, {27, width / 2});
+    op.bp = add_param(m, "stem.conv1.b", EMBCLIP_DTYPE_F32, {width / 2});
+    op.out = add_act(m, "stem.conv1", EMBCLIP_DTYPE_F16, R / 2, R / 2, width / 2);
+    m->ops.push_back(op);
+  }
+  int t = (int)m->acts.size() - 1;
+  t = add_conv(m, "stem.conv2", t, -1, -1, 9, width / 2, 1);
+  t = add_conv(m, "stem.conv3", t, -1, -1, 9, width, 1);
+  t = add_pool(m, "stem.pool", t);
+
+  // ---- bottleneck stages
+  int inplanes = width;
+  for (int li = 0; li < 4; ++li) {
+    const int planes = width << li;
+    for (int bi = 0; bi < cfg->layers[li]; ++bi) {
+      const int stride = (bi == 0 && li > 0) ? 2 : 1;
+      const bool down = (bi == 0);   // stride > 1 or inplanes != planes*4: true exactly for the first block of a stage
+      const bool last = (li == 3 && bi == cfg->layers[3] - 1);
+      char pfx[48];
+      snprintf(pfx, sizeof pfx, "layer%d.%d", li + 1, bi);
+      const std::string P(pfx);
+      const int x = t;
+      int a = add_conv(m, P + ".conv1", x, -1, -1, 1, planes, 1);
+      int b = add_conv(m, P + ".conv2", a, -1, -1, 9, planes, 1);
+      int xp = x;
+      if (stride == 2) {
+        b = add_pool(m, P + ".pool", b);
+        xp = add_pool(m, P + ".xpool", x);
+      }
+      // conv3 (+ downsample conv fused along K when the block has one, else identity residual)
+      if (down) t = add_conv(m, P + ".conv3", b, xp, -1, 1, planes * 4, 1, last ? 1 : 0);
+      else      t = add_conv(m, P + ".conv3", b, -1, x, 1, planes * 4, 1, last ? 1 : 0);
+      inplanes = planes * 4;
+    }
+  }
+  (void)inplanes;
+  m->act_trunk_f32 = t;
+
+  // ---- heads
+  {
+    Op op;
+    op.kind = K_NCHW; op.name = "head.trunk_nchw"; op.head = H_NCHW; op.in0 = t; op.out = -2;
+    m->ops.push_back(op);
+    Op op2;
+    op2.kind = K_AVGHEAD; op2.name = "head.avgpool"; op2.head = H_AVG; op2.in0 = t; op2.out = -3;
+    m->ops.push_back(op2);
+  }
+  {
+    const int heads = cfg->heads, E = embed;
+    const int p_pos = add_param(m, "attnpool.pos", EMBCLIP_DTYPE_F32, {L, E});
+    Op tk;
+    tk.kind = K_TOKENS; tk.name = "attnpool.tokens"; tk.head = H_ATTN; tk.in0 = t; tk.wp = p_pos;
+    tk.out = add_act(m, "attnpool.tokens", EMBCLIP_DTYPE_F16, 1, L, E);
+    m->ops.push_back(tk);
+    // q = (Wq t0 + bq) / sqrt(64): A = tokens viewed as [B, L*E], K window = first E columns
+    Op q;
+    q.kind = K_GEMM; q.name = "attnpool.q"; q.head = H_ATTN; q.in0 = tk.out; q.rows_mode = 1;
+    q.c0 = E; q.lda0 = L * E; q.a_cols = E; q.cout = E; q.ldw = E; q.w_rows = E;
+    q.wp = add_param(m, "attnpool.q.w", EMBCLIP_DTYPE_F16, {E, E});
+    q.bp = add_param(m, "attnpool.q.b", EMBCLIP_DTYPE_F32, {E});
+    q.out = add_act(m, "attnpool.q", EMBCLIP_DTYPE_F16, 1, 1, E);
+    m->ops.push_back(q);
+    // qt[b, h, :] = Wk_h^T q_h : grouped GEMM, N = heads*E, group = head, K = 64
+    Op qt;
+    qt.kind = K_GEMM; qt.name = "attnpool.qk"; qt.head = H_ATTN; qt.in0 = q.out; qt.rows_mode = 1;
+    qt.c0 = 64; qt.lda0 = E; qt.a_cols = E; qt.cout = heads * E; qt.ldw = E; qt.w_rows = E;
+    qt.grp_n = E; qt.grp_a_koff = 64; qt.grp_b_koff = 64; qt.grp_b_nmod = E;
+    qt.wp = add_param(m, "attnpool.kT.w", EMBCLIP_DTYPE_F16, {E, E});   // Wk transposed: [c, (h,d)]
+    qt.out = add_act(m, "attnpool.qk", EMBCLIP_DTYPE_F16, 1, heads, E);
+    m->ops.push_back(qt);
+    Op core;
+    core.kind = K_ATTN_CORE; core.name = "attnpool.core"; core.head = H_ATTN; core.in0 = qt.out; core.in1 = tk.out;
+    core.out = add_act(m, "attnpool.xbar", EMBCLIP_DTYPE_F16, 1, heads, E);
+    m->ops.push_back(core);
+    // o[b, (h,d)] = Wv_h xbar_h + bv : grouped GEMM, N = E, group = head (64 columns), K = E at A offset h*E
+    Op v;
+    v.kind = K_GEMM; v.name = "attnpool.v"; v.head = H_ATTN; v.in0 = core.out; v.rows_mode = 1;
+    v.c0 = E; v.lda0 = heads * E; v.a_cols = heads * E; v.cout = E; v.ldw = E; v.w_rows = E;
+    v.grp_n = 64; v.grp_a_koff = E; v.grp_b_koff = 0; v.grp_b_nmod = 0;
+    v.wp = add_param(m, "attnpool.v.w", EMBCLIP_DTYPE_F16, {E, E});
+    v.bp = add_param(m, "attnpool.v.b", EMBCLIP_DTYPE_F32, {E});
+    v.out = add_act(m, "attnpool.v", EMBCLIP_DTYPE_F16, 1, 1, E);
+    m->ops.push_back(v);
+    Op c;
+    c.kind = K_GEMM; c.name = "attnpool.c"; c.head = H_ATTN; c.in0 = v.out; c.rows_mode = 1;
+    c.c0 = E; c.lda0 = E; c.cout = cfg->output_dim; c.ldw = E; c.w_rows = cfg->output_dim; c.out_f32 = 1;
+    c.wp = add_param(m, "attnpool.c.w", EMBCLIP_DTYPE_F16, {cfg->output_dim, E});
+    c.bp = add_param(m, "attnpool.c.b", EMBCLIP_DTYPE_F32, {cfg->output_dim});
+    c.out = -4;
+    m->ops.push_back(c);
+  }
+  *out = m;
+  return 0;
+}
+
+extern "C" int embclip_rn50_destroy(embclip_rn50_t h) {
+  delete h;
+  return 0;
+}
+extern "C" int embclip_rn50_num_params(embclip_rn50_t h) { return h ? (int)h->params.size() : fail(EMBCLIP_EINVAL, "null handle"); }
+extern "C" int embclip_rn50_param_info(embclip_rn50_t h, int index, embclip_param_info* out) {
+  if (!h || !out || index < 0 || index >= (int)h->params.size()) return fail(EMBCLIP_EINVAL, "param_info: bad argument");
+  *out = h->params[index].info;
+  return 0;
+}
+extern "C" uint64_t embclip_rn50_blob_bytes(embclip_rn50_t h) { return h ? h->blob_bytes : 0; }
+extern "C" int embclip_rn50_bind_weights(embclip_rn50_t h, const void* device_blob, uint64_t nbytes) {
+  if (!h || !device_blob) return fail(EMBCLIP_EINVAL, "bind_weights: null argument");
+  if (nbytes < h->blob_bytes) return fail(EMBCLIP_EINVAL, "bind_weights: blob holds %llu bytes, plan needs %llu",
+                                          (unsigned long long)nbytes, (unsigned long long)h->blob_bytes);
+  if (reinterpret_cast<uintptr_t>(device_blob) % 256) return fail(EMBCLIP_EINVAL, "bind_weights: blob must be 256-B aligned");
+  h->blob = reinterpret_cast<const uint8_t*>(device_blob);
+  return 0;
+}
+
+static uint64_t act_bytes(const Act& a, int B) {
+  const uint64_t n = (uint64_t)B * a.h * a.w * a.c * (a.dtype == EMBCLIP_DTYPE_F16 ? 2 : 4);
+  return (n + 1023) & ~uint64_t(1023);
+}
+static uint64_t act_offset(const embclip_rn50* m, int B, int id) {
+  uint64_t off = 0;
+  for (int i = 0; i < id; ++i) off += act_bytes(m->acts[i], B);
+  return off;
+}
+extern "C" uint64_t embclip_rn50_workspace_bytes(embclip_rn50_t h, int batch) {
+  if (!h || batch <= 0) return 0;
+  return act_offset(h, batch, (int)h->acts.size());
+}
+extern "C" int embclip_rn50_num_acts(embclip_rn50_t h) { return h ? (int)h->acts.size() : fail(EMBCLIP_EINVAL, "null handle"); }
+extern "C" int embclip_rn50_act_info(embclip_rn50_t h, int batch, int index, embclip_act_info* out) {
+  if (!h || !out || index < 0 || index >= (int)h->acts.size() || batch <= 0) return fail(EMBCLIP_EINVAL, "act_info: bad argument");
+  const Act& a = h->acts[index];
+  memset(out, 0, sizeof *out);
+  snprintf(out->name, sizeof out->name, "%s", a.name.c_str());
+  out->dtype = a.dtype; out->n = batch; out->h = a.h; out->w = a.w; out->c = a.c;
+  out->offset = act_offset(h, batch, index);
+  return 0;
+}
+
+static int run_op(embclip_rn50* m, const Op& op, const std::vector<uint64_t>& offs, const float* frames, int B,
+                  float* o_nchw, float* o_avg, float* o_attn, uint8_t* ws, cudaStream_t st) {
+  auto act_ptr = [&](int id) -> void* { return id >= 0 ? (void*)(ws + offs[id]) : nullptr; };
+  auto param_ptr = [&](int id) -> const void* { return id >= 0 ? (const void*)(m->blob + m->params[id].info.offset) : nullptr; };
+  const int P = m->fres * m->fres;
+  switch (op.kind) {
+    case K_STEM1:
+      return launch_stem_conv1(frames, (const float*)param_ptr(op.wp), (const float*)param_ptr(op.bp), act_ptr(op.out), B,
+                               m->cfg.input_resolution, op.cout, st);
+    case K_POOL: {
+      const Act& a = m->acts[op.in0];
+      return launch_avgpool2(act_ptr(op.in0), act_ptr(op.out), B, a.h, a.w, a.c, st);
+    }
+    case K_GEMM: {
+      const Act& a = m->acts[op.in0];
+      GemmOp g;
+      g.a0 = act_ptr(op.in0);
+      if (op.rows_mode == 1) { g.n = 1; g.h = 1; g.w = B; }
+      else if (op.taps == 9) { g.n = B; g.h = a.h; g.w = a.w; }
+      else { g.n = 1; g.h = 1; g.w = B * a.h * a.w; }
+      g.c0 = op.c0; g.lda0 = op.lda0; g.a_cols = op.a_cols; g.taps = op.taps;
+      g.a1 = act_ptr(op.in1); g.c1 = op.c1;
+      g.wgt = param_ptr(op.wp); g.ldw = op.ldw; g.w_rows = op.w_rows;
+      g.bias = (const float*)param_ptr(op.bp);
+      g.residual = act_ptr(op.res);
+      g.out = op.out == -4 ? (void*)o_attn : act_ptr(op.out);
+      g.cout = op.cout; g.relu = op.relu; g.out_f32 = op.out_f32;
+      g.grp_n = op.grp_n; g.grp_a_koff = op.grp_a_koff; g.grp_b_koff = op.grp_b_koff; g.grp_b_nmod = op.grp_b_nmod;
+      return launch_gemm(g, st, op.force_bn);
+    }
+    case K_TOKENS: {
+      dim3 grid((m->embed / 4 + 255) / 256, B);
+      attnpool_tokens_kernel<<<grid, 256, 0, st>>>((const float*)act_ptr(op.in0), (const float*)param_ptr(op.wp),
+                                                   (__half*)act_ptr(op.out), P, m->embed);
+      CUDA_TRY(cudaGetLastError());
+      return 0;
+    }
+    case K_ATTN_CORE: {
+      constexpr int HG = 8;
+      if (m->cfg.heads % HG) return fail(EMBCLIP_EINVAL, "attention pool: heads must be a multiple of %d", HG);
+      const size_t smem = (size_t)HG * m->embed * 2 + HG * 64 * 4;
+      static bool attr = false;
+      if (!attr) {
+        CUDA_TRY(cudaFuncSetAttribute(attnpool_core_kernel<HG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+      }
+      dim3 grid(B, m->cfg.heads / HG);
+      attnpool_core_kernel<HG><<<grid, 256, smem, st>>>((const __half*)act_ptr(op.in0), (const __half*)act_ptr(op.in1),
+                                                        (__half*)act_ptr(op.out), m->cfg.heads, m->tokens, m->embed);
+      CUDA_TRY(cudaGetLastError());
+      return 0;
+    }
+    case K_AVGHEAD: {
+      dim3 grid((m->embed / 4 + 255) / 256, B);
+      avg_head_kernel<<<grid, 256, 0, st>>>((const float*)act_ptr(op.in0), o_avg, P, m->embed);
+      CUDA_TRY(cudaGetLastError());
+      return 0;
+    }
+    case K_NCHW: {
+      dim3 grid(m->embed / 32, B);
+      nhwc_to_nchw_f32_kernel<<<grid, 256, (size_t)P * 33 * 4, st>>>((const float*)act_ptr(op.in0), o_nchw, P, m->embed);
+      CUDA_TRY(cudaGetLastError());
+      return 0;
+    }
+  }
+  return fail(EMBCLIP_EINVAL, "unknown op kind");
+}
+
+static int forward_impl(embclip_rn50* m, const float* frames, int B, float* o_nchw, float* o_avg, float* o_attn, void* ws,
+                        uint64_t ws_bytes, cudaStream_t st, float* op_ms, char* names, int max_ops) {
+  if (!m || !frames || !ws || B <= 0) return fail(EMBCLIP_EINVAL, "forward: null argument or empty batch");
+  if (!m->blob) return fail(EMBCLIP_ESTATE, "forward: weights not bound (call embclip_rn50_bind_weights first)");
+  const uint64_t need = embclip_rn50_workspace_bytes(m, B);
+  if (ws_bytes < need) return fail(EMBCLIP_ENOSPC, "forward: workspace %llu B < required %llu B", (unsigned long long)ws_bytes, (unsigned long long)need);
+  if (reinterpret_cast<uintptr_t>(ws) % 1024) return fail(EMBCLIP_EINVAL, "forward: workspace must be 1024-B aligned");
+  std::vector<uint64_t> offs(m->acts.size());
+  uint64_t off = 0;
+  for (size_t i = 0; i < m->acts.size(); ++i) { offs[i] = off; off += act_bytes(m->acts[i], B); }
+  const int want = (o_nchw ? H_NCHW : 0) | (o_avg ? H_AVG : 0) | (o_attn ? H_ATTN : 0);
+  std::vector<cudaEvent_t> ev;
+  int nrun = 0;
+  for (const Op& op : m->ops) {
+    if (op.head && !(op.head & want)) continue;
+    if (op_ms) {
+      cudaEvent_t e;
+      CUDA_TRY(cudaEventCreate(&e));
+      CUDA_TRY(cudaEventRecord(e, st));
+      ev.push_back(e);
+      if (names && nrun < max_ops) snprintf(names + (size_t)nrun * 64, 64, "%s", op.name.c_str());
+    }
+    const int rc = run_op(m, op, offs, frames, B, o_nchw, o_avg, o_attn, reinterpret_cast<uint8_t*>(ws), st);
+    if (rc) return rc;
+    ++nrun;
+  }
+  if (op_ms) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaEventRecord(e, st));
+    ev.push_back(e);
+    CUDA_TRY(cudaEventSynchronize(e));
+    for (int i = 0; i < nrun && i < max_ops; ++i) CUDA_TRY(cudaEventElapsedTime(&op_ms[i], ev[i], ev[i + 1]));
+    for (cudaEvent_t x : ev) cudaEventDestroy(x);
+  }
+  return nrun;
+}
+
+extern "C" int embclip_rn50_forward(embclip_rn50_t h, const float* frames_nhwc, int batch, float* out_trunk_nchw,
+                                    float* out_avgpool, float* out_attnpool, void* workspace, uint64_t workspace_bytes,
+                                    void* stream) {
+  const int rc = forward_impl(h, frames_nhwc, batch, out_trunk_nchw, out_avgpool, out_attnpool, workspace, workspace_bytes,
+                              (cudaStream_t)stream, nullptr, nullptr, 0);
+  return rc < 0 ? rc : 0;
+}
+extern "C" int embclip_rn50_profile(embclip_rn50_t h, const float* frames_nhwc, int batch, float* out_trunk_nchw,
+                                    float* out_avgpool, float* out_attnpool, void* workspace, uint64_t workspace_bytes,
+                                    void* stream, float* op_ms, char* names, int max_ops) {
+  if (!op_ms || max_ops <= 0) return fail(EMBCLIP_EINVAL, "profile: need op_ms buffer");
+  return forward_impl(h, frames_nhwc, batch, out_trunk_nchw, out_avgpool, out_attnpool, workspace, workspace_bytes,
+                      (cudaStream_t)stream, op_ms, names, max_ops);
+}
+extern "C" int embclip_rn50_launches_per_forward(embclip_rn50_t h, int want_trunk, int want_avgpool, int want_attnpool) {
+  if (!h) return fail(EMBCLIP_EINVAL, "null handle");
+  const int want = (want_trunk ? H_NCHW : 0) | (want_avgpool ? H_AVG : 0) | (want_attnpool ? H_ATTN : 0);
+  int n = 0;
+  for (const Op& op : h->ops)
+    if (!op.head || (op.head & want)) ++n;
+  return n;
+}

@@ -1,0 +1,151 @@
+"""Host-side driver of the CLIP-RN50 encoder plan in libembclip_b200.so.
+
+``ClipRN50Encoder`` is what the plugin surface (plugin.py) and bench.py call: it owns the library
+handle, the packed weight blob and the workspace (torch CUDA allocations -- torch is plumbing for
+device memory and streams only; every FLOP runs in the library's kernels).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .packing import infer_rn_cfg, pack_blob
+
+
+class ClipRN50Encoder:
+    """Frozen CLIP ModifiedResNet forward: frames fp32 NHWC [B,R,R,3] (already mean/std normalised) ->
+    'trunk' fp32 [B,2048,7,7] | 'avgpool' fp32 [B,2048] | 'attnpool' fp32 [B,1024].
+
+    Replaces ``clip_model.visual`` as used at
+    primitive_probing/generate_data/thor_image_features.py:57-67,109-113."""
+
+    HEADS = ("trunk", "avgpool", "attnpool")
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device: torch.device | str = "cuda:0"):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("embclip_b200 has no CPU path: ClipRN50Encoder needs a CUDA (sm_100a) device")
+        cfg = infer_rn_cfg(state_dict)
+        self.cfg = cfg
+        c = _lib.RN50Cfg()
+        c.layers[:] = cfg["layers"]
+        c.width, c.heads, c.output_dim, c.input_resolution = cfg["width"], cfg["heads"], cfg["output_dim"], cfg["input_resolution"]
+        self._h = C.c_void_p()
+        _lib.check(self.lib.embclip_rn50_create(C.byref(c), C.byref(self._h)))
+        self.param_infos = self._param_infos()
+        blob = pack_blob(state_dict, self.param_infos)
+        with torch.cuda.device(self.device):
+            self._blob = blob.to(self.device)
+            _lib.check(self.lib.embclip_rn50_bind_weights(self._h, self._blob.data_ptr(), self._blob.numel()))
+        self._ws: Optional[torch.Tensor] = None
+        self.embed = cfg["width"] * 32
+        self.fres = cfg["input_resolution"] // 32
+
+    # ------------------------------------------------------------------ introspection
+    def _param_infos(self) -> List[Tuple[str, str, tuple, int, int]]:
+        n = _lib.check(self.lib.embclip_rn50_num_params(self._h))
+        out = []
+        for i in range(n):
+            pi = _lib.ParamInfo()
+            _lib.check(self.lib.embclip_rn50_param_info(self._h, i, C.byref(pi)))
+            out.append((pi.name.decode(), "f16" if pi.dtype == _lib.DTYPE_F16 else "f32",
+                        tuple(pi.shape[:pi.ndim]), int(pi.offset), int(pi.nbytes)))
+        return out
+
+    def workspace_bytes(self, batch: int) -> int:
+        return int(self.lib.embclip_rn50_workspace_bytes(self._h, batch))
+
+    def _workspace(self, batch: int) -> torch.Tensor:
+        need = self.workspace_bytes(batch)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def launches_per_forward(self, want: Iterable[str]) -> int:
+        w = set(want)
+        return _lib.check(self.lib.embclip_rn50_launches_per_forward(self._h, "trunk" in w, "avgpool" in w, "attnpool" in w))
+
+    def activations(self, batch: int) -> Dict[str, torch.Tensor]:
+        """Views of the intermediate NHWC activations of the LAST forward at this batch size (test hook)."""
+        ws = self._workspace(batch)
+        n = _lib.check(self.lib.embclip_rn50_num_acts(self._h))
+        out = {}
+        for i in range(n):
+            ai = _lib.ActInfo()
+            _lib.check(self.lib.embclip_rn50_act_info(self._h, batch, i, C.byref(ai)))
+            dt = torch.float16 if ai.dtype == _lib.DTYPE_F16 else torch.float32
+            numel = ai.n * ai.h * ai.w * ai.c
+            nbytes = numel * (2 if dt == torch.float16 else 4)
+            out[ai.name.decode()] = ws[ai.offset:ai.offset + nbytes].view(dt).view(ai.n, ai.h, ai.w, ai.c)
+        return out
+
+    # ------------------------------------------------------------------ compute
+    def _outputs(self, batch: int, want: Iterable[str]) -> Dict[str, torch.Tensor]:
+        outs = {}
+        for k in want:
+            if k == "trunk":
+                outs[k] = torch.empty(batch, self.embed, self.fres, self.fres, dtype=torch.float32, device=self.device)
+            elif k == "avgpool":
+                outs[k] = torch.empty(batch, self.embed, dtype=torch.float32, device=self.device)
+            elif k == "attnpool":
+                outs[k] = torch.empty(batch, self.cfg["output_dim"], dtype=torch.float32, device=self.device)
+            else:
+                raise ValueError(f"unknown head '{k}' (choose from {self.HEADS})")
+        return outs
+
+    def _check_frames(self, frames: torch.Tensor) -> torch.Tensor:
+        R = self.cfg["input_resolution"]
+        if frames.device != self.device:
+            raise ValueError(f"frames on {frames.device}, encoder on {self.device}")
+        if frames.dtype != torch.float32 or frames.dim() != 4 or tuple(frames.shape[1:]) != (R, R, 3):
+            raise ValueError(f"frames must be float32 NHWC [B,{R},{R},3], got {frames.dtype} {tuple(frames.shape)}")
+        return frames.contiguous()
+
+    def forward(self, frames: torch.Tensor, want: Iterable[str] = ("trunk",),
+                out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        want = tuple(want)
+        frames = self._check_frames(frames)
+        B = frames.shape[0]
+        if B == 0:
+            return self._outputs(0, want)
+        outs = out if out is not None else self._outputs(B, want)
+        ws = self._workspace(B)
+        ptr = lambda k: outs[k].data_ptr() if k in outs else None
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(self.lib.embclip_rn50_forward(self._h, frames.data_ptr(), B, ptr("trunk"), ptr("avgpool"),
+                                                     ptr("attnpool"), ws.data_ptr(), ws.numel(), stream))
+        return outs
+
+    __call__ = forward
+
+    def profile(self, frames: torch.Tensor, want: Iterable[str] = ("trunk",)) -> List[Tuple[str, float]]:
+        """Per-op device time (ms) of one forward, CUDA events on the current stream."""
+        want = tuple(want)
+        frames = self._check_frames(frames)
+        B = frames.shape[0]
+        outs = self._outputs(B, want)
+        ws = self._workspace(B)
+        max_ops = 256
+        ms = (C.c_float * max_ops)()
+        names = C.create_string_buffer(64 * max_ops)
+        ptr = lambda k: outs[k].data_ptr() if k in outs else None
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            n = _lib.check(self.lib.embclip_rn50_profile(self._h, frames.data_ptr(), B, ptr("trunk"), ptr("avgpool"),
+                                                         ptr("attnpool"), ws.data_ptr(), ws.numel(), stream,
+                                                         C.cast(ms, C.c_void_p), C.cast(names, C.c_void_p), max_ops))
+        return [(names.raw[i * 64:(i + 1) * 64].split(b"\0")[0].decode(), float(ms[i])) for i in range(n)]
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self.lib.embclip_rn50_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

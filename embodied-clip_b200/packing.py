@@ -1,0 +1,125 @@
+"""Host-side weight preparation for the ModifiedResNet plan in libembclip_b200.so.
+
+Takes a CLIP state dict with the official key names (openai/CLIP ``clip/model.py``:
+``visual.conv1.weight``, ``visual.bn1.running_mean``, ``visual.layer1.0.downsample.0.weight``,
+``visual.attnpool.q_proj.weight`` ...; the ``visual.`` prefix is optional) and produces the packed
+blob the library asks for through ``embclip_rn50_param_info``:
+
+* BatchNorm (eval mode, eps 1e-5 -- the state the reference freezes it in,
+  primitive_probing/generate_data/thor_image_features.py:26-33) is folded into the preceding conv in
+  fp32 *before* the cast to fp16:  w' = w * gamma / sqrt(var + eps),  b' = beta - mean * gamma / sqrt(var + eps).
+* 3x3 weights go tap-major: [Cout, (kh, kw, Cin)] -- the K order the implicit-GEMM producer walks.
+* A bottleneck's downsample conv is concatenated to its conv3 along K ([W3 | Wd], bias b3 + bd): one
+  GEMM over [avgpool(relu(bn2(conv2))) ; avgpool(x)] replaces conv3 + downsample + add.
+* AttentionPool2d: q is pre-scaled by head_dim**-0.5 (= 1/8, exact in fp16); Wk is stored transposed
+  ([c, (head, d)]) for the folded-query contraction; bk is dropped (it shifts all keys of a head by the
+  same amount, which softmax ignores).
+
+Pure torch-on-CPU code: no GPU needed, covered by tests/test_packing.py.
+"""
+from __future__ import annotations
+
+import re
+from typing import Dict, Tuple
+
+import torch
+
+BN_EPS = 1e-5
+
+
+def strip_visual_prefix(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    if any(k.startswith("visual.") for k in sd):
+        return {k[len("visual."):]: v for k, v in sd.items() if k.startswith("visual.")}
+    return dict(sd)
+
+
+def infer_rn_cfg(sd: Dict[str, torch.Tensor]) -> dict:
+    """Mirror of clip/model.py build_model's shape inference for the ModifiedResNet branch."""
+    sd = strip_visual_prefix(sd)
+    layers = []
+    for b in (1, 2, 3, 4):
+        idx = {int(m.group(1)) for k in sd for m in [re.match(rf"layer{b}\.(\d+)\.", k)] if m}
+        layers.append(len(idx))
+    width = sd["layer1.0.conv1.weight"].shape[0]
+    grid = round((sd["attnpool.positional_embedding"].shape[0] - 1) ** 0.5)
+    return dict(layers=tuple(layers), width=int(width), heads=int(width * 32 // 64),
+                output_dim=int(sd["attnpool.c_proj.weight"].shape[0]), input_resolution=int(grid * 32))
+
+
+def fold_bn(sd: Dict[str, torch.Tensor], conv: str, bn: str) -> Tuple[torch.Tensor, torch.Tensor]:
+    """-> (weight [Cout,Cin,kh,kw] fp32 with BN scale folded in, bias [Cout] fp32)."""
+    w = sd[conv + ".weight"].float()
+    scale = sd[bn + ".weight"].float() / torch.sqrt(sd[bn + ".running_var"].float() + BN_EPS)
+    bias = sd[bn + ".bias"].float() - sd[bn + ".running_mean"].float() * scale
+    return w * scale[:, None, None, None], bias
+
+
+def _kmajor(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, kh, kw] -> [Cout, kh*kw*Cin] (tap-major, channel fastest)."""
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+
+
+def packed_tensors(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """name (as in embclip_param_info) -> CPU tensor in its final dtype / layout."""
+    sd = strip_visual_prefix(sd)
+    out: Dict[str, torch.Tensor] = {}
+
+    w, b = fold_bn(sd, "conv1", "bn1")
+    out["stem.conv1.w"] = w.permute(2, 3, 1, 0).reshape(27, -1).contiguous()         # [(kh,kw,ci), co] fp32
+    out["stem.conv1.b"] = b
+    for i in (2, 3):
+        w, b = fold_bn(sd, f"conv{i}", f"bn{i}")
+        out[f"stem.conv{i}.w"] = _kmajor(w).half()
+        out[f"stem.conv{i}.b"] = b
+
+    blocks = sorted({(int(m.group(1)), int(m.group(2))) for k in sd
+                     for m in [re.match(r"layer(\d)\.(\d+)\.conv1\.weight", k)] if m})
+    for (li, bi) in blocks:
+        p = f"layer{li}.{bi}"
+        w, b = fold_bn(sd, p + ".conv1", p + ".bn1")
+        out[p + ".conv1.w"] = _kmajor(w).half()
+        out[p + ".conv1.b"] = b
+        w, b = fold_bn(sd, p + ".conv2", p + ".bn2")
+        out[p + ".conv2.w"] = _kmajor(w).half()
+        out[p + ".conv2.b"] = b
+        w3, b3 = fold_bn(sd, p + ".conv3", p + ".bn3")
+        w3 = _kmajor(w3)
+        if p + ".downsample.0.weight" in sd:
+            wd, bd = fold_bn(sd, p + ".downsample.0", p + ".downsample.1")
+            w3 = torch.cat([w3, _kmajor(wd)], dim=1)
+            b3 = b3 + bd
+        out[p + ".conv3.w"] = w3.half()
+        out[p + ".conv3.b"] = b3
+
+    head_dim = 64
+    s = head_dim ** -0.5
+    out["attnpool.pos"] = sd["attnpool.positional_embedding"].float().contiguous()
+    out["attnpool.q.w"] = (sd["attnpool.q_proj.weight"].float() * s).half()
+    out["attnpool.q.b"] = sd["attnpool.q_proj.bias"].float() * s
+    out["attnpool.kT.w"] = sd["attnpool.k_proj.weight"].float().t().contiguous().half()
+    out["attnpool.v.w"] = sd["attnpool.v_proj.weight"].float().half()
+    out["attnpool.v.b"] = sd["attnpool.v_proj.bias"].float()
+    out["attnpool.c.w"] = sd["attnpool.c_proj.weight"].float().half()
+    out["attnpool.c.b"] = sd["attnpool.c_proj.bias"].float()
+    return out
+
+
+def pack_blob(sd: Dict[str, torch.Tensor], param_infos) -> torch.Tensor:
+    """param_infos: iterable of (name, dtype('f16'|'f32'), shape tuple, offset, nbytes) as reported by the
+    library.  Returns a uint8 CPU tensor holding every packed tensor at its offset."""
+    tensors = packed_tensors(sd)
+    infos = list(param_infos)
+    total = max(off + ((nb + 255) // 256) * 256 for _, _, _, off, nb in infos)
+    blob = torch.zeros(total, dtype=torch.uint8)
+    for name, dtype, shape, off, nbytes in infos:
+        if name not in tensors:
+            raise KeyError(f"packing: library asks for '{name}', which the state dict does not provide")
+        t = tensors[name]
+        want = torch.float16 if dtype == "f16" else torch.float32
+        if t.dtype != want or tuple(t.shape) != tuple(shape):
+            raise ValueError(f"packing: '{name}' is {t.dtype}{tuple(t.shape)}, library expects {want}{tuple(shape)}")
+        raw = t.contiguous().view(torch.uint8).reshape(-1)
+        if raw.numel() != nbytes:
+            raise ValueError(f"packing: '{name}' has {raw.numel()} bytes, library expects {nbytes}")
+        blob[off:off + nbytes] = raw
+    return blob

@@ -1,0 +1,129 @@
+/* embclip_b200 -- C ABI of the B200-native EmbCLIP hot path (libembclip_b200.so).
+ *
+ * The reference (allenai/embodied-clip) has NO native / FFI boundary: its hot path is Python calling
+ * PyTorch modules of two pinned dependencies (openai/CLIP @ 40f5484c, allenai/allenact @ v0.5.0; pins at
+ * /root/reference/primitive_probing/environment.yml:22 and readme_files/baselines_robothor_objectnav.md:6).
+ * Each entry point below therefore cites the *Python call* it replaces; the ctypes binding a maintainer
+ * adds on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions: every call returns 0 on success, a negative EMBCLIP_E* code otherwise (no C++ exception
+ * crosses the ABI; `embclip_last_error()` gives the message of the calling thread's last failure).  The
+ * CALLER owns every tensor and the workspace (device memory, e.g. torch allocations); the library owns only
+ * the handle, its layer table and TMA descriptors.  All work is enqueued on the `cudaStream_t` passed as
+ * `void* stream`; no call synchronises the device or allocates device memory.  A handle is used from one
+ * host thread at a time.
+ */
+#ifndef EMBCLIP_B200_H_
+#define EMBCLIP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMBCLIP_OK 0
+#define EMBCLIP_EINVAL (-1)   /* bad argument / unsupported shape            */
+#define EMBCLIP_ECUDA (-2)    /* a CUDA runtime / driver call failed         */
+#define EMBCLIP_ESTATE (-3)   /* call order violated (e.g. weights not bound) */
+#define EMBCLIP_ENOSPC (-4)   /* workspace too small                         */
+
+#define EMBCLIP_DTYPE_F16 0
+#define EMBCLIP_DTYPE_F32 1
+
+const char* embclip_last_error(void);
+/* ABI version of this library (bumped on any signature change). */
+int embclip_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * CLIP ModifiedResNet encoder (RN50): replaces `clip_model(clip_input)` + `clip_pool(...)` +
+ * `clip_avgpool(...)` at primitive_probing/generate_data/thor_image_features.py:109,112,113
+ * (reachable_image_features.py:88,91,92) and `ClipResNetEmbedder.forward` of
+ * allenact_plugins/clip_plugin/clip_preprocessors.py.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct embclip_rn50* embclip_rn50_t;
+
+typedef struct {
+  int32_t layers[4];         /* (3,4,6,3) for RN50                         */
+  int32_t width;             /* 64                                         */
+  int32_t heads;             /* 32 attention-pool heads                    */
+  int32_t output_dim;        /* 1024                                       */
+  int32_t input_resolution;  /* 224                                        */
+} embclip_rn50_cfg;
+
+/* One packed parameter of the device weight blob.  Python (embclip_b200/packing.py) folds BatchNorm into
+ * the conv weights in fp32, reorders to the layouts named here and writes each tensor at `offset`. */
+typedef struct {
+  char name[64];     /* e.g. "layer1.0.conv2.w"  */
+  int32_t dtype;     /* EMBCLIP_DTYPE_*          */
+  int32_t ndim;
+  int64_t shape[4];
+  uint64_t offset;   /* bytes from blob start, 256-B aligned */
+  uint64_t nbytes;
+} embclip_param_info;
+
+/* Build the layer table.  Needs no GPU. */
+int embclip_rn50_create(const embclip_rn50_cfg* cfg, embclip_rn50_t* out);
+int embclip_rn50_destroy(embclip_rn50_t h);
+int embclip_rn50_num_params(embclip_rn50_t h);
+int embclip_rn50_param_info(embclip_rn50_t h, int index, embclip_param_info* out);
+uint64_t embclip_rn50_blob_bytes(embclip_rn50_t h);
+/* Point the handle at a caller-owned device blob laid out per embclip_rn50_param_info. */
+int embclip_rn50_bind_weights(embclip_rn50_t h, const void* device_blob, uint64_t nbytes);
+/* Bytes of caller-provided scratch a forward at this batch size needs. */
+uint64_t embclip_rn50_workspace_bytes(embclip_rn50_t h, int batch);
+/* frames: fp32 NHWC [batch, R, R, 3], already mean/std normalised (what the AllenAct RGB sensor hands to
+ * ClipResNetPreprocessor.process).  Any output pointer may be NULL (that head is skipped):
+ *   out_trunk_nchw  fp32 [batch, 32*width, R/32, R/32]   (pool=False / 'clip_conv')
+ *   out_avgpool     fp32 [batch, 32*width]               (pool=True  / 'clip_avgpool')
+ *   out_attnpool    fp32 [batch, output_dim]             ('clip_attnpool', AttentionPool2d row 0) */
+int embclip_rn50_forward(embclip_rn50_t h, const float* frames_nhwc, int batch, float* out_trunk_nchw,
+                         float* out_avgpool, float* out_attnpool, void* workspace, uint64_t workspace_bytes,
+                         void* stream);
+/* Introspection for layer-by-layer parity tests: intermediate activations live in the workspace. */
+typedef struct {
+  char name[64];
+  int32_t dtype;
+  int32_t n, h, w, c;   /* NHWC */
+  uint64_t offset;      /* bytes from workspace start */
+} embclip_act_info;
+int embclip_rn50_num_acts(embclip_rn50_t h);
+int embclip_rn50_act_info(embclip_rn50_t h, int batch, int index, embclip_act_info* out);
+/* Per-op device timing of one forward (CUDA events on `stream`; synchronises). op_ms[i] <- milliseconds,
+ * names[i*64..] <- op name.  Returns the number of ops, or a negative error. */
+int embclip_rn50_profile(embclip_rn50_t h, const float* frames_nhwc, int batch, float* out_trunk_nchw,
+                         float* out_avgpool, float* out_attnpool, void* workspace, uint64_t workspace_bytes,
+                         void* stream, float* op_ms, char* names, int max_ops);
+/* How many kernels one forward launches (for bench.py's gpu_launches). */
+int embclip_rn50_launches_per_forward(embclip_rn50_t h, int want_trunk, int want_avgpool, int want_attnpool);
+
+/* ------------------------------------------------------------------------------------------------
+ * Primitive ops (the kernels the plans above are made of), exposed for unit tests and reuse.
+ * All tensors fp16 unless noted, device pointers, row-major.
+ * ------------------------------------------------------------------------------------------------ */
+/* out[M,N] = act( [A0 | A1][M, K0+K1] . W[N, K0+K1]^T + bias[N] + residual[M,N] ).  A1/bias/residual may
+ * be NULL (K1 = 0).  out_f32 != 0 writes fp32.  K0, K1 multiples of 32; N multiple of 32.
+ * Replaces nn.Conv2d(k=1) / nn.Linear of clip/model.py and allenact basic_models. */
+int embclip_gemm_f16(const void* a0, const void* a1, const void* w, const float* bias, const void* residual,
+                     void* out, int M, int N, int K0, int K1, int relu, int out_f32, void* stream);
+/* Grouped variant: N-group g = n / grp_n reads A columns [g*grp_a_koff, +K0) and W columns
+ * [g*grp_b_koff, +K0), W rows n % grp_b_nmod when grp_b_nmod != 0 (per-head contractions of AttentionPool2d).
+ * lda / ldw = row pitches (elements) of A and W. */
+int embclip_gemm_grouped_f16(const void* a, int lda, const void* w, int ldw, int w_rows, const float* bias,
+                             void* out, int M, int N, int K, int grp_n, int grp_a_koff, int grp_b_koff,
+                             int grp_b_nmod, int relu, int out_f32, void* stream);
+/* 3x3 / pad 1 / stride 1 conv, NHWC: in [B,H,W,Cin], w [Cout, 9*Cin] (tap-major: kh, kw, cin), out [B,H,W,Cout].
+ * Replaces nn.Conv2d(k=3, padding=1) + folded BatchNorm + ReLU of clip/model.py Bottleneck / stem. */
+int embclip_conv3x3_f16(const void* in, const void* w, const float* bias, void* out, int B, int H, int W,
+                        int Cin, int Cout, int relu, void* stream);
+/* 2x2 average pool, NHWC fp16 (nn.AvgPool2d(2) of clip/model.py). */
+int embclip_avgpool2_f16(const void* in, void* out, int B, int H, int W, int C, void* stream);
+/* Stem conv1: fp32 NHWC [B,R,R,3] -> fp16 NHWC [B,R/2,R/2,Cout]; w fp32 [27, Cout] (kh,kw,cin major), bias fp32. */
+int embclip_stem_conv1(const float* frames, const float* w, const float* bias, void* out, int B, int R, int Cout,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMBCLIP_B200_H_ */

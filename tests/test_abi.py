@@ -1,0 +1,83 @@
+"""The C-ABI library builds for sm_100a, loads without a GPU, and exports every symbol include/embclip_b200.h
+declares (no compute calls here).  Host-side plan queries that need no device are exercised too."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "embclip_b200.h")
+
+
+def header_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(embclip_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_what_python_binds(built_lib):
+    from embclip_b200 import _lib
+    assert set(header_symbols()) == set(_lib.SIGNATURES), "include/embclip_b200.h and _lib.SIGNATURES disagree"
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = C.CDLL(built_lib)
+    for s in header_symbols():
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+    from embclip_b200 import _lib
+    assert _lib.load().embclip_abi_version() == 1
+
+
+def test_sass_is_blackwell_native(built_lib):
+    sass = subprocess.run(["cuobjdump", "-sass", built_lib], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM"):      # tcgen05.mma, TMA load/store, tcgen05.ld
+        assert mnemonic in sass, f"{mnemonic} missing from SASS"
+    assert "HMMA." not in sass.replace("UTCHMMA", ""), "legacy mma.sync path present"
+    assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", built_lib], capture_output=True, text=True).stdout
+
+
+def test_plan_queries_without_gpu(built_lib):
+    from embclip_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.RN50Cfg()
+    cfg.layers[:] = (3, 4, 6, 3)
+    cfg.width, cfg.heads, cfg.output_dim, cfg.input_resolution = 64, 32, 1024, 224
+    h = C.c_void_p()
+    assert lib.embclip_rn50_create(C.byref(cfg), C.byref(h)) == 0
+    n = lib.embclip_rn50_num_params(h)
+    names, end = [], 0
+    for i in range(n):
+        pi = _lib.ParamInfo()
+        assert lib.embclip_rn50_param_info(h, i, C.byref(pi)) == 0
+        assert pi.offset % 256 == 0 and pi.offset >= end
+        end = pi.offset + pi.nbytes
+        names.append(pi.name.decode())
+    assert lib.embclip_rn50_blob_bytes(h) >= end
+    # 1 stem conv1 + 2 stem convs + 16 blocks x 3 convs, each (w, b); attnpool: pos, q(w,b), kT, v(w,b), c(w,b)
+    assert n == 2 * (3 + 48) + 8
+    assert "layer4.2.conv3.w" in names and "attnpool.kT.w" in names
+    # workspace scales linearly with batch (up to 1 KiB alignment per tensor)
+    w1, w8 = lib.embclip_rn50_workspace_bytes(h, 1), lib.embclip_rn50_workspace_bytes(h, 8)
+    assert 0 < w1 and 7.9 * w1 < w8 <= 8 * w1
+    # 70 trunk launches: stem 3 + pool, 16 x 3 convs, 3 x 2 pools, + heads
+    assert lib.embclip_rn50_launches_per_forward(h, 0, 0, 0) == 4 + 48 + 6
+    assert lib.embclip_rn50_launches_per_forward(h, 1, 1, 1) == 4 + 48 + 6 + 2 + 6
+    # error paths: state and argument checks happen before any CUDA call
+    assert lib.embclip_rn50_forward(h, None, 1, None, None, None, None, 0, None) == -1
+    bad = _lib.RN50Cfg()
+    bad.layers[:] = (3, 4, 6, 3)
+    bad.width, bad.heads, bad.output_dim, bad.input_resolution = 96, 48, 768, 384
+    h2 = C.c_void_p()
+    assert lib.embclip_rn50_create(C.byref(bad), C.byref(h2)) == -1
+    assert b"width" in lib.embclip_last_error()
+    assert lib.embclip_rn50_destroy(h) == 0
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from embclip_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        _lib.load()

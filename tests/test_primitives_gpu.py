@@ -1,0 +1,177 @@
+"""GPU parity of the primitive ops of libembclip_b200.so (called through the C ABI) against plain fp32
+PyTorch on the same fp16-rounded operands.  Tolerance: the kernels accumulate in fp32 and round the result
+to fp16 once, so |err| <= 2^-11 * |ref| + accumulation-order noise; we allow rtol 2e-3 / atol 2e-3*scale."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib(built_lib):
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    from embclip_b200 import _lib
+    return _lib.load()
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(lib, rc):
+    assert rc == 0, lib.embclip_last_error().decode()
+
+
+def _close(out, ref, what):
+    scale = ref.abs().max().item() + 1e-6
+    err = (out.float() - ref).abs()
+    tol = 2e-3 * ref.abs() + 2e-3 * scale
+    bad = err > tol
+    if bad.any():
+        idx = bad.nonzero()
+        rows = idx[:, 0].unique()[:16].tolist()
+        cols = idx[:, -1].unique()[:16].tolist()
+        pytest.fail(f"{what}: {int(bad.sum())}/{bad.numel()} elements off, max err {err.max().item():.4g} "
+                    f"(scale {scale:.3g}); first bad rows {rows} cols {cols}")
+
+
+def _gemm_case(lib, M, N, K0, K1=0, bias=True, res=False, relu=False, out_f32=False, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    a0 = rn(M, K0).half()
+    a1 = rn(M, K1).half() if K1 else None
+    w = (rn(N, K0 + K1) * (K0 + K1) ** -0.5).half()
+    b = rn(N) if bias else None
+    r = rn(M, N).half() if res else None
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32 if out_f32 else torch.float16)
+    _check(lib, lib.embclip_gemm_f16(_ptr(a0), _ptr(a1), _ptr(w), _ptr(b), _ptr(r), _ptr(out), M, N, K0, K1,
+                                     int(relu), int(out_f32), _stream()))
+    torch.cuda.synchronize()
+    a = a0.float() if a1 is None else torch.cat([a0.float(), a1.float()], 1)
+    ref = a @ w.float().t()
+    if bias:
+        ref = ref + b
+    if res:
+        ref = ref + r.float()
+    if relu:
+        ref = ref.relu()
+    _close(out, ref, f"gemm M{M} N{N} K{K0}+{K1} bias{bias} res{res} relu{relu} f32{out_f32}")
+
+
+@pytest.mark.parametrize("M,N,K", [
+    (128, 128, 64),        # one tile, one k-block
+    (128, 128, 256),       # pipeline wrap (4 k-blocks)
+    (256, 128, 1024),      # 16 k-blocks > stages, 2 tiles
+    (1000, 256, 512),      # partial last M tile, 2 N tiles
+    (128 * 150, 64, 64),   # more tiles than SMs: persistent loop + accumulator double-buffering
+    (3136, 64, 256),       # layer1 conv1 shape (one frame)
+    (392, 512, 128),       # layer2 conv3 shape, BN 128
+    (98, 2048, 512),       # layer4 conv3 shape: M < 128
+    (5, 1024, 2048),       # attnpool c_proj at tiny batch
+])
+def test_gemm_plain(lib, M, N, K):
+    _gemm_case(lib, M, N, K)
+
+
+@pytest.mark.parametrize("N,K", [(32, 32), (64, 32), (32, 64), (64, 64), (128, 64), (128, 96), (64, 288)])
+def test_gemm_tile_variants(lib, N, K):
+    """every (BN, BK) instantiation incl. the 64-B-swizzle BK=32 path"""
+    _gemm_case(lib, 777, N, K, relu=True)
+
+
+def test_gemm_epilogues(lib):
+    _gemm_case(lib, 500, 256, 128, res=True, relu=True)
+    _gemm_case(lib, 500, 256, 128, bias=False)
+    _gemm_case(lib, 500, 256, 128, out_f32=True, relu=True)
+    _gemm_case(lib, 300, 128, 64, out_f32=True, res=True)
+
+
+def test_gemm_k_concat(lib):
+    """[W3 | Wd] . [t ; x]: the fused conv3 + downsample of a bottleneck's first block"""
+    _gemm_case(lib, 784, 512, 128, K1=256, relu=True)
+    _gemm_case(lib, 3136, 256, 64, K1=64, relu=True)
+    _gemm_case(lib, 98, 2048, 512, K1=1024, relu=True, out_f32=True)
+
+
+def test_gemm_grouped(lib):
+    """per-head contractions of AttentionPool2d"""
+    torch.manual_seed(1)
+    B, heads, E, hd = 6, 32, 2048, 64
+    q = torch.randn(B, E, device="cuda").half()
+    wkT = (torch.randn(E, E, device="cuda") * E ** -0.5).half()          # [c, (h,d)]
+    out = torch.full((B, heads * E), float("nan"), device="cuda", dtype=torch.float16)
+    _check(lib, lib.embclip_gemm_grouped_f16(_ptr(q), E, _ptr(wkT), E, E, None, _ptr(out), B, heads * E, hd,
+                                             E, hd, hd, E, 0, 0, _stream()))
+    torch.cuda.synchronize()
+    ref = torch.einsum("bhd,chd->bhc", q.float().view(B, heads, hd), wkT.float().view(E, heads, hd)).reshape(B, heads * E)
+    _close(out, ref, "grouped qk")
+
+    xbar = torch.randn(B, heads * E, device="cuda").half()
+    wv = (torch.randn(E, E, device="cuda") * E ** -0.5).half()
+    bv = torch.randn(E, device="cuda")
+    out2 = torch.full((B, E), float("nan"), device="cuda", dtype=torch.float16)
+    _check(lib, lib.embclip_gemm_grouped_f16(_ptr(xbar), heads * E, _ptr(wv), E, E, _ptr(bv), _ptr(out2), B, E, E,
+                                             hd, E, 0, 0, 0, 0, _stream()))
+    torch.cuda.synchronize()
+    ref2 = torch.einsum("bhc,hdc->bhd", xbar.float().view(B, heads, E), wv.float().view(heads, hd, E)).reshape(B, E) + bv
+    _close(out2, ref2, "grouped v")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [
+    (2, 16, 16, 64, 64),     # box 16x8
+    (3, 56, 56, 64, 64),     # layer1 conv2: box 56x2 / partial coverage
+    (2, 28, 28, 128, 128),   # layer2
+    (3, 14, 14, 256, 256),   # layer3: box 14x9, second tile half out of bounds
+    (5, 7, 7, 512, 512),     # layer4: two images per tile, odd batch
+    (2, 112, 112, 32, 32),   # stem conv2: BK 32 / BN 32
+    (1, 112, 112, 32, 64),   # stem conv3
+    (1, 10, 12, 32, 96),     # odd spatial size, N tile 32 x 3
+])
+def test_conv3x3(lib, B, H, W, Cin, Cout):
+    g = torch.Generator(device="cuda").manual_seed(H * 1000 + Cin)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g).half()
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) * (9 * Cin) ** -0.5).half()
+    b = torch.randn(Cout, device="cuda", generator=g)
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    out = torch.full((B, H, W, Cout), float("nan"), device="cuda", dtype=torch.float16)
+    _check(lib, lib.embclip_conv3x3_f16(_ptr(x), _ptr(wk), _ptr(b), _ptr(out), B, H, W, Cin, Cout, 1, _stream()))
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1).relu().permute(0, 2, 3, 1)
+    _close(out.reshape(-1, Cout), ref.reshape(-1, Cout), f"conv3x3 B{B} {H}x{W} {Cin}->{Cout}")
+
+
+def test_avgpool2(lib):
+    x = torch.randn(3, 28, 28, 128, device="cuda").half()
+    out = torch.empty(3, 14, 14, 128, device="cuda", dtype=torch.float16)
+    _check(lib, lib.embclip_avgpool2_f16(_ptr(x), _ptr(out), 3, 28, 28, 128, _stream()))
+    torch.cuda.synchronize()
+    ref = F.avg_pool2d(x.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    assert torch.equal(out, ref.half())     # fp32 sum of 4, one rounding: bit-exact
+
+
+def test_stem_conv1(lib):
+    torch.manual_seed(3)
+    x = torch.randn(2, 224, 224, 3, device="cuda")
+    w = torch.randn(32, 3, 3, 3, device="cuda") * 27 ** -0.5
+    b = torch.randn(32, device="cuda")
+    wk = w.permute(2, 3, 1, 0).reshape(27, 32).contiguous()
+    out = torch.empty(2, 112, 112, 32, device="cuda", dtype=torch.float16)
+    _check(lib, lib.embclip_stem_conv1(_ptr(x), _ptr(wk), _ptr(b), _ptr(out), 2, 224, 32, _stream()))
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, b, stride=2, padding=1).relu().permute(0, 2, 3, 1)
+    _close(out.reshape(-1, 32), ref.reshape(-1, 32), "stem conv1")
+
+
+def test_error_paths(lib):
+    a = torch.zeros(4, 48, device="cuda", dtype=torch.float16)
+    rc = lib.embclip_gemm_f16(_ptr(a), None, _ptr(a), None, None, _ptr(a), 4, 48, 48, 0, 0, 0, _stream())
+    assert rc == -1 and b"multiples of 32" in lib.embclip_last_error()
+    assert lib.embclip_gemm_f16(None, None, None, None, None, None, 4, 64, 64, 0, 0, 0, _stream()) == -1

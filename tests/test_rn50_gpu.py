@@ -1,0 +1,114 @@
+"""GPU parity of the CLIP-RN50 encoder (through the C ABI) against the oracle.
+
+Two bars (DESIGN.md "Numerics"):
+  * vs oracle/fp16_path.py -- same rounding points as the kernels, so only fp32 accumulation order differs:
+    rel-L2 per frame <= 2e-4, layer by layer.  This is the "do the kernels compute the design" check.
+  * vs oracle/clip_model.py in fp32 -- the north-star bar: rel-L2 per frame <= 1e-3 on every head.
+Golden fixtures (tests/golden/rn50_b2_*.pt, made by tests/golden/make_golden.py from the oracle) pin the
+same check without needing the oracle at run time.
+"""
+import os
+
+import pytest
+import torch
+
+from conftest import synthetic_frames
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel_l2(a, b):
+    a, b = a.float().flatten(1), b.float().flatten(1)
+    return ((a - b).norm(dim=1) / b.norm(dim=1).clamp_min(1e-12)).max().item()
+
+
+@pytest.fixture(scope="module")
+def encoder(built_lib, rn50_visual):
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    from embclip_b200.encoder import ClipRN50Encoder
+    return ClipRN50Encoder(rn50_visual.state_dict(), "cuda:0")
+
+
+@pytest.mark.parametrize("batch", [2, 5])
+def test_rn50_layerwise_vs_fp16_path(encoder, rn50_visual, batch):
+    from oracle.fp16_path import rn50_fp16_path
+    frames = synthetic_frames(batch, seed=batch)
+    ref = rn50_fp16_path(rn50_visual, frames.permute(0, 3, 1, 2).contiguous())
+    out = encoder(frames.cuda(), want=("trunk", "avgpool", "attnpool"))
+    torch.cuda.synchronize()
+    acts = encoder.activations(batch)
+    report = []
+    for name, t in acts.items():
+        r = ref[name].reshape(t.shape)
+        report.append((name, rel_l2(t.cpu(), r)))
+    worst = max(report, key=lambda x: x[1])
+    first_bad = next((x for x in report if not x[1] <= 2e-4), None)
+    assert first_bad is None, f"first diverging activation {first_bad}; worst {worst}; all: {report}"
+    assert rel_l2(out["trunk"].cpu(), ref["trunk_nchw"]) <= 2e-4
+    assert rel_l2(out["avgpool"].cpu(), ref["avgpool"]) <= 2e-4
+    assert rel_l2(out["attnpool"].cpu(), ref["attnpool"]) <= 5e-4
+
+
+def test_rn50_vs_fp32_oracle(encoder, rn50_visual):
+    frames = synthetic_frames(4, seed=7)
+    with torch.no_grad():
+        t = rn50_visual.trunk(frames.permute(0, 3, 1, 2).contiguous())
+        ap = rn50_visual.attnpool(t)
+    out = encoder(frames.cuda(), want=("trunk", "avgpool", "attnpool"))
+    torch.cuda.synchronize()
+    e_trunk, e_avg, e_ap = rel_l2(out["trunk"].cpu(), t), rel_l2(out["avgpool"].cpu(), t.mean((2, 3))), rel_l2(out["attnpool"].cpu(), ap)
+    print(f"rel-L2 vs fp32 oracle: trunk {e_trunk:.3e} avgpool {e_avg:.3e} attnpool {e_ap:.3e}")
+    assert e_trunk <= 1e-3, e_trunk
+    assert e_avg <= 1e-3, e_avg
+    assert e_ap <= 1e-3, e_ap
+
+
+def test_rn50_golden(encoder):
+    path = os.path.join(GOLDEN, "rn50_b2_seed0.pt")
+    g = torch.load(path)
+    frames = synthetic_frames(2, seed=0)
+    assert torch.equal(frames[:, ::37, ::41].contiguous(), g["frames_probe"]), "synthetic frame generator drifted"
+    out = encoder(frames.cuda(), want=("trunk", "avgpool", "attnpool"))
+    torch.cuda.synchronize()
+    assert rel_l2(out["avgpool"].cpu(), g["avgpool"]) <= 1e-3
+    assert rel_l2(out["attnpool"].cpu(), g["attnpool"]) <= 1e-3
+    assert rel_l2(out["trunk"].cpu()[:, ::16], g["trunk_every16"]) <= 1e-3
+
+
+def test_rn50_head_selection_and_determinism(encoder):
+    frames = synthetic_frames(3, seed=11).cuda()
+    a = encoder(frames, want=("trunk",))["trunk"].clone()
+    b = encoder(frames, want=("trunk", "attnpool"))
+    torch.cuda.synchronize()
+    assert torch.equal(a, b["trunk"])                                   # bit-identical run to run
+    c = encoder(frames[:1], want=("trunk",))["trunk"]
+    torch.cuda.synchronize()
+    assert torch.equal(c[0], a[0])                                      # batch-invariant (no cross-frame mixing)
+    assert set(encoder(frames, want=("avgpool",)).keys()) == {"avgpool"}
+    empty = encoder(frames[:0], want=("trunk",))["trunk"]
+    assert empty.shape == (0, 2048, 7, 7)
+
+
+def test_rn50_rejects_bad_input(encoder):
+    with pytest.raises(ValueError):
+        encoder(torch.zeros(2, 3, 224, 224, device="cuda"))
+    with pytest.raises(ValueError):
+        encoder(torch.zeros(2, 224, 224, 3, device="cuda", dtype=torch.float16))
+    with pytest.raises(ValueError):
+        encoder(torch.zeros(2, 224, 224, 3))
+
+
+def test_rn50_large_batch_properties(encoder):
+    """BASELINE size (B=256): size-independent properties -- every frame's result equals the same frame run
+    in a small batch (frames are independent), and duplicated frames give identical rows."""
+    B = 256
+    small = synthetic_frames(8, seed=5).cuda()
+    frames = small.repeat(B // 8, 1, 1, 1)
+    big = encoder(frames, want=("trunk", "attnpool"))
+    ref = encoder(small, want=("trunk", "attnpool"))
+    torch.cuda.synchronize()
+    for k in ("trunk", "attnpool"):
+        assert torch.equal(big[k][:8], ref[k]), k
+        assert torch.equal(big[k].view(B // 8, 8, -1), ref[k].view(1, 8, -1).expand(B // 8, -1, -1)), k
