@@ -1,0 +1,59 @@
+"""Seeded synthetic CLIP-RN50 weights with the official state-dict key names (no checkpoint exists offline;
+SURVEY.md section 8d config 2).  Well conditioned: activations stay O(1) through all 16 residual blocks in
+fp16, and the attention-pool logits are O(1) like a trained model's.
+
+conv ~ N(0, 2/fan_in); BN gamma in U(.5,1.5) (x0.5 on every block's last BN and downsample BN), beta ~ N(0,.1),
+running_mean ~ N(0,.1), running_var in U(.5,1.5); linear ~ N(0, 1/in) (x0.25 on q/k projections), bias ~ N(0,.1).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict
+
+import torch
+
+
+def synthetic_rn50_state_dict(seed: int = 1234, layers=(3, 4, 6, 3), width: int = 64, output_dim: int = 1024,
+                              input_resolution: int = 224, prefix: str = "") -> "OrderedDict[str, torch.Tensor]":
+    g = torch.Generator().manual_seed(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    rn = lambda *s: torch.randn(*s, generator=g)
+    ru = lambda *s: torch.rand(*s, generator=g)
+
+    def conv(name, cout, cin, k):
+        sd[prefix + name + ".weight"] = rn(cout, cin, k, k) * (2.0 / (cin * k * k)) ** 0.5
+
+    def bn(name, c, gain=1.0):
+        sd[prefix + name + ".weight"] = (0.5 + ru(c)) * gain
+        sd[prefix + name + ".bias"] = 0.1 * rn(c)
+        sd[prefix + name + ".running_mean"] = 0.1 * rn(c)
+        sd[prefix + name + ".running_var"] = 0.5 + ru(c)
+        sd[prefix + name + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+
+    def linear(name, cout, cin, gain=1.0):
+        sd[prefix + name + ".weight"] = rn(cout, cin) * cin ** -0.5 * gain
+        sd[prefix + name + ".bias"] = 0.1 * rn(cout)
+
+    conv("conv1", width // 2, 3, 3); bn("bn1", width // 2)
+    conv("conv2", width // 2, width // 2, 3); bn("bn2", width // 2)
+    conv("conv3", width, width // 2, 3); bn("bn3", width)
+    inplanes = width
+    for li, nblocks in enumerate(layers):
+        planes = width << li
+        for bi in range(nblocks):
+            p = f"layer{li + 1}.{bi}"
+            stride = 2 if (bi == 0 and li > 0) else 1
+            conv(p + ".conv1", planes, inplanes, 1); bn(p + ".bn1", planes)
+            conv(p + ".conv2", planes, planes, 3); bn(p + ".bn2", planes)
+            conv(p + ".conv3", planes * 4, planes, 1); bn(p + ".bn3", planes * 4, gain=0.5)
+            if stride > 1 or inplanes != planes * 4:
+                conv(p + ".downsample.0", planes * 4, inplanes, 1); bn(p + ".downsample.1", planes * 4, gain=0.5)
+            inplanes = planes * 4
+    embed = width * 32
+    tokens = (input_resolution // 32) ** 2 + 1
+    sd[prefix + "attnpool.positional_embedding"] = rn(tokens, embed) * embed ** -0.5
+    linear("attnpool.k_proj", embed, embed, gain=0.25)
+    linear("attnpool.q_proj", embed, embed, gain=0.25)
+    linear("attnpool.v_proj", embed, embed)
+    linear("attnpool.c_proj", output_dim, embed)
+    return sd

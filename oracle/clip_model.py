@@ -319,39 +319,13 @@ def freeze_model(model: nn.Module) -> nn.Module:
 # --------------------------------------------------------------------------------------
 @torch.no_grad()
 def init_synthetic_rn50_visual(visual: ModifiedResNet, seed: int = 1234) -> ModifiedResNet:
-    """Well-conditioned random weights: activations stay O(1) through all 16 residual blocks so
-    parity tests are neither vacuous nor overflowing in fp16.  conv ~ kaiming(fan_in, relu),
-    BN gamma in U(.5,1.5), beta ~ N(0,.1), mean ~ N(0,.1), var in U(.5,1.5); the last BN of
-    every block is scaled by 0.5 so the residual stream grows slowly."""
-    g = torch.Generator().manual_seed(seed)
-
-    def rn(*shape):
-        return torch.randn(*shape, generator=g)
-
-    def ru(*shape):
-        return torch.rand(*shape, generator=g)
-
-    for name, m in visual.named_modules():
-        if isinstance(m, nn.Conv2d):
-            fan_in = m.in_channels * m.kernel_size[0] * m.kernel_size[1]
-            m.weight.copy_(rn(*m.weight.shape) * (2.0 / fan_in) ** 0.5)
-        elif isinstance(m, nn.BatchNorm2d):
-            c = m.num_features
-            gamma = 0.5 + ru(c)
-            if name.endswith("bn3") and "layer" in name or name.endswith("downsample.1"):
-                gamma = gamma * 0.5
-            m.weight.copy_(gamma)
-            m.bias.copy_(0.1 * rn(c))
-            m.running_mean.copy_(0.1 * rn(c))
-            m.running_var.copy_(0.5 + ru(c))
-        elif isinstance(m, nn.Linear):
-            # q/k projections are scaled down so the attention-pool logits are O(1) (std ~ 1 over the 50
-            # keys, as in a trained model) instead of a saturated, ill-conditioned softmax
-            gain = 0.25 if name.endswith(("q_proj", "k_proj")) else 1.0
-            m.weight.copy_(rn(*m.weight.shape) * m.in_features ** -0.5 * gain)
-            m.bias.copy_(0.1 * rn(*m.bias.shape))
-    ap = visual.attnpool
-    ap.positional_embedding.copy_(rn(*ap.positional_embedding.shape) * ap.positional_embedding.shape[1] ** -0.5)
+    """Loads the seeded, well-conditioned synthetic weights the product package generates
+    (embclip_b200/synthetic.py -- weight *generation* is shared so both sides see the same tensors; no
+    arithmetic of the path is).  strict=True doubles as a check that the restated module has exactly the
+    official state-dict keys."""
+    from embclip_b200.synthetic import synthetic_rn50_state_dict
+    visual.load_state_dict(synthetic_rn50_state_dict(seed, output_dim=visual.output_dim,
+                                                     input_resolution=visual.input_resolution), strict=True)
     return visual
 
 

@@ -35,14 +35,23 @@ def _fold(conv, bn):
 
 
 @torch.no_grad()
-def rn50_fp16_path(m: ModifiedResNet, frames_nchw: torch.Tensor, quantize: bool = True) -> Dict[str, torch.Tensor]:
+def rn50_fp16_path(m: ModifiedResNet, frames_nchw: torch.Tensor, quantize: bool = True,
+                   feed: Dict[str, torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """frames_nchw fp32 [B,3,R,R] -> dict of NHWC activations (+ 'trunk_nchw', 'avgpool', 'attnpool').
-    quantize=False evaluates the same fused graph in pure fp32 (checks the folding algebra)."""
+    quantize=False evaluates the same fused graph in pure fp32 (checks the folding algebra).
+
+    feed: NHWC activations produced by the implementation under test.  When given, every op is evaluated on
+    the *fed* inputs instead of this function's own chain, so each returned tensor is the expected output of
+    ONE op given the inputs the kernels actually saw -- per-op isolation.  (Chained end to end, two fp16
+    pipelines that differ only in fp32 summation order still drift apart by ~1e-3: a different summation
+    order flips a few percent of the fp16 roundings per layer and the flips cascade.)"""
     q = _h if quantize else (lambda t: t)
     acts: Dict[str, torch.Tensor] = {}
 
     def put(name, t_nchw):
         acts[name] = t_nchw.permute(0, 2, 3, 1).contiguous()
+        if feed is not None and name in feed:
+            return feed[name].float().reshape(acts[name].shape).permute(0, 3, 1, 2).contiguous()
         return t_nchw
 
     def cbr(x, conv, bn, relu=True, extra=None, round_out=True, round_w=True):
@@ -76,7 +85,7 @@ def rn50_fp16_path(m: ModifiedResNet, frames_nchw: torch.Tensor, quantize: bool 
             else:
                 idn = x
             x = put(p + ".conv3", cbr(b, blk.conv3, blk.bn3, extra=idn, round_out=not last))
-    acts["trunk_nchw"] = x
+    acts["trunk_nchw"] = x                     # (fed value of the last conv3 when feed is given)
     acts["avgpool"] = x.mean(dim=(2, 3))
 
     # attention pool with the kernel path's algebra and rounding points
@@ -84,19 +93,21 @@ def rn50_fp16_path(m: ModifiedResNet, frames_nchw: torch.Tensor, quantize: bool 
     B, E, Hf, Wf = x.shape
     heads, hd = ap.num_heads, E // ap.num_heads
     t = x.reshape(B, E, Hf * Wf).permute(0, 2, 1)                         # [B, P, E]
-    tok = q(torch.cat([t.mean(dim=1, keepdim=True), t], dim=1) + ap.positional_embedding[None])
-    acts["attnpool.tokens"] = tok[:, None]
+    def put2(name, val, shape4):
+        acts[name] = val.reshape(shape4)
+        if feed is not None and name in feed:
+            return feed[name].float().reshape(val.shape)
+        return val
+
+    L = Hf * Wf + 1
+    tok = put2("attnpool.tokens", q(torch.cat([t.mean(dim=1, keepdim=True), t], dim=1) + ap.positional_embedding[None]), (B, 1, L, E))
     s = hd ** -0.5
-    qv = q(tok[:, 0] @ q(ap.q_proj.weight * s).t() + ap.q_proj.bias * s)  # [B, E]
-    acts["attnpool.q"] = qv[:, None, None]
+    qv = put2("attnpool.q", q(tok[:, 0] @ q(ap.q_proj.weight * s).t() + ap.q_proj.bias * s), (B, 1, 1, E))
     wk = q(ap.k_proj.weight).view(heads, hd, E)
-    qt = q(torch.einsum("bhd,hdc->bhc", qv.view(B, heads, hd), wk))       # [B, heads, E]
-    acts["attnpool.qk"] = qt[:, None]
+    qt = put2("attnpool.qk", q(torch.einsum("bhd,hdc->bhc", qv.view(B, heads, hd), wk)), (B, 1, heads, E))
     p = torch.softmax(torch.einsum("bhc,bjc->bhj", qt, tok), dim=-1)
-    xbar = q(torch.einsum("bhj,bjc->bhc", p, tok))
-    acts["attnpool.xbar"] = xbar[:, None]
+    xbar = put2("attnpool.xbar", q(torch.einsum("bhj,bjc->bhc", p, tok)), (B, 1, heads, E))
     wv = q(ap.v_proj.weight).view(heads, hd, E)
-    o = q(torch.einsum("bhc,hdc->bhd", xbar, wv).reshape(B, E) + ap.v_proj.bias)
-    acts["attnpool.v"] = o[:, None, None]
+    o = put2("attnpool.v", q(torch.einsum("bhc,hdc->bhd", xbar, wv).reshape(B, E) + ap.v_proj.bias), (B, 1, 1, E))
     acts["attnpool"] = o @ q(ap.c_proj.weight).t() + ap.c_proj.bias
     return acts

@@ -1,0 +1,151 @@
+"""Pins the CLIP oracle (oracle/clip_model.py) with what exists offline: FLOP identities,
+torch's own multi_head_attention_forward, the independent HF `transformers` CLIP implementation, and the
+committed golden vectors."""
+import os
+
+import pytest
+import torch
+
+from conftest import synthetic_frames
+from oracle import clip_model as cm
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_flop_identity_rn50(rn50_visual):
+    macs = cm.count_macs_rn50(rn50_visual)
+    total = sum(macs.values())
+    assert abs(2 * total / 1e9 - 10.734) < 1e-3                      # trunk GFLOP / frame
+    stage = lambda p: sum(v for k, v in macs.items() if k.startswith(p)) / 1e9
+    assert abs(stage("conv") - 0.358) < 1e-3 and abs(stage("layer1") - 0.668) < 1e-3
+    assert abs(stage("layer2") - 1.374) < 1e-3 and abs(stage("layer3") - 1.811) < 1e-3 and abs(stage("layer4") - 1.156) < 1e-3
+    # attention pool as written: 3 x 50 x 2048^2 + scores + 50 x 2048 x 1024 -> 12.22 GFLOP tower total
+    ap = 3 * 50 * 2048 * 2048 + 2 * 32 * 50 * 50 * 64 + 50 * 2048 * 1024
+    assert abs(2 * (total + ap) / 1e9 - 12.22) < 0.01
+
+
+def test_attnpool_matches_expanded_form(rn50_visual):
+    ap = rn50_visual.attnpool
+    torch.manual_seed(0)
+    x = torch.randn(3, 2048, 7, 7)
+    with torch.no_grad():
+        got = ap(x)
+        t = x.flatten(2).permute(0, 2, 1)
+        t = torch.cat([t.mean(1, keepdim=True), t], 1) + ap.positional_embedding
+        q = ap.q_proj(t[:, :1]).view(3, 1, 32, 64).transpose(1, 2)
+        k = ap.k_proj(t).view(3, 50, 32, 64).transpose(1, 2)
+        v = ap.v_proj(t).view(3, 50, 32, 64).transpose(1, 2)
+        p = torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1)
+        ref = ap.c_proj((p @ v).transpose(1, 2).reshape(3, 2048))
+    assert torch.allclose(got, ref, atol=2e-5, rtol=1e-4)
+
+
+def _copy_block_to_hf(blk, hf_layer):
+    d = blk.ln_1.weight.shape[0]
+    with torch.no_grad():
+        hf_layer.layer_norm1.load_state_dict(blk.ln_1.state_dict())
+        hf_layer.layer_norm2.load_state_dict(blk.ln_2.state_dict())
+        w, b = blk.attn.in_proj_weight, blk.attn.in_proj_bias
+        for i, proj in enumerate((hf_layer.self_attn.q_proj, hf_layer.self_attn.k_proj, hf_layer.self_attn.v_proj)):
+            proj.weight.copy_(w[i * d:(i + 1) * d])
+            proj.bias.copy_(b[i * d:(i + 1) * d])
+        hf_layer.self_attn.out_proj.load_state_dict(blk.attn.out_proj.state_dict())
+        hf_layer.mlp.fc1.load_state_dict(blk.mlp.c_fc.state_dict())
+        hf_layer.mlp.fc2.load_state_dict(blk.mlp.c_proj.state_dict())
+
+
+@pytest.fixture(scope="module")
+def vit_clip():
+    torch.manual_seed(0)
+    m = cm.build_vit_b32()
+    cm.init_synthetic_transformer(m, seed=4321)
+    return m.eval()
+
+
+def test_vit_b32_matches_hf(vit_clip):
+    from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
+    cfg = CLIPVisionConfig()                                           # defaults == ViT-B/32
+    assert (cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers, cfg.patch_size, cfg.hidden_act) == (768, 3072, 12, 32, "quick_gelu")
+    hf = CLIPVisionModelWithProjection(cfg).eval()
+    v = vit_clip.visual
+    with torch.no_grad():
+        e = hf.vision_model.embeddings
+        e.class_embedding.copy_(v.class_embedding)
+        e.patch_embedding.weight.copy_(v.conv1.weight)
+        e.position_embedding.weight.copy_(v.positional_embedding)
+        hf.vision_model.pre_layrnorm.load_state_dict(v.ln_pre.state_dict())
+        hf.vision_model.post_layernorm.load_state_dict(v.ln_post.state_dict())
+        hf.visual_projection.weight.copy_(v.proj.t())
+        for blk, lyr in zip(v.transformer.resblocks, hf.vision_model.encoder.layers):
+            _copy_block_to_hf(blk, lyr)
+        x = synthetic_frames(2, seed=3).permute(0, 3, 1, 2).contiguous()
+        got = vit_clip.encode_image(x)
+        ref = hf(pixel_values=x).image_embeds
+    assert got.shape == (2, 512)
+    assert ((got - ref).norm() / ref.norm()).item() < 2e-5
+
+
+def test_text_tower_matches_hf(vit_clip):
+    from transformers import CLIPTextConfig, CLIPTextModelWithProjection
+    cfg = CLIPTextConfig(eos_token_id=49407, bos_token_id=49406)
+    assert (cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads, cfg.max_position_embeddings) == (512, 12, 8, 77)
+    hf = CLIPTextModelWithProjection(cfg).eval()
+    m = vit_clip
+    g = torch.Generator().manual_seed(0)
+    toks = torch.zeros(4, 77, dtype=torch.long)
+    for i in range(4):                                                 # SURVEY.md section 8d config 5 token recipe
+        n = int(torch.randint(2, 9, (1,), generator=g))
+        toks[i, 0] = 49406
+        toks[i, 1:1 + n] = torch.randint(1, 49405, (n,), generator=g)
+        toks[i, 1 + n] = 49407
+    with torch.no_grad():
+        hf.text_model.embeddings.token_embedding.weight.copy_(m.token_embedding.weight)
+        hf.text_model.embeddings.position_embedding.weight.copy_(m.positional_embedding)
+        hf.text_model.final_layer_norm.load_state_dict(m.ln_final.state_dict())
+        hf.text_projection.weight.copy_(m.text_projection.t())
+        for blk, lyr in zip(m.transformer.resblocks, hf.text_model.encoder.layers):
+            _copy_block_to_hf(blk, lyr)
+        got = m.encode_text(toks)
+        ref = hf(input_ids=toks).text_embeds
+    assert ((got - ref).norm() / ref.norm()).item() < 2e-5
+
+
+def test_clip_logits(vit_clip):
+    x = synthetic_frames(2, seed=1).permute(0, 3, 1, 2).contiguous()
+    toks = torch.zeros(3, 77, dtype=torch.long)
+    toks[:, 0] = 49406
+    toks[:, 1] = torch.tensor([5, 6, 7])
+    toks[:, 2] = 49407
+    with torch.no_grad():
+        li, lt = vit_clip(x, toks)
+    assert li.shape == (2, 3) and torch.equal(li.t(), lt)
+    assert li.abs().max() <= 100.0 + 1e-3                              # cosine in [-1,1] x exp(ln 100)
+
+
+def test_oracle_reproduces_golden(rn50_visual):
+    g = torch.load(os.path.join(GOLDEN, "rn50_b2_seed0.pt"))
+    frames = synthetic_frames(2, seed=0)
+    assert torch.equal(frames[:, ::37, ::41].contiguous(), g["frames_probe"])
+    assert torch.equal(rn50_visual.layer3[2].conv2.weight[:4, :4, 1, 1], g["weight_probe"])
+    with torch.no_grad():
+        t = rn50_visual.trunk(frames.permute(0, 3, 1, 2).contiguous())
+        a = rn50_visual.attnpool(t)
+    # thread-count dependent summation order only
+    assert torch.allclose(t[:, ::16], g["trunk_every16"], rtol=1e-4, atol=1e-4)
+    assert torch.allclose(a, g["attnpool"], rtol=1e-4, atol=1e-4)
+    assert torch.allclose(t.mean((2, 3)), g["avgpool"], rtol=1e-4, atol=1e-4)
+
+
+def test_fp16_path_budget(rn50_visual):
+    """The design's rounding points stay inside the 1e-3 north-star bar against the fp32 oracle (CPU emulation;
+    the GPU test repeats this with the real kernels), and the fused graph is exact algebra in fp32."""
+    from oracle.fp16_path import rn50_fp16_path
+    frames = synthetic_frames(2, seed=0).permute(0, 3, 1, 2).contiguous()
+    with torch.no_grad():
+        t = rn50_visual.trunk(frames)
+        a = rn50_visual.attnpool(t)
+    rel = lambda x, y: ((x - y).flatten(1).norm(dim=1) / y.flatten(1).norm(dim=1)).max().item()
+    exact = rn50_fp16_path(rn50_visual, frames, quantize=False)
+    assert rel(exact["trunk_nchw"], t) < 1e-5 and rel(exact["attnpool"], a) < 1e-5
+    q = rn50_fp16_path(rn50_visual, frames, quantize=True)
+    assert rel(q["trunk_nchw"], t) < 1e-3 and rel(q["attnpool"], a) < 1e-3 and rel(q["avgpool"], t.mean((2, 3))) < 1e-3

@@ -32,23 +32,25 @@ def encoder(built_lib, rn50_visual):
 
 
 @pytest.mark.parametrize("batch", [2, 5])
-def test_rn50_layerwise_vs_fp16_path(encoder, rn50_visual, batch):
+def test_rn50_per_op_vs_fp16_path(encoder, rn50_visual, batch):
+    """Per-op isolation: every op's output is compared with the oracle evaluated on the inputs the kernels
+    actually saw (feed=GPU activations).  Only fp32 summation order differs -> rel-L2 <= 1e-4 per op."""
     from oracle.fp16_path import rn50_fp16_path
     frames = synthetic_frames(batch, seed=batch)
-    ref = rn50_fp16_path(rn50_visual, frames.permute(0, 3, 1, 2).contiguous())
     out = encoder(frames.cuda(), want=("trunk", "avgpool", "attnpool"))
     torch.cuda.synchronize()
-    acts = encoder.activations(batch)
-    report = []
-    for name, t in acts.items():
-        r = ref[name].reshape(t.shape)
-        report.append((name, rel_l2(t.cpu(), r)))
-    worst = max(report, key=lambda x: x[1])
-    first_bad = next((x for x in report if not x[1] <= 2e-4), None)
-    assert first_bad is None, f"first diverging activation {first_bad}; worst {worst}; all: {report}"
-    assert rel_l2(out["trunk"].cpu(), ref["trunk_nchw"]) <= 2e-4
-    assert rel_l2(out["avgpool"].cpu(), ref["avgpool"]) <= 2e-4
-    assert rel_l2(out["attnpool"].cpu(), ref["attnpool"]) <= 5e-4
+    acts = {k: v.cpu() for k, v in encoder.activations(batch).items()}
+    nchw = frames.permute(0, 3, 1, 2).contiguous()
+    ref = rn50_fp16_path(rn50_visual, nchw, feed=acts)
+    report = [(name, rel_l2(t, ref[name].reshape(t.shape))) for name, t in acts.items()]
+    bad = [x for x in report if not x[1] <= 1e-4]
+    assert not bad, f"ops off: {bad}; all: {report}"
+    assert rel_l2(out["trunk"].cpu(), ref["trunk_nchw"]) <= 1e-6          # pure layout change of the fed tensor
+    assert rel_l2(out["avgpool"].cpu(), ref["avgpool"]) <= 1e-5
+    assert rel_l2(out["attnpool"].cpu(), ref["attnpool"]) <= 1e-4
+    # chained end to end the two fp16 pipelines decorrelate (see oracle/fp16_path.py); bound it loosely
+    chained = rn50_fp16_path(rn50_visual, nchw)
+    assert rel_l2(out["trunk"].cpu(), chained["trunk_nchw"]) <= 1.5e-3
 
 
 def test_rn50_vs_fp32_oracle(encoder, rn50_visual):

@@ -10,7 +10,7 @@ for t in test_gemm_plain test_gemm_tile_variants test_gemm_epilogues test_gemm_k
   echo "=================== $t" >> $LOG
   timeout 300 python -m pytest tests/test_primitives_gpu.py -m gpu -q -k "$t" -p no:cacheprovider 2>&1 | tail -60 >> $LOG
 done
-for t in test_rn50_layerwise_vs_fp16_path test_rn50_vs_fp32_oracle test_rn50_golden test_rn50_head_selection_and_determinism \
+for t in test_rn50_per_op_vs_fp16_path test_rn50_vs_fp32_oracle test_rn50_golden test_rn50_head_selection_and_determinism \
          test_rn50_rejects_bad_input test_rn50_large_batch_properties; do
   echo "=================== $t" >> $LOG
   timeout 600 python -m pytest tests/test_rn50_gpu.py -m gpu -q -s -k "$t" -p no:cacheprovider 2>&1 | tail -60 >> $LOG
