@@ -70,22 +70,28 @@ def time_cpu_oracle(model, batch, iters, warmup):
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms from before the warm-up; stop(t0, t1) keeps the
+    samples whose timestamp falls inside the timed region [t0, t1] (wall clock), or -- if the region was shorter
+    than one sampling period -- the samples taken under load since the warm-up began."""
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t_start = time.time()
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                        "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
-    def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    def stop(self, t0=None, t1=None):
+        import datetime
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "window": None}
         if self.p is None:
             return out
+        time.sleep(0.15)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -93,23 +99,33 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, reasons, mx = [], set(), None
+        rows = []
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
             try:
-                sm.append(float(c[1]))
-                mx = float(c[2])
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(c[1]), float(c[2]), float(c[3]), c[5:9]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
         os.unlink(self.f.name)
-        if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        sel, window = [], None
+        if t0 is not None:
+            sel = [r for r in rows if t0 <= r[0] <= t1]
+            window = "timed region"
+        if not sel:
+            busy = [r for r in rows if r[3] > 250.0] or rows      # under load (power draw) since warm-up
+            sel, window = busy, "warm-up + timed region (timed region shorter than the 100 ms sampling period)"
+        if sel:
+            sm = sorted(r[1] for r in sel)
+            reasons = set()
+            for r in sel:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=sel[0][2], reasons=sorted(reasons), samples=len(sel),
+                       window=window, power_w_max=max(r[3] for r in sel))
         return out
 
 
@@ -179,18 +195,20 @@ def run_ours(args, rank, local_rank, world):
         return float(t.item())
 
     # ---------------- device-resident throughput (value)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(W):
         enc.forward(frames, HEADS, out=outs)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
     e0.record()
     for _ in range(K):
         enc.forward(frames, HEADS, out=outs)
     e1.record()
     barrier()
+    wall1 = time.time()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(wall0, wall1) if sampler else None
     ms_step = ms_total / K
     value = world * BATCH * K / (ms_total * 1e-3)
 
@@ -282,8 +300,8 @@ def run_ours(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -10,8 +10,8 @@
 //   conv into its conv3 ( [W3 | Wd] . [t ; x] ), so the identity tensor never touches HBM.
 // * "Grouped" mode offsets the K window per N-group (per attention head), which is how AttentionPool2d's
 //   per-head contractions run on the same kernel.
-// * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread tcgen05.mma
-//   issuer, warps 2..5 = epilogue (TMEM -> regs -> +bias (+residual) -> ReLU -> fp16 -> swizzled smem -> TMA
+// * Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread tcgen05.mma
+//   issuer, warps 2..9 = epilogue (TMEM -> regs -> +bias (+residual) -> ReLU -> fp16 -> swizzled smem -> TMA
 //   store).  smem stages are handed over with full/empty mbarriers; the accumulator is double-buffered
 //   in TMEM (2 x BN columns) so tile i's epilogue overlaps tile i+1's MMAs.  Persistent grid.
 #pragma once
@@ -32,8 +32,6 @@ struct ConvGemmParams {
   int out_f32;                  // 1: epilogue stores fp32 rows straight to `out_f32_ptr` (2-D mode only)
   int M, N;                     // logical GEMM extents (rows valid for residual / fp32 stores)
   const float* bias;            // [N] or nullptr
-  const __half* residual;       // [M, ldr] or nullptr (2-D mode only)
-  int ldr;
   float* out_f32_ptr;           // [M, ldo]
   int ldo;
   // grouped mode (0 = off): N-group g = n0 / grp_n reads A at k + g*grp_a_koff, W at k + g*grp_b_koff,
@@ -41,7 +39,7 @@ struct ConvGemmParams {
   int grp_n, grp_a_koff, grp_b_koff, grp_b_nmod;
 };
 
-template <int BN, int BK>
+template <int BN, int BK, bool kRes = false>
 struct ConvGemmCfg {
   static constexpr int BM = 128;
   static constexpr int kSwz = BK * 2;                          // operand swizzle span (bytes)
@@ -52,37 +50,46 @@ struct ConvGemmCfg {
   static constexpr int kCSwz = kCS * 2;
   static constexpr int kCChunkBytes = BM * kCS * 2;
   static constexpr int kCBytes = BM * BN * 2;
+  // two staging buffers: tile i's TMA store drains while tile i+1's epilogue fills the other one, and
+  // (kRes) residual tiles are prefetched one tile ahead.  BN = 256 only has room for one.
+  static constexpr int kCBufs = (kRes || BN <= 128) ? 2 : 1;
+  static constexpr int kEpiWarps = 8;                          // two warps per TMEM lane quarter, half the columns each
+  static constexpr int kEpiThreads = kEpiWarps * 32;
+  static constexpr int kThreads = 64 + kEpiThreads;
+  static constexpr int kColsPerWarp = BN / 2;
+  static constexpr int kChunk = kColsPerWarp < 32 ? kColsPerWarp : 32;   // columns per tcgen05.ld
   static constexpr int kBudget = 200 * 1024;
-  static constexpr int kStagesRaw = (kBudget - kCBytes) / kStageBytes;
+  static constexpr int kStagesRaw = (kBudget - kCBufs * kCBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr int kBarBytes = 256;                        // mbarriers + tmem ptr
   static constexpr int kBiasBytes = BN * 4;
-  static constexpr size_t kSmemBytes = 1024 /*align slack*/ + size_t(kStages) * kStageBytes + kCBytes + kBiasBytes + kBarBytes;
+  static constexpr size_t kSmemBytes = 1024 /*align slack*/ + size_t(kStages) * kStageBytes + kCBufs * kCBytes + kBiasBytes + kBarBytes;
   static_assert(kStages >= 2, "pipeline needs at least two stages");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
   static_assert(kABytes % 1024 == 0 && kBBytes % 1024 == 0, "stage tiles must keep 1024-B alignment");
 };
 
-template <int BN, int BK>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, int BK, bool kRes>
+__global__ void __launch_bounds__(64 + 8 * 32, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-                 const ConvGemmParams p) {
-  using Cfg = ConvGemmCfg<BN, BK>;
+                 const __grid_constant__ CUtensorMap tmR, const ConvGemmParams p) {
+  using Cfg = ConvGemmCfg<BN, BK, kRes>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + S * Cfg::kABytes;
   const uint32_t sC = sB + S * Cfg::kBBytes;
-  const uint32_t sBias = sC + Cfg::kCBytes;
+  const uint32_t sBias = sC + Cfg::kCBufs * Cfg::kCBytes;
   const uint32_t sBar = sBias + Cfg::kBiasBytes;
   const uint32_t bar_full = sBar;                 // S x 8 B
   const uint32_t bar_empty = sBar + 8 * S;        // S x 8 B
   const uint32_t bar_tfull = sBar + 16 * S;       // 2 x 8 B
   const uint32_t bar_tempty = bar_tfull + 16;     // 2 x 8 B
-  const uint32_t tmem_slot = bar_tempty + 16;     // 4 B
+  const uint32_t bar_res = bar_tempty + 16;       // 2 x 8 B (residual tile landed in staging buffer i)
+  const uint32_t tmem_slot = bar_res + 16;        // 4 B
   uint8_t* const gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   float* const sBias_ptr = reinterpret_cast<float*>(gen_base + (sBias - smem_base));
 
@@ -95,13 +102,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
     if (p.kb_src0 < p.kb_total) tma_prefetch_desc(&tmA1);
+    if (kRes) tma_prefetch_desc(&tmR);
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 4);           // one arrive per epilogue warp
+      mbar_init(bar_tempty + 8 * a, Cfg::kEpiWarps);   // one arrive per epilogue warp
+      mbar_init(bar_res + 8 * a, 1);
     }
     fence_barrier_init();
   }
@@ -183,13 +192,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     __syncwarp();
   } else {
-    // ============================ epilogue (warps 2..5) ============================
+    // ============================ epilogue (warps 2..9) ============================
     const int q = warp & 3;                                    // TMEM lane quarter this warp may touch
     const int row = q * 32 + lane;                             // row of the 128-row tile
+    const int col_base = ((warp - 2) >> 2) * Cfg::kColsPerWarp;   // this warp's half of the tile's columns
+    constexpr int CH = Cfg::kChunk;                            // 32 or 16 columns per TMEM load
+    constexpr int NP = CH / 8;                                 // 16-B pieces per chunk
     const int epi_tid = threadIdx.x - 64;
     const bool store_leader = (threadIdx.x == 64);
     int acc = 0;
     uint32_t acc_phase = 0;
+    int cbuf = 0;                                              // staging buffer of this tile (kRes: alternates)
+    uint32_t res_phase = 0;
+    // residual tile of tile `tt` -> staging buffer `buf` (TMA, one tile ahead of its use)
+    auto prefetch_residual = [&](int tt, int buf) {
+      const int nb = tt % p.num_n_blks, mb = tt / p.num_n_blks;
+      const uint32_t bar = bar_res + 8 * buf;
+      mbar_arrive_expect_tx(bar, Cfg::kCBytes);
+#pragma unroll
+      for (int cc = 0; cc < BN / Cfg::kCS; ++cc)
+        tma_load_4d(&tmR, bar, sC + buf * Cfg::kCBytes + cc * Cfg::kCChunkBytes, nb * BN + cc * Cfg::kCS, mb * 128, 0, 0);
+    };
+    if (kRes && store_leader && int(blockIdx.x) < num_tiles) prefetch_residual(blockIdx.x, 0);
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int n_blk = t % p.num_n_blks;
       const int m_blk = t / p.num_n_blks;
@@ -200,32 +224,48 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int n0 = n_blk * BN;
       const int grow = w0 + row;                               // global row (2-D mode)
       const bool row_ok = grow < p.M;
+      const uint32_t sCt = sC + uint32_t(cbuf) * Cfg::kCBytes;
 
-      // staging smem + bias tile are reused: previous tile's TMA store must have read them
-      if (store_leader) tma_store_wait_read0();
-      for (int i = epi_tid; i < BN; i += 128) sBias_ptr[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
-      named_bar_sync(1, 128);
+      // staging smem + bias tile are reused: the TMA store that last read them must be done reading
+      if (store_leader) {
+        if (kRes) {
+          // buffer cbuf^1 (tile t-1's output) must be drained before tile t+1's residual lands in it
+          tma_store_wait_read0();
+          if (t + int(gridDim.x) < num_tiles) prefetch_residual(t + gridDim.x, cbuf ^ 1);
+        } else if (Cfg::kCBufs == 2) {
+          tma_store_wait_read1();                              // only tile t-2's store (same buffer) must be done
+        } else {
+          tma_store_wait_read0();
+        }
+      }
+      for (int i = epi_tid; i < BN; i += Cfg::kEpiThreads) sBias_ptr[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+      named_bar_sync(1, Cfg::kEpiThreads);
 
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tcgen05_fence_after();
+      if (kRes) mbar_wait(bar_res + 8 * cbuf, res_phase);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + c * 32), v);
-        uint4 rres[4];
-        const bool has_res = (p.residual != nullptr) && row_ok;
-        if (has_res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + size_t(grow) * p.ldr + n0 + c * 32);
+      for (int c = 0; c < Cfg::kColsPerWarp / CH; ++c) {
+        const int col = col_base + c * CH;
+        uint32_t v[CH];
+        tmem_ld_32x32b<CH>(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + col), v);
+        const uint32_t chunk_base = sCt + uint32_t(col / Cfg::kCS) * Cfg::kCChunkBytes;
+        const int piece0 = (col % Cfg::kCS) / 8;
+        uint4 rres[NP];
+        if (kRes) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) rres[i] = __ldg(rp + i);
+          for (int i = 0; i < NP; ++i) {
+            const uint32_t a = chunk_base + swizzle_off<Cfg::kCSwz>(uint32_t(row), uint32_t(piece0 + i));
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rres[i].x), "=r"(rres[i].y), "=r"(rres[i].z), "=r"(rres[i].w) : "r"(a));
+          }
         }
         tmem_ld_wait();
-        float f[32];
+        float f[CH];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + sBias_ptr[c * 32 + i];
-        if (has_res) {
+        for (int i = 0; i < CH; ++i) f[i] = __uint_as_float(v[i]) + sBias_ptr[col + i];
+        if (kRes) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < NP; ++i) {
             const __half2* h = reinterpret_cast<const __half2*>(&rres[i]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -237,21 +277,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         if (p.relu) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+          for (int i = 0; i < CH; ++i) f[i] = fmaxf(f[i], 0.f);
         }
         if (p.out_f32) {
           if (row_ok) {
-            float4* op = reinterpret_cast<float4*>(p.out_f32_ptr + size_t(grow) * p.ldo + n0 + c * 32);
+            float4* op = reinterpret_cast<float4*>(p.out_f32_ptr + size_t(grow) * p.ldo + n0 + col);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            for (int i = 0; i < CH / 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
           }
         } else {
           // chunk of kCS channels = one TMA store box; 16-B pieces land at their swizzled slot
-          const int col = c * 32;
-          const uint32_t chunk_base = sC + uint32_t(col / Cfg::kCS) * Cfg::kCChunkBytes;
-          const int piece0 = (col % Cfg::kCS) / 8;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < NP; ++i) {
             const uint32_t a = chunk_base + swizzle_off<Cfg::kCSwz>(uint32_t(row), uint32_t(piece0 + i));
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
                          "r"(pack_half2(f[8 * i], f[8 * i + 1])), "r"(pack_half2(f[8 * i + 2], f[8 * i + 3])),
@@ -268,15 +305,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
       // all epilogue threads are done with sBias / have written their staging rows
       if (!p.out_f32) fence_proxy_async_smem();
-      named_bar_sync(1, 128);
+      named_bar_sync(1, Cfg::kEpiThreads);
       if (!p.out_f32) {
         if (store_leader) {
 #pragma unroll
           for (int cc = 0; cc < BN / Cfg::kCS; ++cc)
-            tma_store_4d(&tmC, sC + cc * Cfg::kCChunkBytes, n0 + cc * Cfg::kCS, w0, h0, i0);
+            tma_store_4d(&tmC, sCt + cc * Cfg::kCChunkBytes, n0 + cc * Cfg::kCS, w0, h0, i0);
           tma_store_commit();
         }
       }
+      if (Cfg::kCBufs == 2) { cbuf ^= 1; if (cbuf == 0) res_phase ^= 1u; }
     }
     if (store_leader) tma_store_wait_all0();
   }

@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -141,17 +142,17 @@ static void choose_box(int H, int W, int B, int* bw, int* bh, int* bn) {
   *bw = bbw; *bh = bbh; *bn = 1;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool kRes>
 static int launch_cfg(const GemmOp& op, cudaStream_t st) {
-  using Cfg = ConvGemmCfg<BN, BK>;
+  using Cfg = ConvGemmCfg<BN, BK, kRes>;
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<BN, BK, kRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
     attr_set = true;
   }
   ConvGemmParams p;
   memset(&p, 0, sizeof p);
-  CUtensorMap tmA0, tmA1, tmB, tmC;
+  CUtensorMap tmA0, tmA1, tmB, tmC, tmR;
   const long long M = (long long)op.n * op.h * op.w;
   const bool conv = op.taps == 9;
   int rc;
@@ -174,6 +175,11 @@ static int launch_cfg(const GemmOp& op, cudaStream_t st) {
     if (!op.out_f32 && (rc = make_map_nhwc(&tmC, op.out, 1, 1, (int)M, op.cout, op.cout, Cfg::kCS, 128, 1, 1))) return rc;
   }
   if (op.out_f32) tmC = tmA0;
+  if (kRes) {
+    if ((rc = make_map_nhwc(&tmR, op.residual, 1, 1, (int)M, op.cout, op.cout, Cfg::kCS, 128, 1, 1))) return rc;
+  } else {
+    tmR = tmA0;
+  }
   if (op.a1) {
     if ((rc = make_map_nhwc(&tmA1, op.a1, 1, 1, (int)M, op.c1, op.c1, BK, 128, 1, 1))) return rc;
   } else {
@@ -191,15 +197,13 @@ static int launch_cfg(const GemmOp& op, cudaStream_t st) {
   p.M = (int)M;
   p.N = op.cout;
   p.bias = op.bias;
-  p.residual = reinterpret_cast<const __half*>(op.residual);
-  p.ldr = op.cout;
   p.out_f32_ptr = reinterpret_cast<float*>(op.out);
   p.ldo = op.cout;
   p.grp_n = op.grp_n; p.grp_a_koff = op.grp_a_koff; p.grp_b_koff = op.grp_b_koff; p.grp_b_nmod = op.grp_b_nmod;
   const long long tiles = (long long)p.num_m_blks * p.num_n_blks;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   if (grid <= 0) return 0;
-  conv_gemm_kernel<BN, BK><<<grid, 192, Cfg::kSmemBytes, st>>>(tmA0, tmA1, tmB, tmC, p);
+  conv_gemm_kernel<BN, BK, kRes><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmA0, tmA1, tmB, tmC, tmR, p);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -219,20 +223,20 @@ static int launch_gemm(const GemmOp& op, cudaStream_t st, int force_bn = 0) {
   int bn = force_bn ? force_bn : pick_bn(op.cout);
   if (op.grp_n && op.grp_n % bn) bn = op.grp_n % 64 == 0 ? 64 : 32;
   if (op.cout % bn) return fail(EMBCLIP_EINVAL, "cout %d not a multiple of tile N %d", op.cout, bn);
-  if (bk == 64) {
-    switch (bn) {
-      case 256: return launch_cfg<256, 64>(op, st);
-      case 128: return launch_cfg<128, 64>(op, st);
-      case 64: return launch_cfg<64, 64>(op, st);
-      case 32: return launch_cfg<32, 64>(op, st);
-    }
-  } else {
-    switch (bn) {
-      case 128: return launch_cfg<128, 32>(op, st);
-      case 64: return launch_cfg<64, 32>(op, st);
-      case 32: return launch_cfg<32, 32>(op, st);
-    }
-  }
+  const bool res = op.residual != nullptr;
+  static const int big_bn = getenv("EMBCLIP_BN256") ? atoi(getenv("EMBCLIP_BN256")) : 0;
+  if (big_bn && !force_bn && !res && !op.grp_n && op.cout % 256 == 0 && bk == 64) bn = 256;
+  if (res && bn > 128) bn = 128;                       // residual variant double-buffers the staging tile
+#define EMBCLIP_CASE(BN_, BK_) \
+  if (bn == BN_ && bk == BK_) return res ? launch_cfg<BN_, BK_, true>(op, st) : launch_cfg<BN_, BK_, false>(op, st);
+  if (bn == 256 && bk == 64) return launch_cfg<256, 64, false>(op, st);   // (no residual variant: staging would not fit)
+  EMBCLIP_CASE(128, 64)
+  EMBCLIP_CASE(64, 64)
+  EMBCLIP_CASE(32, 64)
+  EMBCLIP_CASE(128, 32)
+  EMBCLIP_CASE(64, 32)
+  EMBCLIP_CASE(32, 32)
+#undef EMBCLIP_CASE
   return fail(EMBCLIP_EINVAL, "no kernel for tile N %d K %d", bn, bk);
 }
 
@@ -430,6 +434,7 @@ extern "C" int embclip_rn50_create(const embclip_rn50_cfg* cfg, embclip_rn50_t* 
 
   // ---- bottleneck stages
   int inplanes = width;
+  (void)inplanes;
   for (int li = 0; li < 4; ++li) {
     const int planes = width << li;
     for (int bi = 0; bi < cfg->layers[li]; ++bi) {
