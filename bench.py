@@ -271,7 +271,7 @@ def run_ours(args, rank, local_rank, world):
     step_tflops = (FLOP_TRUNK + FLOP_ATTNPOOL_MIN) * BATCH / (ms_step * 1e-3) / 1e12
     top = sorted(prof, key=lambda x: -x[1])[:8]
 
-    cpu_fps, cpu_sec = time_cpu_oracle(oracle_model(), 32, 4, 1)
+    cpu_fps, cpu_sec = (None, None) if args.no_cpu else time_cpu_oracle(oracle_model(), 32, 4, 1)
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -303,6 +303,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiler runs only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
