@@ -46,7 +46,7 @@ SIGNATURES = {
     "embclip_rn50_launches_per_forward": (_I, [_VP, _I, _I, _I]),
     "embclip_gemm_f16": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "embclip_gemm_grouped_f16": (_I, [_VP, _I, _VP, _I, _I, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP]),
-    "embclip_conv3x3_f16": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
+    "embclip_conv3x3_f16": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "embclip_avgpool2_f16": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
     "embclip_stem_conv1": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
 }

@@ -1,0 +1,304 @@
+// conv3x3_halo: 3x3 / pad 1 / stride 1 convolution (+ folded BN bias, ReLU, optional fused 2x2 average pool)
+// as an implicit GEMM whose A operand is a HALO STRIP resident in shared memory.
+//
+// The first version of this path loaded the activation box nine times (once per tap); the ncu capture in
+// profiles/r1a_conv_gemm_full.txt shows the consequence: L2->SM traffic 9x the input and the tensor pipe 17 %
+// busy.  Here one TMA box per 64-channel chunk brings a strip of rows [h0-1, h0+R] x cols [-1, W-1] (TMA's
+// out-of-bounds zero fill supplies the padding) into smem as a flat list of "padded pixels", one swizzled
+// row of KC channels each, Wp = W + 1 pixels per image row.  With output position  p = r*Wp + w  the input
+// pixel of tap (kh, kw) is simply row  p + kh*Wp + kw  of that list, so each tap's A operand is the SAME
+// smem plane viewed through a UMMA descriptor whose start address is shifted by (kh*Wp + kw) rows.
+// (tools/exp_baseoffset.cu verified on B200 that a K-major swizzled operand may start at any row with
+// base_offset = 0: the swizzle XOR is taken from absolute smem address bits.)  Positions with w == W, and the
+// rows between images, produce junk accumulator rows that the epilogue simply does not store.
+//
+// * MS sub-tiles of 128 positions share every weight stage (MS x BN accumulator columns, double buffered in
+//   TMEM), which divides the weight traffic per MAC by MS; the strip is read from L2 (R+2)/R times, not 9.
+// * Small images ("images" geometry): G whole images per tile, each (H+1) rows -- the zero row under image g
+//   doubles as the zero row above image g+1.
+// * K loop is chunk-major / tap-minor: a plane is released after its 9 taps so the next tile's plane for the
+//   same chunk streams in while later chunks compute.  Planes and weight stages have separate producers.
+// * Warp roles (384 threads): warp 0 = weight (B) producer, warp 1 = TMEM owner + MMA issuer, warp 2 = plane
+//   (A) producer, warp 3 idle, warps 4..11 = epilogue (TMEM -> regs -> bias/ReLU -> fp16 -> global, or ->
+//   smem strip -> 2x2 average -> global when the pool is fused).
+#pragma once
+#include "ptx.cuh"
+
+namespace embclip {
+
+struct Conv3Params {
+  int num_m_tiles, num_n_blks;
+  int strips_per_image;        // "rows" geometry: ceil(H / R); "images" geometry: 0
+  int R;                       // valid output rows per group (rows: strip height; images: H)
+  int G;                       // image groups per tile (rows: 1)
+  int BHo;                     // plane rows per group (rows: R + 2; images: H + 1)
+  int H, W, Wp, B;
+  int C;                       // input channels
+  int chunks;                  // C / KC
+  int n_a, n_b;                // ring depths: planes, weight stages
+  uint32_t plane_bytes;        // allocation per plane (multiple of 1024)
+  uint32_t plane_tx_bytes;     // bytes one plane's TMA box delivers
+  uint32_t plane_rows_tma;     // rows written by TMA; rows [plane_rows_tma, plane_rows_alloc) are zeroed once
+  uint32_t plane_rows_alloc;
+  int relu;
+  int N;                       // Cout
+  int pool;                    // 1: write avgpool2(relu(conv)) [B, H/2, W/2, N] instead of the full-resolution map
+  const float* bias;
+  __half* out;
+};
+
+constexpr int kC3Threads = 384;
+constexpr int kC3EpiWarps = 8;
+constexpr int kC3EpiThreads = kC3EpiWarps * 32;
+constexpr int kC3MaxA = 4, kC3MaxB = 16;
+constexpr int kC3BarBytes = 512;
+
+template <int BN, int MS, int KC, bool kPool>
+__global__ void __launch_bounds__(kC3Threads, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Conv3Params p) {
+  constexpr int SWZ = KC * 2;
+  constexpr int kBBytes = BN * SWZ;
+  constexpr int kAccCols = MS * BN;
+  constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;
+  static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "accumulators must fit TMEM (power of two)");
+  static_assert(KC == 64 || KC == 32, "chunk = one swizzle span");
+  static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "UMMA N");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + uint32_t(p.n_a) * p.plane_bytes;
+  const uint32_t sBar = sB + uint32_t(p.n_b) * kBBytes;
+  const uint32_t sStage = sBar + kC3BarBytes;                  // kPool: fp16 strip [MS*128][BN], row pitch BN*2 + 16
+  const uint32_t bar_afull = sBar, bar_aempty = sBar + 8 * kC3MaxA;
+  const uint32_t bar_bfull = sBar + 16 * kC3MaxA, bar_bempty = bar_bfull + 8 * kC3MaxB;
+  const uint32_t bar_tfull = bar_bempty + 8 * kC3MaxB, bar_tempty = bar_tfull + 16;
+  const uint32_t tmem_slot = bar_tempty + 16;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_blks;
+
+  // rows of every plane that TMA never writes must read as zero (right pad of the last row + MMA window slack)
+  {
+    const uint32_t tail_rows = p.plane_rows_alloc - p.plane_rows_tma;
+    const uint32_t vec_per_plane = tail_rows * (SWZ / 16);
+    for (uint32_t i = threadIdx.x; i < vec_per_plane * uint32_t(p.n_a); i += blockDim.x) {
+      const uint32_t pl = i / vec_per_plane, v = i - pl * vec_per_plane;
+      *reinterpret_cast<uint4*>(gen_base + size_t(pl) * p.plane_bytes + size_t(p.plane_rows_tma) * SWZ + size_t(v) * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.n_a; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
+    for (int s = 0; s < p.n_b; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, kC3EpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  auto tile_coords = [&](int t, int& n_blk, int& img0, int& h0) {
+    n_blk = t % p.num_n_blks;
+    const int m_tile = t / p.num_n_blks;
+    if (p.strips_per_image) { img0 = m_tile / p.strips_per_image; h0 = (m_tile - img0 * p.strips_per_image) * p.R; }
+    else { img0 = m_tile * p.G; h0 = 0; }
+  };
+
+  if (warp == 0) {
+    // ============================ weight (B) producer ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int n_blk = t % p.num_n_blks;
+        for (int c = 0; c < p.chunks; ++c) {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(bar_bempty + 8 * stage, phase ^ 1u);
+            const uint32_t full = bar_bfull + 8 * stage;
+            mbar_arrive_expect_tx(full, kBBytes);
+            tma_load_2d(&tmB, full, sB + stage * kBBytes, tap * p.C + c * KC, n_blk * BN);
+            if (++stage == p.n_b) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ============================ plane (A) producer ============================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int n_blk, img0, h0;
+        tile_coords(t, n_blk, img0, h0);
+        for (int c = 0; c < p.chunks; ++c) {
+          mbar_wait(bar_aempty + 8 * slot, phase ^ 1u);
+          const uint32_t full = bar_afull + 8 * slot;
+          mbar_arrive_expect_tx(full, p.plane_tx_bytes);
+          tma_load_4d(&tmA, full, sA + uint32_t(slot) * p.plane_bytes, c * KC, -1, h0 - 1, img0);
+          if (++slot == p.n_a) { slot = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16_f32(128, BN);
+      int stage = 0, slot = 0, acc = 0;
+      uint32_t bphase = 0, aphase = 0, acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * kAccCols);
+        for (int c = 0; c < p.chunks; ++c) {
+          mbar_wait(bar_afull + 8 * slot, aphase);
+          const uint32_t plane = sA + uint32_t(slot) * p.plane_bytes;
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(bar_bfull + 8 * stage, bphase);
+            tcgen05_fence_after();
+            const int kh = tap / 3, kw = tap - kh * 3;
+            const uint32_t a_tap = plane + uint32_t(kh * p.Wp + kw) * SWZ;
+            const uint64_t b_desc = make_kmajor_desc<SWZ>(sB + stage * kBBytes);
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k) {
+#pragma unroll
+              for (int s = 0; s < MS; ++s) {
+                const uint64_t a_desc = make_kmajor_desc<SWZ>(a_tap + uint32_t(s * 128) * SWZ);
+                umma_f16_ss(d_tmem + uint32_t(s * BN), a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc,
+                            uint32_t((c | tap | k) != 0));
+              }
+            }
+            umma_commit(bar_bempty + 8 * stage);
+            if (++stage == p.n_b) { stage = 0; bphase ^= 1u; }
+          }
+          umma_commit(bar_aempty + 8 * slot);                  // plane free once its 9 taps have retired
+          if (++slot == p.n_a) { slot = 0; aphase ^= 1u; }
+        }
+        umma_commit(bar_tfull + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ============================ epilogue (warps 4..11) ============================
+    const int q = warp & 3;                                    // TMEM lane quarter
+    const int row = q * 32 + lane;
+    constexpr int kColsPerWarp = BN / 2;
+    constexpr int CH = kColsPerWarp < 32 ? kColsPerWarp : 32;
+    const int col_base = ((warp - 4) >> 2) * kColsPerWarp;
+    constexpr uint32_t kStagePitch = BN * 2 + 16;              // bytes; +16 spreads rows over banks
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int n_blk, img0, h0;
+      tile_coords(t, n_blk, img0, h0);
+      const int n0 = n_blk * BN;
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int s = 0; s < MS; ++s) {
+        const int pos = s * 128 + row;
+        const int prow = pos / p.Wp;
+        const int w = pos - prow * p.Wp;
+        const int g = prow / p.BHo;
+        const int r = prow - g * p.BHo;
+        const bool valid = w < p.W && r < p.R && g < p.G && h0 + r < p.H && img0 + g < p.B;
+        __half* optr = p.out + ((size_t(img0 + g) * p.H + (h0 + r)) * p.W + w) * p.N + n0;
+#pragma unroll 1
+        for (int c = 0; c < kColsPerWarp / CH; ++c) {
+          const int col = col_base + c * CH;
+          uint32_t v[CH];
+          tmem_ld_32x32b<CH>(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * kAccCols + s * BN + col), v);
+          float bv[CH];
+#pragma unroll
+          for (int i = 0; i < CH / 4; ++i) {
+            const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col) + i) : make_float4(0, 0, 0, 0);
+            bv[4 * i] = b4.x; bv[4 * i + 1] = b4.y; bv[4 * i + 2] = b4.z; bv[4 * i + 3] = b4.w;
+          }
+          tmem_ld_wait();
+          uint32_t h2[CH / 2];
+#pragma unroll
+          for (int i = 0; i < CH / 2; ++i) {
+            float a = __uint_as_float(v[2 * i]) + bv[2 * i], b = __uint_as_float(v[2 * i + 1]) + bv[2 * i + 1];
+            if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+            h2[i] = pack_half2(a, b);
+          }
+          if constexpr (kPool) {
+            const uint32_t a = sStage + uint32_t(pos) * kStagePitch + uint32_t(col) * 2;
+#pragma unroll
+            for (int i = 0; i < CH / 8; ++i)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 16 * i), "r"(h2[4 * i]), "r"(h2[4 * i + 1]),
+                           "r"(h2[4 * i + 2]), "r"(h2[4 * i + 3]) : "memory");
+          } else if (valid) {
+            uint4* o = reinterpret_cast<uint4*>(optr + col);
+#pragma unroll
+            for (int i = 0; i < CH / 8; ++i) o[i] = make_uint4(h2[4 * i], h2[4 * i + 1], h2[4 * i + 2], h2[4 * i + 3]);
+          }
+        }
+      }
+      // accumulator drained -> MMA warp may overwrite it
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+
+      if constexpr (kPool) {
+        // strip [positions][BN] fp16 is complete in smem: every epilogue thread averages 2x2 quads, 8 channels at a time
+        named_bar_sync(1, kC3EpiThreads);
+        const int Wo = p.W >> 1, Ho = p.H >> 1, Ro = p.R >> 1;
+        constexpr int V = BN / 8;                               // 16-B vectors per pixel
+        const int total = p.G * Ro * Wo * V;
+        for (int i = threadIdx.x - 128; i < total; i += kC3EpiThreads) {
+          const int v = i % V;
+          int rest = i / V;
+          const int wo = rest % Wo;
+          rest /= Wo;
+          const int ro = rest % Ro;
+          const int g = rest / Ro;
+          const int ho = (h0 >> 1) + ro;
+          if (ho >= Ho || img0 + g >= p.B) continue;
+          const int pos = (g * p.BHo + 2 * ro) * p.Wp + 2 * wo;
+          const uint32_t a = sStage + uint32_t(pos) * kStagePitch + uint32_t(v) * 16;
+          float s8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t aj = a + uint32_t((j >> 1) * p.Wp + (j & 1)) * kStagePitch;
+            uint4 x;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(aj));
+            const __half2* hx = reinterpret_cast<const __half2*>(&x);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = __half22float2(hx[k]);
+              s8[2 * k] += f.x;
+              s8[2 * k + 1] += f.y;
+            }
+          }
+          uint4 o;
+          o.x = pack_half2(s8[0] * .25f, s8[1] * .25f);
+          o.y = pack_half2(s8[2] * .25f, s8[3] * .25f);
+          o.z = pack_half2(s8[4] * .25f, s8[5] * .25f);
+          o.w = pack_half2(s8[6] * .25f, s8[7] * .25f);
+          *reinterpret_cast<uint4*>(p.out + ((size_t(img0 + g) * Ho + ho) * Wo + wo) * p.N + n0 + v * 8) = o;
+        }
+        named_bar_sync(1, kC3EpiThreads);                       // strip may be overwritten by the next tile
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace embclip

@@ -14,6 +14,7 @@
 #include "../../include/embclip_b200.h"
 #include "aux_kernels.cuh"
 #include "conv_gemm.cuh"
+#include "conv3x3_halo.cuh"
 
 using namespace embclip;
 
@@ -37,7 +38,7 @@ static int fail(int code, const char* fmt, ...) {
   } while (0)
 
 extern "C" const char* embclip_last_error(void) { return g_err.c_str(); }
-extern "C" int embclip_abi_version(void) { return 1; }
+extern "C" int embclip_abi_version(void) { return 2; }
 
 // =============================================================================================
 // TMA descriptors (driver entry point resolved at run time: the library links only against cudart)
@@ -241,6 +242,126 @@ static int launch_gemm(const GemmOp& op, cudaStream_t st, int force_bn = 0) {
 }
 
 // =============================================================================================
+// conv3x3_halo launcher: geometry (strip / image packing), ring depths, kernel variant
+// =============================================================================================
+struct C3Geom {
+  int R, G, BH, BHo, strips, tiles, Wp;
+  uint32_t rows_tma, rows_alloc;
+  double eff;
+};
+static bool c3_geometry(int B, int H, int W, int MS, bool pool, C3Geom* g) {
+  const int Wp = W + 1, cap = MS * 128;
+  g->Wp = Wp;
+  if (Wp > 256) return false;
+  if ((H - 1) * Wp + W - 1 < cap) {               // whole images: G per tile, (H+1) rows each
+    int G = (cap - ((H - 1) * Wp + W)) / ((H + 1) * Wp) + 1;
+    if (G > B) G = B;
+    if (H + 1 > 256 || G > 256) return false;
+    g->R = H; g->G = G; g->BH = H + 1; g->BHo = H + 1; g->strips = 0;
+    g->tiles = (B + G - 1) / G;
+    g->rows_tma = uint32_t(G) * (H + 1) * Wp;
+    g->eff = double(B) * H * W / (double(g->tiles) * cap);
+  } else {                                        // row strips of one image
+    int R = (cap - W) / Wp + 1;
+    if (pool) R &= ~1;
+    if (R < (pool ? 2 : 1)) return false;
+    const int strips = (H + R - 1) / R;
+    R = (H + strips - 1) / strips;
+    if (pool && (R & 1)) ++R;
+    if ((R - 1) * Wp + W - 1 >= cap || R + 2 > 256) return false;
+    g->R = R; g->G = 1; g->BH = R + 2; g->BHo = R + 2; g->strips = strips;
+    g->tiles = B * strips;
+    g->rows_tma = uint32_t(R + 2) * Wp;
+    g->eff = double(B) * H * W / (double(g->tiles) * cap);
+  }
+  uint32_t need = uint32_t(cap + 2 * Wp + 2);
+  if (need < g->rows_tma) need = g->rows_tma;
+  g->rows_alloc = (need + 15u) & ~15u;
+  return true;
+}
+
+struct Conv3Op {
+  const void* in; const void* wgt; const float* bias; void* out;
+  int B, H, W, C, N, relu, pool;
+};
+
+template <int BN, int MS, int KC, bool kPool>
+static int launch_c3_cfg(const Conv3Op& op, const C3Geom& g, cudaStream_t st) {
+  constexpr int SWZ = KC * 2;
+  constexpr uint32_t kBBytes = BN * SWZ;
+  const uint32_t plane_bytes = (g.rows_alloc * SWZ + 1023u) & ~1023u;
+  const uint32_t stage_bytes = kPool ? uint32_t(MS) * 128u * (BN * 2 + 16) : 0u;
+  const uint32_t budget = 227u * 1024u - 1024u - kC3BarBytes - stage_bytes;
+  const int chunks = op.C / KC;
+  static const int env_na = getenv("EMBCLIP_C3_NA") ? atoi(getenv("EMBCLIP_C3_NA")) : 0;
+  int n_a = 2;
+  if (2u * plane_bytes + 3u * kBBytes > budget) return fail(EMBCLIP_EINVAL, "conv3x3: strip does not fit shared memory (plane %u B)", plane_bytes);
+  int n_b = int((budget - 2u * plane_bytes) / kBBytes);
+  if (chunks > 1 && n_b >= 6 + int(plane_bytes / kBBytes)) { n_a = 3; n_b -= int((plane_bytes + kBBytes - 1) / kBBytes); }
+  if (env_na >= 2 && env_na <= kC3MaxA && uint32_t(env_na) * plane_bytes + 4u * kBBytes <= budget) {
+    n_a = env_na;
+    n_b = int((budget - uint32_t(n_a) * plane_bytes) / kBBytes);
+  }
+  if (n_b > 12) n_b = 12;
+  const size_t smem = 1024 + size_t(n_a) * plane_bytes + size_t(n_b) * kBBytes + kC3BarBytes + stage_bytes;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    CUDA_TRY(cudaFuncSetAttribute(conv3x3_halo_kernel<BN, MS, KC, kPool>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_map_nhwc(&tmA, op.in, op.B, op.H, op.W, op.C, op.C, KC, g.Wp, g.BH, g.G))) return rc;
+  if ((rc = make_map_2d(&tmB, op.wgt, op.N, 9 * op.C, 9 * op.C, KC, BN))) return rc;
+  Conv3Params p;
+  memset(&p, 0, sizeof p);
+  p.num_m_tiles = g.tiles; p.num_n_blks = op.N / BN;
+  p.strips_per_image = g.strips; p.R = g.R; p.G = g.G; p.BHo = g.BHo;
+  p.H = op.H; p.W = op.W; p.Wp = g.Wp; p.B = op.B; p.C = op.C; p.chunks = chunks;
+  p.n_a = n_a; p.n_b = n_b;
+  p.plane_bytes = plane_bytes; p.plane_tx_bytes = g.rows_tma * SWZ;
+  p.plane_rows_tma = g.rows_tma; p.plane_rows_alloc = plane_bytes / SWZ;
+  p.relu = op.relu; p.N = op.N; p.pool = op.pool;
+  p.bias = op.bias; p.out = reinterpret_cast<__half*>(op.out);
+  const long long tiles = (long long)p.num_m_tiles * p.num_n_blks;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  if (grid <= 0) return 0;
+  conv3x3_halo_kernel<BN, MS, KC, kPool><<<grid, kC3Threads, smem, st>>>(tmA, tmB, p);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int launch_conv3x3_halo(const Conv3Op& op, cudaStream_t st) {
+  if (op.C % 32 || op.N % 32) return fail(EMBCLIP_EINVAL, "conv3x3: channels must be multiples of 32 (cin %d cout %d)", op.C, op.N);
+  if (op.pool && ((op.H | op.W) & 1)) return fail(EMBCLIP_EINVAL, "conv3x3: fused 2x2 pool needs even H, W");
+  const int kc = op.C % 64 == 0 ? 64 : 32;
+  static const int env_bn = getenv("EMBCLIP_C3_BN") ? atoi(getenv("EMBCLIP_C3_BN")) : 0;
+  static const int env_ms = getenv("EMBCLIP_C3_MS") ? atoi(getenv("EMBCLIP_C3_MS")) : 0;
+  int bn = op.N % 128 == 0 ? 128 : (op.N % 64 == 0 ? 64 : 32);
+  if (env_bn && op.N % env_bn == 0 && env_bn >= 128 && op.N % 128 == 0) bn = env_bn;
+  int ms = bn == 256 ? 1 : (bn == 128 ? 2 : 4);
+  if (env_ms && env_ms * bn * 2 <= 512) ms = env_ms;
+  C3Geom g;
+  for (;; ms >>= 1) {
+    if (ms < 1) return fail(EMBCLIP_EINVAL, "conv3x3: no strip geometry for H %d W %d", op.H, op.W);
+    if (!c3_geometry(op.B, op.H, op.W, ms, op.pool != 0, &g)) continue;
+    const uint32_t plane = ((g.rows_alloc * (kc * 2)) + 1023u) & ~1023u;
+    const uint32_t stage = op.pool ? uint32_t(ms) * 128u * (bn * 2 + 16) : 0u;
+    if (2u * plane + 3u * uint32_t(bn * kc * 2) + stage + 1024u + kC3BarBytes <= 227u * 1024u) break;
+  }
+#define EMBCLIP_C3(BN_, MS_, KC_) \
+  if (bn == BN_ && ms == MS_ && kc == KC_) \
+    return op.pool ? launch_c3_cfg<BN_, MS_, KC_, true>(op, g, st) : launch_c3_cfg<BN_, MS_, KC_, false>(op, g, st);
+  EMBCLIP_C3(32, 4, 32) EMBCLIP_C3(32, 2, 32) EMBCLIP_C3(32, 1, 32)
+  EMBCLIP_C3(64, 4, 32) EMBCLIP_C3(64, 2, 32) EMBCLIP_C3(64, 1, 32)
+  EMBCLIP_C3(64, 4, 64) EMBCLIP_C3(64, 2, 64) EMBCLIP_C3(64, 1, 64)
+  EMBCLIP_C3(128, 2, 64) EMBCLIP_C3(128, 1, 64)
+  EMBCLIP_C3(256, 1, 64)
+#undef EMBCLIP_C3
+  return fail(EMBCLIP_EINVAL, "conv3x3: no kernel for tile N %d x %d sub-tiles, chunk %d", bn, ms, kc);
+}
+
+// =============================================================================================
 // primitive-op entry points
 // =============================================================================================
 extern "C" int embclip_gemm_f16(const void* a0, const void* a1, const void* w, const float* bias, const void* residual,
@@ -267,13 +388,18 @@ extern "C" int embclip_gemm_grouped_f16(const void* a, int lda, const void* w, i
 }
 
 extern "C" int embclip_conv3x3_f16(const void* in, const void* w, const float* bias, void* out, int B, int H, int W,
-                                   int Cin, int Cout, int relu, void* stream) {
+                                   int Cin, int Cout, int relu, int pool, void* stream) {
   if (!in || !w || !out || B <= 0) return fail(EMBCLIP_EINVAL, "conv3x3: null pointer or empty batch");
-  GemmOp op;
-  op.a0 = in; op.n = B; op.h = H; op.w = W; op.c0 = Cin; op.lda0 = Cin; op.taps = 9;
-  op.wgt = w; op.ldw = 9 * Cin; op.w_rows = Cout;
-  op.bias = bias; op.out = out; op.cout = Cout; op.relu = relu;
-  return launch_gemm(op, (cudaStream_t)stream);
+  static const bool legacy = getenv("EMBCLIP_CONV3_LEGACY") != nullptr;   // 9-box-loads implicit GEMM (first version), for A/B timing
+  if (legacy && !pool) {
+    GemmOp op;
+    op.a0 = in; op.n = B; op.h = H; op.w = W; op.c0 = Cin; op.lda0 = Cin; op.taps = 9;
+    op.wgt = w; op.ldw = 9 * Cin; op.w_rows = Cout;
+    op.bias = bias; op.out = out; op.cout = Cout; op.relu = relu;
+    return launch_gemm(op, (cudaStream_t)stream);
+  }
+  Conv3Op op{in, w, bias, out, B, H, W, Cin, Cout, relu, pool};
+  return launch_conv3x3_halo(op, (cudaStream_t)stream);
 }
 
 static int launch_avgpool2(const void* in, void* out, int B, int H, int W, int C, cudaStream_t st) {
@@ -333,6 +459,7 @@ struct Op {
   int in0 = -1, in1 = -1, res = -1, out = -1;   // Act ids (-1: none; out -2/-3/-4: external outputs)
   int wp = -1, bp = -1;          // Param ids
   int taps = 1, c0 = 0, c1 = 0, cout = 0, relu = 0, out_f32 = 0;
+  int pool = 0;                  // 3x3 only: 2x2 average pool fused into the epilogue
   int rows_mode = 0;             // 0: M = B*h*w of in0;  1: M = B (one row per image)
   int lda0 = 0, a_cols = 0, ldw = 0, w_rows = 0;
   int grp_n = 0, grp_a_koff = 0, grp_b_koff = 0, grp_b_nmod = 0;
@@ -373,7 +500,7 @@ static int add_param(embclip_rn50* m, const std::string& name, int dtype, std::i
 }
 // conv (+folded BN) as GEMM: weights fp16 [cout, taps*c0 + c1], bias fp32 [cout]
 static int add_conv(embclip_rn50* m, const std::string& name, int in0, int in1, int res, int taps, int cout, int relu,
-                    int out_f32 = 0) {
+                    int out_f32 = 0, int pool = 0) {
   const Act& a = m->acts[in0];
   Op op;
   op.kind = K_GEMM;
@@ -384,7 +511,9 @@ static int add_conv(embclip_rn50* m, const std::string& name, int in0, int in1, 
   op.ldw = taps * op.c0 + op.c1; op.w_rows = cout;
   op.wp = add_param(m, name + ".w", EMBCLIP_DTYPE_F16, {cout, op.ldw});
   op.bp = add_param(m, name + ".b", EMBCLIP_DTYPE_F32, {cout});
-  op.out = add_act(m, name, out_f32 ? EMBCLIP_DTYPE_F32 : EMBCLIP_DTYPE_F16, a.h, a.w, cout);
+  op.pool = pool;
+  const int oh = pool ? a.h / 2 : a.h, ow = pool ? a.w / 2 : a.w;   // (a is a reference into m->acts: read before add_act)
+  op.out = add_act(m, name, out_f32 ? EMBCLIP_DTYPE_F32 : EMBCLIP_DTYPE_F16, oh, ow, cout);
   m->ops.push_back(op);
   return op.out;
 }
@@ -429,8 +558,7 @@ extern "C" int embclip_rn50_create(const embclip_rn50_cfg* cfg, embclip_rn50_t* 
   }
   int t = (int)m->acts.size() - 1;
   t = add_conv(m, "stem.conv2", t, -1, -1, 9, width / 2, 1);
-  t = add_conv(m, "stem.conv3", t, -1, -1, 9, width, 1);
-  t = add_pool(m, "stem.pool", t);
+  t = add_conv(m, "stem.conv3", t, -1, -1, 9, width, 1, 0, /*pool=*/1);   // AvgPool2d(2) fused into the epilogue
 
   // ---- bottleneck stages
   int inplanes = width;
@@ -446,12 +574,9 @@ extern "C" int embclip_rn50_create(const embclip_rn50_cfg* cfg, embclip_rn50_t* 
       const std::string P(pfx);
       const int x = t;
       int a = add_conv(m, P + ".conv1", x, -1, -1, 1, planes, 1);
-      int b = add_conv(m, P + ".conv2", a, -1, -1, 9, planes, 1);
+      int b = add_conv(m, P + ".conv2", a, -1, -1, 9, planes, 1, 0, /*pool=*/stride == 2);   // avgpool(stride) fused
       int xp = x;
-      if (stride == 2) {
-        b = add_pool(m, P + ".pool", b);
-        xp = add_pool(m, P + ".xpool", x);
-      }
+      if (stride == 2) xp = add_pool(m, P + ".xpool", x);
       // conv3 (+ downsample conv fused along K when the block has one, else identity residual)
       if (down) t = add_conv(m, P + ".conv3", b, xp, -1, 1, planes * 4, 1, last ? 1 : 0);
       else      t = add_conv(m, P + ".conv3", b, -1, x, 1, planes * 4, 1, last ? 1 : 0);
@@ -577,6 +702,10 @@ static int run_op(embclip_rn50* m, const Op& op, const std::vector<uint64_t>& of
     }
     case K_GEMM: {
       const Act& a = m->acts[op.in0];
+      if (op.taps == 9) {
+        Conv3Op c{act_ptr(op.in0), param_ptr(op.wp), (const float*)param_ptr(op.bp), act_ptr(op.out), B, a.h, a.w, op.c0, op.cout, op.relu, op.pool};
+        return launch_conv3x3_halo(c, st);
+      }
       GemmOp g;
       g.a0 = act_ptr(op.in0);
       if (op.rows_mode == 1) { g.n = 1; g.h = 1; g.w = B; }

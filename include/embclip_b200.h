@@ -113,10 +113,12 @@ int embclip_gemm_f16(const void* a0, const void* a1, const void* w, const float*
 int embclip_gemm_grouped_f16(const void* a, int lda, const void* w, int ldw, int w_rows, const float* bias,
                              void* out, int M, int N, int K, int grp_n, int grp_a_koff, int grp_b_koff,
                              int grp_b_nmod, int relu, int out_f32, void* stream);
-/* 3x3 / pad 1 / stride 1 conv, NHWC: in [B,H,W,Cin], w [Cout, 9*Cin] (tap-major: kh, kw, cin), out [B,H,W,Cout].
- * Replaces nn.Conv2d(k=3, padding=1) + folded BatchNorm + ReLU of clip/model.py Bottleneck / stem. */
+/* 3x3 / pad 1 / stride 1 conv, NHWC: in [B,H,W,Cin], w [Cout, 9*Cin] (tap-major: kh, kw, cin), out [B,H,W,Cout];
+ * pool != 0 fuses the nn.AvgPool2d(2) that follows it in the anti-aliased strided Bottleneck / the stem:
+ * out [B,H/2,W/2,Cout] = avgpool2(act(conv)) (H, W even).  Replaces nn.Conv2d(k=3, padding=1) + folded
+ * BatchNorm + ReLU (+ AvgPool2d) of clip/model.py Bottleneck / ModifiedResNet stem. */
 int embclip_conv3x3_f16(const void* in, const void* w, const float* bias, void* out, int B, int H, int W,
-                        int Cin, int Cout, int relu, void* stream);
+                        int Cin, int Cout, int relu, int pool, void* stream);
 /* 2x2 average pool, NHWC fp16 (nn.AvgPool2d(2) of clip/model.py). */
 int embclip_avgpool2_f16(const void* in, void* out, int B, int H, int W, int C, void* stream);
 /* Stem conv1: fp32 NHWC [B,R,R,3] -> fp16 NHWC [B,R/2,R/2,Cout]; w fp32 [27, Cout] (kh,kw,cin major), bias fp32. */

@@ -66,19 +66,21 @@ def rn50_fp16_path(m: ModifiedResNet, frames_nchw: torch.Tensor, quantize: bool 
     # stem conv1 runs on CUDA cores from the fp32 frames with fp32 weights; only its output is rounded
     x = put("stem.conv1", cbr(frames_nchw, m.conv1, m.bn1, round_w=False))
     x = put("stem.conv2", cbr(x, m.conv2, m.bn2))
-    x = put("stem.conv3", cbr(x, m.conv3, m.bn3))
-    x = put("stem.pool", q(F.avg_pool2d(x, 2)))
+    # AvgPool2d(2) is fused into conv3's epilogue: the full-resolution map is rounded to fp16, averaged in fp32
+    # and rounded once more (same rounding points as the separate pool kernel it replaced)
+    x = put("stem.conv3", q(F.avg_pool2d(cbr(x, m.conv3, m.bn3), 2)))
     stages = [m.layer1, m.layer2, m.layer3, m.layer4]
     for li, layer in enumerate(stages):
         for bi, blk in enumerate(layer):
             p = f"layer{li + 1}.{bi}"
             last = li == 3 and bi == len(layer) - 1
             a = put(p + ".conv1", cbr(x, blk.conv1, blk.bn1))
-            b = put(p + ".conv2", cbr(a, blk.conv2, blk.bn2))
+            b = cbr(a, blk.conv2, blk.bn2)
             xp = x
-            if blk.stride > 1:
-                b = put(p + ".pool", q(F.avg_pool2d(b, blk.stride)))
+            if blk.stride > 1:                      # anti-aliased stride: avgpool fused into conv2's epilogue
+                b = q(F.avg_pool2d(b, blk.stride))
                 xp = put(p + ".xpool", q(F.avg_pool2d(x, blk.stride)))
+            b = put(p + ".conv2", b)
             if blk.downsample is not None:
                 wd, bd = _fold(blk.downsample[1], blk.downsample[2])
                 idn = F.conv2d(xp, q(wd)) + bd[None, :, None, None]      # fused along K: never rounded on its own

@@ -136,16 +136,35 @@ def test_gemm_grouped(lib):
     (1, 10, 12, 32, 96),     # odd spatial size, N tile 32 x 3
 ])
 def test_conv3x3(lib, B, H, W, Cin, Cout):
+    _conv3x3_case(lib, B, H, W, Cin, Cout, pool=False)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [
+    (2, 112, 112, 32, 64),   # stem conv3 + pool
+    (3, 56, 56, 128, 128),   # layer2.0 conv2 + pool
+    (3, 28, 28, 256, 256),   # layer3.0
+    (5, 14, 14, 512, 512),   # layer4.0: whole images per tile
+    (2, 12, 20, 64, 64),     # odd strip split
+])
+def test_conv3x3_fused_pool(lib, B, H, W, Cin, Cout):
+    _conv3x3_case(lib, B, H, W, Cin, Cout, pool=True)
+
+
+def _conv3x3_case(lib, B, H, W, Cin, Cout, pool):
     g = torch.Generator(device="cuda").manual_seed(H * 1000 + Cin)
     x = torch.randn(B, H, W, Cin, device="cuda", generator=g).half()
     w = (torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) * (9 * Cin) ** -0.5).half()
     b = torch.randn(Cout, device="cuda", generator=g)
     wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
-    out = torch.full((B, H, W, Cout), float("nan"), device="cuda", dtype=torch.float16)
-    _check(lib, lib.embclip_conv3x3_f16(_ptr(x), _ptr(wk), _ptr(b), _ptr(out), B, H, W, Cin, Cout, 1, _stream()))
+    oshape = (B, H // 2, W // 2, Cout) if pool else (B, H, W, Cout)
+    out = torch.full(oshape, float("nan"), device="cuda", dtype=torch.float16)
+    _check(lib, lib.embclip_conv3x3_f16(_ptr(x), _ptr(wk), _ptr(b), _ptr(out), B, H, W, Cin, Cout, 1, int(pool), _stream()))
     torch.cuda.synchronize()
-    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1).relu().permute(0, 2, 3, 1)
-    _close(out.reshape(-1, Cout), ref.reshape(-1, Cout), f"conv3x3 B{B} {H}x{W} {Cin}->{Cout}")
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1).relu()
+    if pool:
+        ref = F.avg_pool2d(ref.half().float(), 2)     # the kernel rounds the full-resolution map to fp16 before averaging
+    ref = ref.permute(0, 2, 3, 1)
+    _close(out.reshape(-1, Cout), ref.reshape(-1, Cout), f"conv3x3 B{B} {H}x{W} {Cin}->{Cout} pool{pool}")
 
 
 def test_avgpool2(lib):

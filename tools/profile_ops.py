@@ -34,9 +34,12 @@ def main():
         if n + ".w" in pinfo and n in shapes and n != "stem.conv1":
             cout, k = pinfo[n + ".w"]
             m = shapes[n][0] * shapes[n][1] * shapes[n][2]
-            flop = 2.0 * m * cout * k
-            kin = k // 9 if ".conv2" in n or n in ("stem.conv2", "stem.conv3") else k
-            byts = m * kin * 2 + m * cout * (4 if acts[n].dtype == torch.float32 else 2) + cout * k * 2
+            conv3 = ".conv2" in n or n in ("stem.conv2", "stem.conv3")
+            src = {"stem.conv2": "stem.conv1", "stem.conv3": "stem.conv2"}.get(n, n.replace(".conv2", ".conv1"))
+            m_in = shapes[src][0] * shapes[src][1] * shapes[src][2] if conv3 else m     # fused avgpool: 4x the output pixels
+            flop = 2.0 * m_in * cout * k
+            kin = k // 9 if conv3 else k
+            byts = m_in * kin * 2 + m * cout * (4 if acts[n].dtype == torch.float32 else 2) + cout * k * 2
             if ".conv3" in n and k == cout // 4:
                 byts += m * cout * 2     # residual read
         rows.append(dict(op=n, ms=t, shape=shapes.get(n), gflop=flop / 1e9, mb=byts / 1e6,
