@@ -150,43 +150,50 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncwarp();
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16_f32(128, BN);
-      int stage = 0, slot = 0, acc = 0;
-      uint32_t bphase = 0, aphase = 0, acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(acc * kAccCols);
-        for (int c = 0; c < p.chunks; ++c) {
-          mbar_wait(bar_afull + 8 * slot, aphase);
-          const uint32_t plane = sA + uint32_t(slot) * p.plane_bytes;
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(bar_bfull + 8 * stage, bphase);
-            tcgen05_fence_after();
-            const int kh = tap / 3, kw = tap - kh * 3;
-            const uint32_t a_tap = plane + uint32_t(kh * p.Wp + kw) * SWZ;
-            const uint64_t b_desc = make_kmajor_desc<SWZ>(sB + stage * kBBytes);
+    // The whole warp runs the loop with warp-uniform values (so descriptors live in uniform registers and an
+    // operand step is one add); one elected lane issues.  The first version built every descriptor from scratch
+    // inside `if (lane == 0)`: ~23 SASS instructions per MMA, which made the single issuing thread the bottleneck.
+    constexpr uint32_t idesc = make_idesc_f16_f32(128, BN);
+    constexpr uint32_t dhi = kmajor_desc_hi<SWZ>();
+    int stage = 0, slot = 0, acc = 0;
+    uint32_t bphase = 0, aphase = 0, acc_phase = 0;
+    const uint32_t sB_lo = kmajor_desc_lo(sB);
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + uint32_t(acc * kAccCols);
+      for (int c = 0; c < p.chunks; ++c) {
+        mbar_wait(bar_afull + 8 * slot, aphase);
+        const uint32_t plane_lo = kmajor_desc_lo(sA + uint32_t(slot) * p.plane_bytes);
+        uint32_t tap_off = 0;                                  // (kh*Wp + kw) * SWZ / 16
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(bar_bfull + 8 * stage, bphase);
+          tcgen05_fence_after();
+          const uint32_t a_lo = plane_lo + tap_off;
+          const uint32_t b_lo = sB_lo + uint32_t(stage) * (kBBytes / 16);
+          const uint32_t first = uint32_t((c | tap) != 0);
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < KC / 16; ++k) {
 #pragma unroll
-              for (int s = 0; s < MS; ++s) {
-                const uint64_t a_desc = make_kmajor_desc<SWZ>(a_tap + uint32_t(s * 128) * SWZ);
-                umma_f16_ss(d_tmem + uint32_t(s * BN), a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc,
-                            uint32_t((c | tap | k) != 0));
-              }
+              for (int s = 0; s < MS; ++s)
+                umma_f16_ss(d_tmem + uint32_t(s * BN), desc64(a_lo + uint32_t(s * 128 * SWZ / 16 + 2 * k), dhi),
+                            desc64(b_lo + uint32_t(2 * k), dhi), idesc, k == 0 ? first : 1u);
             }
             umma_commit(bar_bempty + 8 * stage);
-            if (++stage == p.n_b) { stage = 0; bphase ^= 1u; }
           }
-          umma_commit(bar_aempty + 8 * slot);                  // plane free once its 9 taps have retired
-          if (++slot == p.n_a) { slot = 0; aphase ^= 1u; }
+          __syncwarp();
+          tap_off += (tap % 3 == 2) ? uint32_t(p.Wp - 2) * (SWZ / 16) : uint32_t(SWZ / 16);
+          if (++stage == p.n_b) { stage = 0; bphase ^= 1u; }
         }
-        umma_commit(bar_tfull + 8 * acc);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (elect_one()) umma_commit(bar_aempty + 8 * slot);   // plane free once its 9 taps have retired
+        __syncwarp();
+        if (++slot == p.n_a) { slot = 0; aphase ^= 1u; }
       }
+      if (elect_one()) umma_commit(bar_tfull + 8 * acc);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // ============================ epilogue (warps 4..11) ============================
     const int q = warp & 3;                                    // TMEM lane quarter

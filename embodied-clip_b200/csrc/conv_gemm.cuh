@@ -163,34 +163,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     __syncwarp();
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16_f32(128, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);       // epilogue has drained this accumulator
+    // warp-uniform loop, one elected lane issues; descriptors are stepped with 32-bit adds (see ptx.cuh)
+    constexpr uint32_t idesc = make_idesc_f16_f32(128, BN);
+    constexpr uint32_t dhi = kmajor_desc_hi<Cfg::kSwz>();
+    const uint32_t sA_lo = kmajor_desc_lo(sA), sB_lo = kmajor_desc_lo(sB);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);       // epilogue has drained this accumulator
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+      for (int kb = 0; kb < p.kb_total; ++kb) {
+        mbar_wait(bar_full + 8 * stage, phase);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
-        for (int kb = 0; kb < p.kb_total; ++kb) {
-          mbar_wait(bar_full + 8 * stage, phase);
-          tcgen05_fence_after();
-          const uint64_t a_desc = make_kmajor_desc<Cfg::kSwz>(sA + stage * Cfg::kABytes);
-          const uint64_t b_desc = make_kmajor_desc<Cfg::kSwz>(sB + stage * Cfg::kBBytes);
+        const uint32_t a_lo = sA_lo + uint32_t(stage) * (Cfg::kABytes / 16);
+        const uint32_t b_lo = sB_lo + uint32_t(stage) * (Cfg::kBBytes / 16);
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 elements (32 B) along K inside the swizzle span: +2 in the (addr >> 4) field
-            umma_f16_ss(d_tmem, a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc, uint32_t((kb | k) != 0));
-          }
-          umma_commit(bar_empty + 8 * stage);                  // smem stage free once these MMAs retire
-          if (++stage == S) { stage = 0; phase ^= 1u; }
+          for (int k = 0; k < BK / 16; ++k)                  // 16 elements (32 B) along K inside the swizzle span: +2
+            umma_f16_ss(d_tmem, desc64(a_lo + 2 * k, dhi), desc64(b_lo + 2 * k, dhi), idesc, k == 0 ? uint32_t(kb != 0) : 1u);
+          umma_commit(bar_empty + 8 * stage);                // smem stage free once these MMAs retire
         }
-        umma_commit(bar_tfull + 8 * acc);                      // accumulator complete
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1u; }
       }
+      if (elect_one()) umma_commit(bar_tfull + 8 * acc);     // accumulator complete
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
-    __syncwarp();
   } else {
     // ============================ epilogue (warps 2..9) ============================
     const int q = warp & 3;                                    // TMEM lane quarter this warp may touch

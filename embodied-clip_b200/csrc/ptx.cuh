@@ -153,6 +153,25 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
   return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (sbo << 32) |
          (uint64_t(1) << 46) | (layout << 61);
 }
+// Split form for hot issue loops: the high word is a compile-time constant and the low word is
+// (addr >> 4) | LBO, so stepping an operand by `bytes` is a plain 32-bit add of (bytes >> 4) -- shared-memory
+// addresses stay below 256 KB, so the add never carries out of the 14-bit address field.
+template <int kSwizzleBytes>
+__device__ __forceinline__ constexpr uint32_t kmajor_desc_hi() {
+  return uint32_t((8 * kSwizzleBytes) >> 4) | (1u << 14) | ((kSwizzleBytes == 128 ? 2u : (kSwizzleBytes == 64 ? 4u : 6u)) << 29);
+}
+__device__ __forceinline__ uint32_t kmajor_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return (uint64_t(hi) << 32) | lo; }
+// One lane of a converged warp (elect.sync): the issuing lane of tcgen05.mma / TMA in warp-uniform code.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): fp16 x fp16 -> fp32, both K-major.
 __host__ __device__ constexpr uint32_t make_idesc_f16_f32(int m, int n) {
   return (1u << 4)                 // c_format = F32
