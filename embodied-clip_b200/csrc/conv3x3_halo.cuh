@@ -165,26 +165,33 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int c = 0; c < p.chunks; ++c) {
         mbar_wait(bar_afull + 8 * slot, aphase);
         const uint32_t plane_lo = kmajor_desc_lo(sA + uint32_t(slot) * p.plane_bytes);
-        uint32_t tap_off = 0;                                  // (kh*Wp + kw) * SWZ / 16
-        for (int tap = 0; tap < 9; ++tap) {
-          mbar_wait(bar_bfull + 8 * stage, bphase);
+        // one issue round = one kernel row (3 taps): their weight stages are polled by three lanes at once and
+        // the 3 * MS * KC/16 MMAs go out back to back, so barrier / elect latency is paid once per 3 taps
+        for (int kh = 0; kh < 3; ++kh) {
+          ring_wait(bar_bfull, stage, bphase, 3, p.n_b);
           tcgen05_fence_after();
-          const uint32_t a_lo = plane_lo + tap_off;
-          const uint32_t b_lo = sB_lo + uint32_t(stage) * (kBBytes / 16);
-          const uint32_t first = uint32_t((c | tap) != 0);
+          const uint32_t a_row = plane_lo + uint32_t(kh * p.Wp) * (SWZ / 16);
+          const uint32_t first = uint32_t((c | kh) != 0);
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < KC / 16; ++k) {
+            for (int kw = 0; kw < 3; ++kw) {
+              int st = stage + kw;
+              if (st >= p.n_b) st -= p.n_b;
+              const uint32_t a_lo = a_row + uint32_t(kw * (SWZ / 16));
+              const uint32_t b_lo = sB_lo + uint32_t(st) * (kBBytes / 16);
 #pragma unroll
-              for (int s = 0; s < MS; ++s)
-                umma_f16_ss(d_tmem + uint32_t(s * BN), desc64(a_lo + uint32_t(s * 128 * SWZ / 16 + 2 * k), dhi),
-                            desc64(b_lo + uint32_t(2 * k), dhi), idesc, k == 0 ? first : 1u);
+              for (int k = 0; k < KC / 16; ++k) {
+#pragma unroll
+                for (int s = 0; s < MS; ++s)
+                  umma_f16_ss(d_tmem + uint32_t(s * BN), desc64(a_lo + uint32_t(s * 128 * SWZ / 16 + 2 * k), dhi),
+                              desc64(b_lo + uint32_t(2 * k), dhi), idesc, (kw | k) == 0 ? first : 1u);
+              }
+              umma_commit(bar_bempty + 8 * st);
             }
-            umma_commit(bar_bempty + 8 * stage);
           }
           __syncwarp();
-          tap_off += (tap % 3 == 2) ? uint32_t(p.Wp - 2) * (SWZ / 16) : uint32_t(SWZ / 16);
-          if (++stage == p.n_b) { stage = 0; bphase ^= 1u; }
+          stage += 3;
+          if (stage >= p.n_b) { stage -= p.n_b; bphase ^= 1u; }
         }
         if (elect_one()) umma_commit(bar_aempty + 8 * slot);   // plane free once its 9 taps have retired
         __syncwarp();
@@ -196,58 +203,75 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ============================ epilogue (warps 4..11) ============================
+    // Two warps share each TMEM lane quarter.  Wide tiles split the columns between them; narrow tiles
+    // (BN <= 64, MS >= 2) split the sub-tiles instead, so every thread still stores whole 64..128-B pixel rows.
     const int q = warp & 3;                                    // TMEM lane quarter
     const int row = q * 32 + lane;
-    constexpr int kColsPerWarp = BN / 2;
+    const int half = (warp - 4) >> 2;
+    constexpr bool kSplitSub = (BN <= 64 && MS >= 2);
+    constexpr int kColsPerWarp = kSplitSub ? BN : BN / 2;
     constexpr int CH = kColsPerWarp < 32 ? kColsPerWarp : 32;
-    const int col_base = ((warp - 4) >> 2) * kColsPerWarp;
+    constexpr int kSubStep = kSplitSub ? 2 : 1;
+    constexpr int kMyMS = MS / kSubStep;
+    const int col_base = kSplitSub ? 0 : half * kColsPerWarp;
+    const int sub0 = kSplitSub ? half : 0;
     constexpr uint32_t kStagePitch = BN * 2 + 16;              // bytes; +16 spreads rows over banks
+    // positions are tile-invariant: decode (group, row, col) of this thread's sub-tile rows once
+    int rel[kMyMS], rg[kMyMS];                                 // rel: pixel offset inside the tile's first image row; rg: r | g << 16, -1 = never valid
+#pragma unroll
+    for (int i = 0; i < kMyMS; ++i) {
+      const int pos = (sub0 + i * kSubStep) * 128 + row;
+      const int prow = pos / p.Wp;
+      const int w = pos - prow * p.Wp;
+      const int g = prow / p.BHo;
+      const int r = prow - g * p.BHo;
+      rel[i] = (g * p.H + r) * p.W + w;
+      rg[i] = (w < p.W && r < p.R && g < p.G) ? (r | (g << 16)) : -1;
+    }
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int n_blk, img0, h0;
       tile_coords(t, n_blk, img0, h0);
       const int n0 = n_blk * BN;
+      __half* const tile_out = p.out + (size_t(img0) * p.H + h0) * p.W * p.N + n0;
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int s = 0; s < MS; ++s) {
-        const int pos = s * 128 + row;
-        const int prow = pos / p.Wp;
-        const int w = pos - prow * p.Wp;
-        const int g = prow / p.BHo;
-        const int r = prow - g * p.BHo;
-        const bool valid = w < p.W && r < p.R && g < p.G && h0 + r < p.H && img0 + g < p.B;
-        __half* optr = p.out + ((size_t(img0 + g) * p.H + (h0 + r)) * p.W + w) * p.N + n0;
-#pragma unroll 1
-        for (int c = 0; c < kColsPerWarp / CH; ++c) {
-          const int col = col_base + c * CH;
-          uint32_t v[CH];
-          tmem_ld_32x32b<CH>(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * kAccCols + s * BN + col), v);
-          float bv[CH];
+      for (int c = 0; c < kColsPerWarp / CH; ++c) {
+        const int col = col_base + c * CH;
+        float bv[CH];
 #pragma unroll
-          for (int i = 0; i < CH / 4; ++i) {
-            const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col) + i) : make_float4(0, 0, 0, 0);
-            bv[4 * i] = b4.x; bv[4 * i + 1] = b4.y; bv[4 * i + 2] = b4.z; bv[4 * i + 3] = b4.w;
-          }
+        for (int i = 0; i < CH / 4; ++i) {
+          const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col) + i) : make_float4(0, 0, 0, 0);
+          bv[4 * i] = b4.x; bv[4 * i + 1] = b4.y; bv[4 * i + 2] = b4.z; bv[4 * i + 3] = b4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < kMyMS; ++i) {
+          const int sub = sub0 + i * kSubStep;
+          uint32_t v[CH];
+          tmem_ld_32x32b<CH>(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * kAccCols + sub * BN + col), v);
           tmem_ld_wait();
           uint32_t h2[CH / 2];
 #pragma unroll
-          for (int i = 0; i < CH / 2; ++i) {
-            float a = __uint_as_float(v[2 * i]) + bv[2 * i], b = __uint_as_float(v[2 * i + 1]) + bv[2 * i + 1];
+          for (int j = 0; j < CH / 2; ++j) {
+            float a = __uint_as_float(v[2 * j]) + bv[2 * j], b = __uint_as_float(v[2 * j + 1]) + bv[2 * j + 1];
             if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-            h2[i] = pack_half2(a, b);
+            h2[j] = pack_half2(a, b);
           }
           if constexpr (kPool) {
-            const uint32_t a = sStage + uint32_t(pos) * kStagePitch + uint32_t(col) * 2;
+            const uint32_t a = sStage + uint32_t(sub * 128 + row) * kStagePitch + uint32_t(col) * 2;
 #pragma unroll
-            for (int i = 0; i < CH / 8; ++i)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 16 * i), "r"(h2[4 * i]), "r"(h2[4 * i + 1]),
-                           "r"(h2[4 * i + 2]), "r"(h2[4 * i + 3]) : "memory");
-          } else if (valid) {
-            uint4* o = reinterpret_cast<uint4*>(optr + col);
+            for (int j = 0; j < CH / 8; ++j)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 16 * j), "r"(h2[4 * j]), "r"(h2[4 * j + 1]),
+                           "r"(h2[4 * j + 2]), "r"(h2[4 * j + 3]) : "memory");
+          } else {
+            const bool valid = rg[i] >= 0 && h0 + (rg[i] & 0xffff) < p.H && img0 + (rg[i] >> 16) < p.B;
+            if (valid) {
+              uint4* o = reinterpret_cast<uint4*>(tile_out + size_t(rel[i]) * p.N + col);
 #pragma unroll
-            for (int i = 0; i < CH / 8; ++i) o[i] = make_uint4(h2[4 * i], h2[4 * i + 1], h2[4 * i + 2], h2[4 * i + 3]);
+              for (int j = 0; j < CH / 8; ++j) o[j] = make_uint4(h2[4 * j], h2[4 * j + 1], h2[4 * j + 2], h2[4 * j + 3]);
+            }
           }
         }
       }

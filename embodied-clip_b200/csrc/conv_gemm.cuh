@@ -175,6 +175,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);       // epilogue has drained this accumulator
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+      // (one k-block per issue round: these GEMMs are bound by the L2 -> smem fill, so a stage is consumed -- and
+      // released -- as soon as it lands; polling two stages per round measured 10 % slower)
       for (int kb = 0; kb < p.kb_total; ++kb) {
         mbar_wait(bar_full + 8 * stage, phase);
         tcgen05_fence_after();

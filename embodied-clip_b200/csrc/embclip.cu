@@ -295,7 +295,7 @@ static int launch_c3_cfg(const Conv3Op& op, const C3Geom& g, cudaStream_t st) {
   const int chunks = op.C / KC;
   static const int env_na = getenv("EMBCLIP_C3_NA") ? atoi(getenv("EMBCLIP_C3_NA")) : 0;
   int n_a = 2;
-  if (2u * plane_bytes + 3u * kBBytes > budget) return fail(EMBCLIP_EINVAL, "conv3x3: strip does not fit shared memory (plane %u B)", plane_bytes);
+  if (2u * plane_bytes + 4u * kBBytes > budget) return fail(EMBCLIP_EINVAL, "conv3x3: strip does not fit shared memory (plane %u B)", plane_bytes);
   int n_b = int((budget - 2u * plane_bytes) / kBBytes);
   if (chunks > 1 && n_b >= 6 + int(plane_bytes / kBBytes)) { n_a = 3; n_b -= int((plane_bytes + kBBytes - 1) / kBBytes); }
   if (env_na >= 2 && env_na <= kC3MaxA && uint32_t(env_na) * plane_bytes + 4u * kBBytes <= budget) {
@@ -347,7 +347,7 @@ static int launch_conv3x3_halo(const Conv3Op& op, cudaStream_t st) {
     if (!c3_geometry(op.B, op.H, op.W, ms, op.pool != 0, &g)) continue;
     const uint32_t plane = ((g.rows_alloc * (kc * 2)) + 1023u) & ~1023u;
     const uint32_t stage = op.pool ? uint32_t(ms) * 128u * (bn * 2 + 16) : 0u;
-    if (2u * plane + 3u * uint32_t(bn * kc * 2) + stage + 1024u + kC3BarBytes <= 227u * 1024u) break;
+    if (2u * plane + 4u * uint32_t(bn * kc * 2) + stage + 1024u + kC3BarBytes <= 227u * 1024u) break;
   }
 #define EMBCLIP_C3(BN_, MS_, KC_) \
   if (bn == BN_ && ms == MS_ && kc == KC_) \

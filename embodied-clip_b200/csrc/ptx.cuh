@@ -58,6 +58,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Lanes [0, n) of a converged warp each wait on one slot of a ring of `depth` mbarriers (8 B apart), starting at
+// `stage` with parity `phase` (parity flips where the ring wraps): n barrier round trips cost one latency.
+__device__ __forceinline__ void ring_wait(uint32_t bar0, int stage, uint32_t phase, int n, int depth) {
+  const int lane = int(threadIdx.x & 31u);
+  if (lane < n) {
+    int idx = stage + lane;
+    uint32_t ph = phase;
+    if (idx >= depth) { idx -= depth; ph ^= 1u; }
+    mbar_wait(bar0 + 8u * uint32_t(idx), ph);
+  }
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
