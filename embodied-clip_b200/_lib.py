@@ -27,8 +27,13 @@ class ActInfo(C.Structure):
                 ("w", C.c_int32), ("c", C.c_int32), ("offset", C.c_uint64)]
 
 
+class ACCfg(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("feat_channels", "feat_pixels", "compress_hidden", "compress_out", "goal_dims",
+                                         "combine_hidden", "combine_out", "hidden", "num_actions", "num_goals")]
+
+
 # symbol -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
-_VP, _I, _U64, _FP = C.c_void_p, C.c_int, C.c_uint64, C.c_void_p
+_VP, _I, _U64, _FP, _LL, _F = C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_longlong, C.c_float
 SIGNATURES = {
     "embclip_last_error": (C.c_char_p, []),
     "embclip_abi_version": (_I, []),
@@ -49,6 +54,23 @@ SIGNATURES = {
     "embclip_conv3x3_f16": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "embclip_avgpool2_f16": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
     "embclip_stem_conv1": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
+    # actor-critic / PPO update
+    "embclip_ac_create": (_I, [C.POINTER(ACCfg), C.POINTER(_VP)]),
+    "embclip_ac_destroy": (_I, [_VP]),
+    "embclip_ac_num_params": (_I, [_VP]),
+    "embclip_ac_param_info": (_I, [_VP, _I, C.POINTER(ParamInfo)]),
+    "embclip_ac_param_floats": (_U64, [_VP]),
+    "embclip_ac_workspace_bytes": (_U64, [_VP, _I, _I]),
+    "embclip_ac_pack_features": (_I, [_VP, _FP, _LL, _VP, _VP]),
+    "embclip_ac_forward": (_I, [_VP, _FP, _VP, _VP, _FP, _FP, _I, _I, _FP, _FP, _FP, _VP, _U64, _I, _VP]),
+    "embclip_ac_ppo_loss": (_I, [_VP, _FP, _I, _I, _VP, _FP, _FP, _FP, _FP, _F, _F, _F, _F, _FP, _FP, _FP, _VP, _U64, _VP]),
+    "embclip_ac_backward": (_I, [_VP, _FP, _VP, _VP, _FP, _FP, _I, _I, _FP, _FP, _FP, _FP, _VP, _U64, _VP]),
+    "embclip_gae": (_I, [_FP, _FP, _FP, _I, _I, _F, _F, _FP, _FP, _FP, _F, _VP]),
+    "embclip_sumsq_f32": (_I, [_FP, _LL, _FP, _VP]),
+    "embclip_adam_clip_step": (_I, [_FP, _FP, _FP, _FP, _LL, _FP, _F, _F, _F, _F, _F, _I, _VP]),
+    "embclip_wgrad_f16": (_I, [_VP, _I, _I, _VP, _I, _I, _LL, _FP, _LL, _LL, _FP, _VP]),
+    "embclip_gru_forward": (_I, [_FP, _FP, _FP, _FP, _FP, _I, _I, _I, _FP, _FP, _FP, _FP, _FP, _VP, _VP]),
+    "embclip_gru_backward": (_I, [_FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _I, _I, _I, _FP, _FP, _VP, _FP, _VP, _VP]),
 }
 
 _lib = None

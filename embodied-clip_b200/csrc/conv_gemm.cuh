@@ -29,6 +29,7 @@ struct ConvGemmParams {
   int kb_total;
   uint32_t a0_box_bytes;        // bytes one A0 box load delivers (box may hold fewer than 128 rows)
   int relu;
+  int res_mode;                 // kRes only. 0: out += residual;  1: out = residual > 0 ? out : 0  (ReLU backward mask)
   int out_f32;                  // 1: epilogue stores fp32 rows straight to `out_f32_ptr` (2-D mode only)
   int M, N;                     // logical GEMM extents (rows valid for residual / fp32 stores)
   const float* bias;            // [N] or nullptr
@@ -274,8 +275,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float2 r2 = __half22float2(h[j]);
-              f[i * 8 + j * 2] += r2.x;
-              f[i * 8 + j * 2 + 1] += r2.y;
+              if (p.res_mode == 0) {
+                f[i * 8 + j * 2] += r2.x;
+                f[i * 8 + j * 2 + 1] += r2.y;
+              } else {
+                f[i * 8 + j * 2] = r2.x > 0.f ? f[i * 8 + j * 2] : 0.f;
+                f[i * 8 + j * 2 + 1] = r2.y > 0.f ? f[i * 8 + j * 2 + 1] : 0.f;
+              }
             }
           }
         }

@@ -11,7 +11,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/embclip_b200.h"
+#include "host.h"
 #include "aux_kernels.cuh"
 #include "conv_gemm.cuh"
 #include "conv3x3_halo.cuh"
@@ -22,7 +22,7 @@ using namespace embclip;
 // errors
 // =============================================================================================
 static thread_local std::string g_err;
-static int fail(int code, const char* fmt, ...) {
+int embclip::fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
@@ -31,14 +31,8 @@ static int fail(int code, const char* fmt, ...) {
   g_err = buf;
   return code;
 }
-#define CUDA_TRY(expr)                                                                      \
-  do {                                                                                      \
-    cudaError_t e_ = (expr);                                                                \
-    if (e_ != cudaSuccess) return fail(EMBCLIP_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
-  } while (0)
-
 extern "C" const char* embclip_last_error(void) { return g_err.c_str(); }
-extern "C" int embclip_abi_version(void) { return 2; }
+extern "C" int embclip_abi_version(void) { return 3; }
 
 // =============================================================================================
 // TMA descriptors (driver entry point resolved at run time: the library links only against cudart)
@@ -62,8 +56,8 @@ static CUtensorMapSwizzle swizzle_for_bytes(int inner_bytes) {
                             : (inner_bytes >= 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 // fp16 tensor, dims fastest-first, `pitch[i]` = byte stride of dim i+1.
-static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* pitch,
-                    const uint32_t* box) {
+int embclip::make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* pitch,
+                      const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(EMBCLIP_ECUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint64_t gd[5], gs[4];
@@ -87,7 +81,7 @@ static int make_map_nhwc(CUtensorMap* m, const void* base, int n, int h, int w, 
   const uint32_t box[4] = {(uint32_t)box_c, (uint32_t)box_w, (uint32_t)box_h, (uint32_t)box_n};
   return make_map(m, base, 4, dims, pitch, box);
 }
-static int make_map_2d(CUtensorMap* m, const void* base, int rows, int cols, int ld, int box_cols, int box_rows) {
+int embclip::make_map_2d(CUtensorMap* m, const void* base, int rows, int cols, int ld, int box_cols, int box_rows) {
   const uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
   const uint64_t pitch[1] = {(uint64_t)ld * 2};
   const uint32_t box[2] = {(uint32_t)box_cols, (uint32_t)box_rows};
@@ -98,7 +92,7 @@ static int make_map_2d(CUtensorMap* m, const void* base, int rows, int cols, int
 // conv_gemm launcher
 // =============================================================================================
 static int g_num_sms = 0;
-static int num_sms() {
+int embclip::num_sms() {
   if (!g_num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -107,26 +101,6 @@ static int num_sms() {
   }
   return g_num_sms;
 }
-
-struct GemmOp {
-  // A0: NHWC view
-  const void* a0 = nullptr;
-  int n = 1, h = 1, w = 1, c0 = 0, lda0 = 0;   // c0 = channels of source 0 (K per tap); lda0 pixel pitch (elements)
-  int taps = 1;
-  // A1: optional 2-D source [M, c1]
-  const void* a1 = nullptr;
-  int c1 = 0;
-  // weights [w_rows, ldw] (row n holds K values), bias
-  const void* wgt = nullptr;
-  int ldw = 0, w_rows = 0;
-  const float* bias = nullptr;
-  const void* residual = nullptr;   // fp16 [M, cout]
-  void* out = nullptr;              // fp16 NHWC [n,h,w,cout] or fp32 [M, cout]
-  int cout = 0;
-  int relu = 0, out_f32 = 0;
-  int grp_n = 0, grp_a_koff = 0, grp_b_koff = 0, grp_b_nmod = 0;
-  int a_cols = 0;                   // logical width of an A0 row for the tensor map (>= c0; grouped mode: full row)
-};
 
 static void choose_box(int H, int W, int B, int* bw, int* bh, int* bn) {
   if (W * H <= 64) { *bw = W; *bh = H; *bn = 128 / (W * H); if (*bn > B) *bn = B; if (*bn < 1) *bn = 1; return; }
@@ -194,6 +168,7 @@ static int launch_cfg(const GemmOp& op, cudaStream_t st) {
   p.kb_total = p.kb_src0 + op.c1 / BK;
   p.a0_box_bytes = uint32_t(p.box_w * p.box_h * p.box_n) * BK * 2;
   p.relu = op.relu;
+  p.res_mode = op.res_mode;
   p.out_f32 = op.out_f32;
   p.M = (int)M;
   p.N = op.cout;
@@ -216,7 +191,7 @@ static int pick_bn(int cout) {
   return 0;
 }
 
-static int launch_gemm(const GemmOp& op, cudaStream_t st, int force_bn = 0) {
+int embclip::launch_gemm(const GemmOp& op, cudaStream_t st, int force_bn) {
   if (op.c0 % 32 || op.c1 % 32 || op.cout % 32) return fail(EMBCLIP_EINVAL, "channels must be multiples of 32 (c0 %d c1 %d cout %d)", op.c0, op.c1, op.cout);
   if (op.taps != 1 && op.taps != 9) return fail(EMBCLIP_EINVAL, "taps must be 1 or 9");
   if (op.taps == 9 && (op.a1 || op.residual || op.out_f32 || op.grp_n)) return fail(EMBCLIP_EINVAL, "3x3 mode supports bias+relu only");

@@ -1,0 +1,46 @@
+// Host-side helpers shared by the translation units of libembclip_b200.so (embclip.cu: encoder plan and GEMM
+// launchers; ac_path.cu: actor-critic / PPO-update plan).  Internal: nothing here is part of the C ABI.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/embclip_b200.h"
+
+namespace embclip {
+
+int fail(int code, const char* fmt, ...);
+#define CUDA_TRY(expr)                                                                                  \
+  do {                                                                                                  \
+    cudaError_t e_ = (expr);                                                                            \
+    if (e_ != cudaSuccess) return ::embclip::fail(EMBCLIP_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+int num_sms();
+// fp16 tensor maps; dims fastest-first, `pitch[i]` = byte stride of dim i+1; swizzle follows the box's inner bytes
+int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* pitch, const uint32_t* box);
+int make_map_2d(CUtensorMap* m, const void* base, int rows, int cols, int ld, int box_cols, int box_rows);
+
+struct GemmOp {
+  // A0: NHWC view
+  const void* a0 = nullptr;
+  int n = 1, h = 1, w = 1, c0 = 0, lda0 = 0;   // c0 = channels of source 0 (K per tap); lda0 pixel pitch (elements)
+  int taps = 1;
+  // A1: optional 2-D source [M, c1]
+  const void* a1 = nullptr;
+  int c1 = 0;
+  // weights [w_rows, ldw] (row n holds K values), bias
+  const void* wgt = nullptr;
+  int ldw = 0, w_rows = 0;
+  const float* bias = nullptr;
+  const void* residual = nullptr;   // fp16 [M, cout]
+  int res_mode = 0;                 // 0: add residual; 1: zero the output where residual <= 0 (ReLU backward)
+  void* out = nullptr;              // fp16 NHWC [n,h,w,cout] or fp32 [M, cout]
+  int cout = 0;
+  int relu = 0, out_f32 = 0;
+  int grp_n = 0, grp_a_koff = 0, grp_b_koff = 0, grp_b_nmod = 0;
+  int a_cols = 0;                   // logical width of an A0 row for the tensor map (>= c0; grouped mode: full row)
+};
+int launch_gemm(const GemmOp& op, cudaStream_t st, int force_bn = 0);
+
+}  // namespace embclip

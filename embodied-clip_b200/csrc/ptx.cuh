@@ -45,7 +45,7 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __noinline__ void mbar_timeout_trap(uint32_t bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_timeout_trap(uint32_t bar, uint32_t parity) {
   printf("embclip: mbarrier timeout block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
   __trap();
 }

@@ -125,6 +125,94 @@ int embclip_avgpool2_f16(const void* in, void* out, int B, int H, int W, int C, 
 int embclip_stem_conv1(const float* frames, const float* w, const float* bias, void* out, int B, int R, int Cout,
                        void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * ObjectNav actor-critic + PPO update: replaces, on the update hot path,
+ *   ResnetTensorNavActorCritic.forward   (allenact projects/objectnav_baselines/models/object_nav_models.py)
+ *   RNNStateEncoder.forward              (allenact/embodiedai/models/basic_models.py)
+ *   LinearActorHead / LinearCriticHead   (allenact/algorithms/onpolicy_sync/policy.py)
+ *   PPO.loss_per_step                    (allenact/algorithms/onpolicy_sync/losses/ppo.py)
+ *   RolloutStorage.compute_returns       (allenact/algorithms/onpolicy_sync/storage.py)
+ *   OnPolicyTrainer.backprop_step: total_loss.backward(), clip_grad_norm_, Adam.step  (.../engine.py)
+ * of allenai/allenact v0.5.0 (pin: /root/reference/readme_files/baselines_robothor_objectnav.md:6; the
+ * experiment that instantiates them is named at :51).  All tensors are [steps T, samplers N, ...] row-major.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct embclip_ac* embclip_ac_t;
+
+typedef struct {
+  int32_t feat_channels;    /* 2048: channels of the CLIP-RN50 trunk feature            */
+  int32_t feat_pixels;      /* 49 = 7 x 7                                                */
+  int32_t compress_hidden;  /* 128  resnet_compressor.0 out                              */
+  int32_t compress_out;     /* 32   resnet_compressor.2 out                              */
+  int32_t goal_dims;        /* 32   embed_class width                                    */
+  int32_t combine_hidden;   /* 128  target_obs_combiner.0 out                            */
+  int32_t combine_out;      /* 32   target_obs_combiner.2 out; GRU input = 32 * 49       */
+  int32_t hidden;           /* 512  GRU hidden size                                      */
+  int32_t num_actions;      /* 6                                                         */
+  int32_t num_goals;        /* 12                                                        */
+} embclip_ac_cfg;
+
+int embclip_ac_create(const embclip_ac_cfg* cfg, embclip_ac_t* out);   /* needs no GPU */
+int embclip_ac_destroy(embclip_ac_t h);
+/* Parameters live in ONE flat fp32 buffer (and gradients / Adam moments in buffers of the same layout):
+ * param_info(i).name is the upstream state_dict key, .offset/.nbytes its slot (256-B aligned, padding zero). */
+int embclip_ac_num_params(embclip_ac_t h);
+int embclip_ac_param_info(embclip_ac_t h, int index, embclip_param_info* out);
+uint64_t embclip_ac_param_floats(embclip_ac_t h);
+uint64_t embclip_ac_workspace_bytes(embclip_ac_t h, int T, int N);
+/* Rollout features fp32 [frames, C, H*W] (what ClipResNetPreprocessor wrote into RolloutStorage) -> fp16
+ * [frames*H*W, C] rows, the layout every update pass reads.  Once per rollout. */
+int embclip_ac_pack_features(embclip_ac_t h, const float* feats_nchw, long long frames, void* feats_f16, void* stream);
+/* ActorCriticModel.forward on a [T, N] block: goals int64 [T,N]; masks fp32 [T,N] (0 = episode start);
+ * h0 fp32 [N, hidden] -> logits fp32 [T,N,A], values fp32 [T,N], h_last fp32 [N, hidden] (may be NULL).
+ * save_for_backward != 0 keeps what embclip_ac_backward needs in the workspace. */
+int embclip_ac_forward(embclip_ac_t h, const float* params, const void* feats_f16, const long long* goals,
+                       const float* masks, const float* h0, int T, int N, float* logits, float* values, float* h_last,
+                       void* workspace, uint64_t workspace_bytes, int save_for_backward, void* stream);
+/* PPO.loss_per_step on the block embclip_ac_forward just evaluated (reads its hidden states from the workspace):
+ * loss_sums[3] <- sums over the block of {action loss, value loss, entropy}; the gradient of
+ *   grad_scale * sum(action + value_loss_coef * value - entropy_coef * entropy)
+ * w.r.t. logits / values is left in the workspace for embclip_ac_backward(dlogits = NULL). */
+int embclip_ac_ppo_loss(embclip_ac_t h, const float* params, int T, int N, const long long* actions,
+                        const float* old_action_log_probs, const float* norm_adv, const float* old_values,
+                        const float* returns, float clip_param, float value_loss_coef, float entropy_coef,
+                        float grad_scale, float* logits, float* values, float* loss_sums, void* workspace,
+                        uint64_t workspace_bytes, void* stream);
+/* Backward of embclip_ac_forward(save_for_backward = 1): ACCUMULATES into `grads` (flat, caller zeroes it).
+ * dlogits [T,N,A] / dvalues [T,N] / dh_last [N,hidden] are the output gradients (autograd path); pass
+ * dlogits = dvalues = NULL to use the ones embclip_ac_ppo_loss left in the workspace. */
+int embclip_ac_backward(embclip_ac_t h, const float* params, const void* feats_f16, const long long* goals,
+                        const float* masks, const float* h0, int T, int N, const float* dlogits, const float* dvalues,
+                        const float* dh_last, float* grads, void* workspace, uint64_t workspace_bytes, void* stream);
+
+/* RolloutStorage.compute_returns(use_gae): rewards [T,N]; values [T+1,N] (row T = next value); masks [T+1,N]
+ * -> returns [T,N], advantages [T,N] and (if non-NULL) norm_advantages = (A - mean) / (std + eps). */
+int embclip_gae(const float* rewards, const float* values, const float* masks, int T, int N, float gamma, float tau,
+                float* returns, float* advantages, float* norm_advantages, float eps, void* stream);
+/* out[0] = sum x^2 (the squared global gradient norm of clip_grad_norm_). */
+int embclip_sumsq_f32(const float* x, long long n, float* out, void* stream);
+/* clip_grad_norm_(max_grad_norm) from *grad_sumsq (skipped when max_grad_norm <= 0), then torch.optim.Adam
+ * (no weight decay / amsgrad) step number `step` (1-based) on flat buffers; grads are scaled in place. */
+int embclip_adam_clip_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                           const float* grad_sumsq, float max_grad_norm, float lr, float beta1, float beta2, float eps,
+                           int step, void* stream);
+
+/* Primitives of the plan above, exposed for unit tests. */
+/* out[m*ldo_m + n*ldo_n] += alpha * sum_k A[k][m] * B[k][n]; A fp16 [Kdim][lda], B fp16 [Kdim][ldb]; N1 % 32 == 0;
+ * alpha = device scalar or NULL.  (weight gradients: both operands row-major activations, contraction over rows) */
+int embclip_wgrad_f16(const void* a, int lda, int M1, const void* b, int ldb, int N1, long long Kdim, float* out,
+                      long long ldo_m, long long ldo_n, const float* alpha, void* stream);
+/* nn.GRU (1 layer) with RNNStateEncoder's episode masking: gi = x W_ih^T + b_ih precomputed [T,N,3H];
+ * out [T,N,H]; save_* [T,N,H] (all NULL for inference); scratch32 = 64 B of device scratch. */
+int embclip_gru_forward(const float* gi, const float* w_hh, const float* b_hh, const float* h0, const float* masks,
+                        int T, int N, int H, float* out, float* save_r, float* save_z, float* save_n, float* save_hn,
+                        void* scratch32, void* stream);
+/* BPTT of the above: dout [T,N,H], dh_last [N,H] or NULL -> dgi, dgh [T,N,3H] fp32, hm_f16 [T,N,H] fp16
+ * (masked previous hidden state), dh0 [N,H] or NULL. */
+int embclip_gru_backward(const float* w_hh, const float* h0, const float* masks, const float* out, const float* save_r,
+                         const float* save_z, const float* save_n, const float* save_hn, const float* dout,
+                         const float* dh_last, int T, int N, int H, float* dgi, float* dgh, void* hm_f16, float* dh0,
+                         void* scratch32, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     for s in header_symbols():
         assert hasattr(lib, s), f"{s} declared in the header but not exported"
     from embclip_b200 import _lib
-    assert _lib.load().embclip_abi_version() == 2
+    assert _lib.load().embclip_abi_version() == 3
 
 
 def test_sass_is_blackwell_native(built_lib):
@@ -81,3 +81,33 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU"):
         _lib.load()
+
+
+def test_actor_critic_plan_matches_upstream_state_dict(built_lib):
+    """The flat parameter layout the library reports carries the upstream (AllenAct) state_dict names and shapes,
+    in 256-B aligned, non-overlapping slots; 3,480,775 parameters."""
+    from embclip_b200 import _lib
+    from oracle.allenact_models import ResnetTensorNavActorCritic
+    lib = _lib.load()
+    cfg = _lib.ACCfg(feat_channels=2048, feat_pixels=49, compress_hidden=128, compress_out=32, goal_dims=32,
+                     combine_hidden=128, combine_out=32, hidden=512, num_actions=6, num_goals=12)
+    h = C.c_void_p()
+    assert lib.embclip_ac_create(C.byref(cfg), C.byref(h)) == 0
+    ref = {k: tuple(v.shape) for k, v in ResnetTensorNavActorCritic().state_dict().items()}
+    got, end, total = {}, 0, 0
+    for i in range(lib.embclip_ac_num_params(h)):
+        pi = _lib.ParamInfo()
+        assert lib.embclip_ac_param_info(h, i, C.byref(pi)) == 0
+        assert pi.offset % 256 == 0 and pi.offset >= end and pi.dtype == _lib.DTYPE_F32
+        end = pi.offset + pi.nbytes
+        got[pi.name.decode()] = tuple(pi.shape[:pi.ndim])
+        total += pi.nbytes // 4
+    assert got == ref
+    assert total == 3_480_775
+    assert lib.embclip_ac_param_floats(h) * 4 >= end
+    assert lib.embclip_ac_workspace_bytes(h, 128, 60) > 0
+    bad = _lib.ACCfg(feat_channels=2048, feat_pixels=49, compress_hidden=128, compress_out=64, goal_dims=32,
+                     combine_hidden=128, combine_out=32, hidden=512, num_actions=6, num_goals=12)
+    h2 = C.c_void_p()
+    assert lib.embclip_ac_create(C.byref(bad), C.byref(h2)) < 0 and b"compress_out" in lib.embclip_last_error()
+    assert lib.embclip_ac_destroy(h) == 0
