@@ -61,6 +61,8 @@ SIGNATURES = {
     "embclip_ac_param_info": (_I, [_VP, _I, C.POINTER(ParamInfo)]),
     "embclip_ac_param_floats": (_U64, [_VP]),
     "embclip_ac_workspace_bytes": (_U64, [_VP, _I, _I]),
+    "embclip_ac_num_acts": (_I, [_VP]),
+    "embclip_ac_act_info": (_I, [_VP, _I, _I, _I, C.POINTER(ActInfo)]),
     "embclip_ac_pack_features": (_I, [_VP, _FP, _LL, _VP, _VP]),
     "embclip_ac_forward": (_I, [_VP, _FP, _VP, _VP, _FP, _FP, _I, _I, _FP, _FP, _FP, _VP, _U64, _I, _VP]),
     "embclip_ac_ppo_loss": (_I, [_VP, _FP, _I, _I, _VP, _FP, _FP, _FP, _FP, _F, _F, _F, _F, _FP, _FP, _FP, _VP, _U64, _VP]),

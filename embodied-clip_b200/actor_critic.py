@@ -114,10 +114,9 @@ class _ACFunction(torch.autograd.Function):
     """forward = embclip_ac_forward, backward = embclip_ac_backward; gradients arrive as one flat tensor."""
 
     @staticmethod
-    def forward(ctx, flat_params, model, feats16, goals, masks, h0, T, N):
+    def forward(ctx, flat_params, model, feats16, goals, masks, h0, T, N, need_grad):
         plan, dev = model._plan, flat_params.device
         A, H = plan.cfg["num_actions"], plan.cfg["hidden"]
-        need_grad = torch.is_grad_enabled() and flat_params.requires_grad
         ws = model._workspace(T, N)
         logits = torch.empty(T, N, A, dtype=torch.float32, device=dev)
         values = torch.empty(T, N, dtype=torch.float32, device=dev)
@@ -146,7 +145,7 @@ class _ACFunction(torch.autograd.Function):
                                                     masks.data_ptr(), h0.data_ptr(), T, N, dl.data_ptr(), dv.data_ptr(),
                                                     dh.data_ptr() if dh is not None else None, grads.data_ptr(), ws.data_ptr(),
                                                     ws.numel(), _stream(dev)))
-        return grads, None, None, None, None, None, None, None
+        return grads, None, None, None, None, None, None, None, None
 
 
 class ResnetTensorNavActorCritic(nn.Module):
@@ -256,6 +255,18 @@ class ResnetTensorNavActorCritic(nn.Module):
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.flat_params.device)
         return self._ws
 
+    def activations(self, T: int, N: int) -> Dict[str, torch.Tensor]:
+        """Views of the workspace intermediates of the LAST forward / backward on a [T, N] block (test hook)."""
+        ws = self._workspace(T, N)
+        out = {}
+        for i in range(_lib.check(self._plan.lib.embclip_ac_num_acts(self._plan._h))):
+            ai = _lib.ActInfo()
+            _lib.check(self._plan.lib.embclip_ac_act_info(self._plan._h, T, N, i, C.byref(ai)))
+            dt = torch.float16 if ai.dtype == _lib.DTYPE_F16 else torch.float32
+            nbytes = ai.w * ai.c * (2 if dt == torch.float16 else 4)
+            out[ai.name.decode()] = ws[ai.offset:ai.offset + nbytes].view(dt).view(ai.w, ai.c)
+        return out
+
     def pack_features(self, feats: torch.Tensor) -> PackedFeatures:
         """fp32 [T, N, C, H, W] -> PackedFeatures (fp16 pixel rows)."""
         C_, Hh, Ww = self.resnet_tensor_shape
@@ -278,7 +289,8 @@ class ResnetTensorNavActorCritic(nn.Module):
         g = goals.reshape(T, N).to(dev, torch.int64).contiguous()
         m = _f32c(masks.reshape(T, N).to(dev))
         h0 = _f32c(memory.reshape(N, self.hidden_size).to(dev))
-        return _ACFunction.apply(self.flat_params, self, pf.data, g, m, h0, T, N)
+        need_grad = torch.is_grad_enabled() and self.flat_params.requires_grad    # (grad mode is off inside Function.forward)
+        return _ACFunction.apply(self.flat_params, self, pf.data, g, m, h0, T, N, need_grad)
 
     def forward(self, observations: Dict[str, Any], memory: Any, prev_actions: Optional[torch.Tensor],
                 masks: torch.Tensor) -> Tuple[ActorCriticOutput, Any]:

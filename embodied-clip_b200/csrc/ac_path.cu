@@ -331,6 +331,30 @@ int check_block(const embclip_ac* m, int T, int N, const void* ws, uint64_t ws_b
 
 }  // namespace
 
+extern "C" int embclip_ac_num_acts(embclip_ac_t h) { return h ? 25 : fail(EMBCLIP_EINVAL, "null handle"); }
+extern "C" int embclip_ac_act_info(embclip_ac_t h, int T, int N, int index, embclip_act_info* out) {
+  if (!h || !out || T <= 0 || N <= 0 || index < 0 || index >= 25) return fail(EMBCLIP_EINVAL, "ac_act_info: bad argument");
+  const embclip_ac_cfg& c = h->cfg;
+  AcWs w;
+  ac_workspace(h, T, N, nullptr, &w);
+  const int F = T * N, M = F * c.feat_pixels, H = c.hidden, I = c.combine_out * c.feat_pixels;
+  struct E { const char* name; const void* p; int dtype, rows, cols; };
+  const E tab[25] = {
+      {"goal_rows", w.G, 0, M, c.goal_dims}, {"compress0", w.Y1, 0, M, c.compress_hidden}, {"compress2", w.Y2, 0, M, c.compress_out},
+      {"combine0", w.Y3, 0, M, c.combine_hidden}, {"x", w.X, 0, F, I}, {"d_x", w.dX, 0, F, I}, {"d_combine0", w.dY3, 0, M, c.combine_hidden},
+      {"d_compress2", w.dY2, 0, M, c.compress_out}, {"d_goal_rows", w.dG, 0, M, c.goal_dims}, {"d_compress0", w.dY1, 0, M, c.compress_hidden},
+      {"d_gi_f16", w.dgi_h, 0, F, 3 * H}, {"d_gh_f16", w.dgh_h, 0, F, 3 * H}, {"hm_f16", w.hm_h, 0, F, H},
+      {"gi", w.GI, 1, F, 3 * H}, {"h", w.Hout, 1, F, H}, {"r", w.R, 1, F, H}, {"z", w.Z, 1, F, H}, {"n", w.Nn, 1, F, H}, {"hn", w.HN, 1, F, H},
+      {"d_h", w.dH, 1, F, H}, {"d_gi", w.dGI, 1, F, 3 * H}, {"d_gh", w.dGH, 1, F, 3 * H}, {"d_logits", w.dlogits, 1, F, c.num_actions},
+      {"d_values", w.dvalues, 1, F, 1}, {"loss_scale", w.scale, 1, 1, 2}};
+  const E& e = tab[index];
+  memset(out, 0, sizeof *out);
+  snprintf(out->name, sizeof out->name, "%s", e.name);
+  out->dtype = e.dtype; out->n = 1; out->h = 1; out->w = e.rows; out->c = e.cols;
+  out->offset = (uint64_t)reinterpret_cast<uintptr_t>(e.p);      // carved from a null base: the pointer value IS the offset
+  return 0;
+}
+
 extern "C" uint64_t embclip_ac_workspace_bytes(embclip_ac_t h, int T, int N) {
   if (!h || T <= 0 || N <= 0) return 0;
   AcWs w;

@@ -159,6 +159,10 @@ int embclip_ac_num_params(embclip_ac_t h);
 int embclip_ac_param_info(embclip_ac_t h, int index, embclip_param_info* out);
 uint64_t embclip_ac_param_floats(embclip_ac_t h);
 uint64_t embclip_ac_workspace_bytes(embclip_ac_t h, int T, int N);
+/* Introspection for layer-by-layer parity tests: the intermediates of the last forward / backward on a [T, N]
+ * block live in the workspace as row-major 2-D tensors (info.w rows x info.c columns, info.offset bytes in). */
+int embclip_ac_num_acts(embclip_ac_t h);
+int embclip_ac_act_info(embclip_ac_t h, int T, int N, int index, embclip_act_info* out);
 /* Rollout features fp32 [frames, C, H*W] (what ClipResNetPreprocessor wrote into RolloutStorage) -> fp16
  * [frames*H*W, C] rows, the layout every update pass reads.  Once per rollout. */
 int embclip_ac_pack_features(embclip_ac_t h, const float* feats_nchw, long long frames, void* feats_f16, void* stream);
