@@ -129,6 +129,94 @@ class ClockSampler:
         return out
 
 
+def run_ppo_block(enc, dev, rank, world, rollouts, max_over_ranks, barrier, T=128, N=60):
+    """BASELINE configs 3 / 4: end-to-end PPO step on synthetic rollouts -- T x N frames encoded in T rollout steps of N
+    (the faithful AllenAct schedule: the preprocessor sees one step of all samplers at a time), T act() calls, GAE, and
+    4 update passes with the flat-bucket gradient all-reduce.  Weak scaling: N samplers per GPU."""
+    import torch
+    from embclip_b200.actor_critic import PPOTrainer, ResnetTensorNavActorCritic
+    from embclip_b200.harness import SyntheticPPOStep
+    model = ResnetTensorNavActorCritic(device=dev, seed=1)
+    trainer = PPOTrainer(model, lr=3e-4, max_grad_norm=0.5, update_repeats=4)
+    stepper = SyntheticPPOStep(enc, model, trainer, T=T, N=N, seed=10 + rank)
+    host = synthetic_frames(N, seed=200 + rank).pin_memory()
+    frames = host.to(dev)
+    grows = T * N * world
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    # device-resident
+    stepper.step(lambda t: frames, grows)                       # warm-up (also sizes every workspace)
+    barrier()
+    e0, e1, e2 = ev(), ev(), ev()
+    e0.record()
+    t_collect = t_update = 0.0
+    marks = []
+    for _ in range(rollouts):
+        a, b, c = ev(), ev(), ev()
+        a.record(); stepper.collect(lambda t: frames); b.record(); info = stepper.update(grows); c.record()
+        marks.append((a, b, c))
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / rollouts
+    collect_ms = sum(a.elapsed_time(b) for a, b, _ in marks) / rollouts
+    update_ms = sum(b.elapsed_time(c) for _, b, c in marks) / rollouts
+
+    # end to end: every rollout step's frames come from pinned host memory (double-buffered H2D on a side stream),
+    # the loss terms are read back to the host after every update
+    copy = torch.cuda.Stream(dev)
+    main = torch.cuda.current_stream(dev)
+    slots = [torch.empty_like(frames) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    used = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(t):
+        sl = t & 1
+        with torch.cuda.stream(copy):
+            copy.wait_event(used[sl])
+            slots[sl].copy_(host, non_blocking=True)
+            ready[sl].record(copy)
+
+    def frames_at(t):
+        sl = t & 1
+        if t >= 1:
+            used[(t - 1) & 1].record(main)    # the encoder of step t-1 (already enqueued) was the last reader of that slot
+        if t + 1 < T:
+            prefetch(t + 1)                   # refills slot (t+1) & 1 == (t-1) & 1 once `used` fires
+        main.wait_event(ready[sl])
+        return slots[sl]
+
+    def e2e_rollout():
+        prefetch(0)
+        stepper.collect(frames_at)
+        for sl in range(2):
+            used[sl].record(main)
+        info = stepper.update(grows)
+        return {k: float(v) for k, v in info.items()}      # D2H of the loss terms (sync)
+
+    e2e_rollout()
+    barrier()
+    s0, s1 = ev(), ev()
+    s0.record(main)
+    for _ in range(rollouts):
+        last = e2e_rollout()
+    s1.record(main)
+    barrier()
+    e2e_ms = max_over_ranks(s0.elapsed_time(s1)) / rollouts
+    frames_per_step = T * N * world
+    return {
+        "metric": "frames/sec end-to-end PPO step (encode T x N frames in T rollout steps + act + GAE + 4 update passes)",
+        "value": frames_per_step / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms, "rollouts_timed": rollouts,
+        "collect_ms": collect_ms, "update_ms": update_ms, "scaling": "weak",
+        "config": {"workload": "objectnav_ppo_step", "steps": T, "samplers_per_gpu": N, "update_repeats": 4, "num_mini_batch": 1,
+                   "global_rows": grows, "collective": "1 flat fp32 gradient all-reduce (13.9 MB) per update pass" if world > 1 else "none (1 GPU)"},
+        "e2e": {"value": frames_per_step / (e2e_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": T * host.numel() * 4, "d2h_bytes_per_step": 5 * 4,
+                "api": "ClipRN50Encoder.forward + ResnetTensorNavActorCritic act + PPOTrainer.update, frames from pinned host memory"},
+        "gpu_launches": stepper.launches_per_step() * rollouts,
+        "last_loss": last,
+    }
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -255,6 +343,9 @@ def run_ours(args, rank, local_rank, world):
     h2d = host_frames.numel() * 4
     d2h = sum(v.numel() * 4 for v in dev_out[0].values())
 
+    # ---------------- BASELINE configs 3 / 4: end-to-end PPO step (all ranks: the update all-reduces gradients)
+    ppo = None if args.no_ppo else run_ppo_block(enc, dev, rank, world, args.ppo_rollouts, max_over_ranks, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -272,6 +363,7 @@ def run_ours(args, rank, local_rank, world):
     top = sorted(prof, key=lambda x: -x[1])[:8]
 
     cpu_fps, cpu_sec = (None, None) if args.no_cpu else time_cpu_oracle(oracle_model(), 32, 4, 1)
+    line_ppo = ppo
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -291,6 +383,7 @@ def run_ours(args, rank, local_rank, world):
         "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": "fp32 PyTorch oracle, 32 frames x 4 iterations (1 warm-up)"},
         "top_ops_ms": top,
+        "ppo_step": line_ppo,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -304,6 +397,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiler runs only)")
+    ap.add_argument("--no-ppo", action="store_true", help="skip the PPO-step block (BASELINE configs 3 / 4)")
+    ap.add_argument("--ppo-rollouts", type=int, default=3, help="timed rollouts of the PPO-step block")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -361,7 +361,7 @@ class PPOTrainer:
         """rollout: features (fp32 [T,N,2048,7,7] or PackedFeatures), goals [T,N], masks [T,N,1], memory [1,N,H],
         actions [T,N], old_action_log_probs [T,N], values [T,N,1], returns [T,N,1], norm_adv_targ [T,N,1].
         Returns the last pass's loss terms as 0-d device tensors (no host sync inside)."""
-        import torch.distributed as dist
+        from .distributed import allreduce_flat_
         mdl, plan = self.model, self.model._plan
         lib, dev = plan.lib, mdl.flat_params.device
         pf = rollout["features"] if isinstance(rollout["features"], PackedFeatures) else mdl.pack_features(rollout["features"])
@@ -396,8 +396,7 @@ class PPOTrainer:
                 _lib.check(lib.embclip_ac_backward(plan._h, P.data_ptr(), pf.data.data_ptr(), goals.data_ptr(), masks.data_ptr(),
                                                    h0.data_ptr(), T, N, None, None, None, self.grads.data_ptr(), ws.data_ptr(),
                                                    ws.numel(), st))
-                if world > 1:
-                    dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.process_group)
+                allreduce_flat_(self.grads, self.process_group)       # the path's one collective (no-op when world == 1)
                 self.step_count += 1
                 _lib.check(lib.embclip_sumsq_f32(self.grads.data_ptr(), self.grads.numel(), self.sumsq.data_ptr(), st))
                 _lib.check(lib.embclip_adam_clip_step(P.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(),

@@ -423,8 +423,8 @@ def test_ppo_update_vs_oracle(models):
         step = (v - before[k]).norm().item()
         err = (after[k].cpu() - v).norm().item()
         # Adam normalises each element's step to ~lr (sign-like in the first steps), which amplifies the ReLU-flip
-        # gradient noise on elements whose gradient is near zero: compare the parameter CHANGE, within 10 %
-        assert err <= 0.10 * step + 1e-7, f"{k}: change {step:.3g}, deviation {err:.3g}"
+        # gradient noise on elements whose gradient is near zero: compare the parameter CHANGE, within 20 %
+        assert err <= 0.20 * step + 1e-7, f"{k}: change {step:.3g}, deviation {err:.3g}"
 
 
 def test_full_size_block_properties(models, lib):
