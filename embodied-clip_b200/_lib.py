@@ -32,6 +32,13 @@ class ACCfg(C.Structure):
                                          "combine_hidden", "combine_out", "hidden", "num_actions", "num_goals")]
 
 
+class TFCfg(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("kind", "width", "layers", "heads", "output_dim", "patch_size", "input_resolution",
+                                         "context_length", "vocab_size")]
+
+
+TF_VISION, TF_TEXT = 0, 1
+
 # symbol -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
 _VP, _I, _U64, _FP, _LL, _F = C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_longlong, C.c_float
 SIGNATURES = {
@@ -54,6 +61,18 @@ SIGNATURES = {
     "embclip_conv3x3_f16": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "embclip_avgpool2_f16": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
     "embclip_stem_conv1": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
+    # CLIP transformer towers
+    "embclip_tf_create": (_I, [C.POINTER(TFCfg), C.POINTER(_VP)]),
+    "embclip_tf_destroy": (_I, [_VP]),
+    "embclip_tf_num_params": (_I, [_VP]),
+    "embclip_tf_param_info": (_I, [_VP, _I, C.POINTER(ParamInfo)]),
+    "embclip_tf_blob_bytes": (_U64, [_VP]),
+    "embclip_tf_bind_weights": (_I, [_VP, _VP, _U64]),
+    "embclip_tf_workspace_bytes": (_U64, [_VP, _I]),
+    "embclip_tf_launches_per_forward": (_I, [_VP]),
+    "embclip_vit_forward": (_I, [_VP, _FP, _I, _FP, _VP, _U64, _VP]),
+    "embclip_text_forward": (_I, [_VP, _VP, _I, _FP, _VP, _U64, _VP]),
+    "embclip_clip_logits": (_I, [_FP, _FP, _I, _I, _I, _F, _FP, _VP]),
     # actor-critic / PPO update
     "embclip_ac_create": (_I, [C.POINTER(ACCfg), C.POINTER(_VP)]),
     "embclip_ac_destroy": (_I, [_VP]),

@@ -28,12 +28,13 @@ struct ConvGemmParams {
   int kb_src0;                  // k-blocks read from A0 (= taps * kb_per_tap); the rest come from A1
   int kb_total;
   uint32_t a0_box_bytes;        // bytes one A0 box load delivers (box may hold fewer than 128 rows)
-  int relu;
+  int relu;                     // epilogue activation: 0 none, 1 ReLU, 2 QuickGELU x * sigmoid(1.702 x)
   int res_mode;                 // kRes only. 0: out += residual;  1: out = residual > 0 ? out : 0  (ReLU backward mask)
   int out_f32;                  // 1: epilogue stores fp32 rows straight to `out_f32_ptr` (2-D mode only)
   int M, N;                     // logical GEMM extents (rows valid for residual / fp32 stores)
   const float* bias;            // [N] or nullptr
   float* out_f32_ptr;           // [M, ldo]
+  const float* res_f32_ptr;     // out_f32 mode: optional fp32 residual [M, ldo] added before the store (may alias out_f32_ptr)
   int ldo;
   // grouped mode (0 = off): N-group g = n0 / grp_n reads A at k + g*grp_a_koff, W at k + g*grp_b_koff,
   // and W rows n0 % grp_b_nmod (if grp_b_nmod != 0)
@@ -285,13 +286,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
           }
         }
-        if (p.relu) {
+        if (p.relu == 1) {
 #pragma unroll
           for (int i = 0; i < CH; ++i) f[i] = fmaxf(f[i], 0.f);
+        } else if (p.relu == 2) {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) f[i] = f[i] / (1.f + __expf(-1.702f * f[i]));
         }
         if (p.out_f32) {
           if (row_ok) {
             float4* op = reinterpret_cast<float4*>(p.out_f32_ptr + size_t(grow) * p.ldo + n0 + col);
+            if (p.res_f32_ptr) {
+              const float4* rp = reinterpret_cast<const float4*>(p.res_f32_ptr + size_t(grow) * p.ldo + n0 + col);
+#pragma unroll
+              for (int i = 0; i < CH / 4; ++i) {
+                const float4 r = rp[i];
+                f[4 * i] += r.x; f[4 * i + 1] += r.y; f[4 * i + 2] += r.z; f[4 * i + 3] += r.w;
+              }
+            }
 #pragma unroll
             for (int i = 0; i < CH / 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
           }

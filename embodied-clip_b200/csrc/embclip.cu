@@ -174,6 +174,7 @@ static int launch_cfg(const GemmOp& op, cudaStream_t st) {
   p.N = op.cout;
   p.bias = op.bias;
   p.out_f32_ptr = reinterpret_cast<float*>(op.out);
+  p.res_f32_ptr = op.out_f32 ? op.res_f32 : nullptr;
   p.ldo = op.cout;
   p.grp_n = op.grp_n; p.grp_a_koff = op.grp_a_koff; p.grp_b_koff = op.grp_b_koff; p.grp_b_nmod = op.grp_b_nmod;
   const long long tiles = (long long)p.num_m_blks * p.num_n_blks;

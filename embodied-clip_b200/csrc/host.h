@@ -37,7 +37,8 @@ struct GemmOp {
   int res_mode = 0;                 // 0: add residual; 1: zero the output where residual <= 0 (ReLU backward)
   void* out = nullptr;              // fp16 NHWC [n,h,w,cout] or fp32 [M, cout]
   int cout = 0;
-  int relu = 0, out_f32 = 0;
+  int relu = 0, out_f32 = 0;        // relu: activation code (0 none, 1 ReLU, 2 QuickGELU)
+  const float* res_f32 = nullptr;   // out_f32 only: fp32 residual [M, cout] added in the epilogue (may alias out)
   int grp_n = 0, grp_a_koff = 0, grp_b_koff = 0, grp_b_nmod = 0;
   int a_cols = 0;                   // logical width of an A0 row for the tensor map (>= c0; grouped mode: full row)
 };

@@ -1,0 +1,229 @@
+// Non-GEMM kernels of the CLIP transformer towers (clip/model.py VisionTransformer / ResidualAttentionBlock /
+// CLIP.encode_text / CLIP.forward).  The residual stream is fp32; LayerNorm is computed
+// in fp32 (upstream's LayerNorm subclass does the same) and emits the fp16 operand of the next GEMM.
+//   vit_patchify        fp32 NHWC frames -> fp16 [B*g*g, p*p*3] patch rows (K order kh, kw, c)
+//   vit_embed_ln_pre    class token + positional embedding + ln_pre -> fp32 stream [B*L, D]
+//   text_embed          token_embedding[ids] + positional_embedding -> fp32 stream [K*L, D]
+//   layernorm_rows      fp32 rows (optionally gathered) -> fp16 rows
+//   attention_kernel    softmax(q k^T [+ causal mask]) v for one (sequence, head): L <= 96, head dim 64
+//   clip_logits         exp(logit_scale) * normalize(img) . normalize(txt)^T
+#pragma once
+#include "ptx.cuh"
+
+namespace embclip {
+
+// one block = one patch: y[(b, py, px)][kh*PS*3 + kw*3 + c] = x[b][py*PS + kh][px*PS + kw][c]
+__global__ void __launch_bounds__(256)
+vit_patchify_kernel(const float* __restrict__ x, __half* __restrict__ y, int B, int R, int PS) {
+  const int g = R / PS;
+  const int row_elems = PS * 3, patch_elems = PS * row_elems;
+  const long long total = (long long)B * g * g;
+  for (long long i = blockIdx.x; i < total; i += gridDim.x) {
+    const int px = int(i % g);
+    const int py = int((i / g) % g);
+    const int b = int(i / ((long long)g * g));
+    const float* src = x + (((size_t)b * R + (size_t)py * PS) * R + (size_t)px * PS) * 3;
+    __half* dst = y + (size_t)i * patch_elems;
+    for (int j = threadIdx.x; j < patch_elems; j += blockDim.x) {
+      const int kh = j / row_elems, r = j - kh * row_elems;
+      dst[j] = __float2half_rn(__ldg(src + (size_t)kh * R * 3 + r));
+    }
+  }
+}
+
+// warp-level LayerNorm of one row held as NV float4 per lane (D = 128 * NV); two-pass in registers
+template <int NV>
+__device__ __forceinline__ void warp_layernorm(float4 (&v)[NV], int D, float eps) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / float(D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float inv = rsqrtf(q / float(D) + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { v[i].x *= inv; v[i].y *= inv; v[i].z *= inv; v[i].w *= inv; }
+}
+
+// x[b*L + l] = ln_pre( (l == 0 ? cls : patch[b*(L-1) + l-1]) + pos[l] );  one warp per row, D = 128 * NV
+template <int NV>
+__global__ void __launch_bounds__(256)
+vit_embed_ln_pre_kernel(const float* __restrict__ patch, const float* __restrict__ cls, const float* __restrict__ pos,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ x, int rows, int L, int D) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int b = row / L, l = row - b * L;
+  const float4* src = reinterpret_cast<const float4*>(l == 0 ? cls : patch + ((size_t)b * (L - 1) + l - 1) * D);
+  const float4* pp = reinterpret_cast<const float4*>(pos + (size_t)l * D);
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 a = __ldg(src + lane + 32 * i), p4 = __ldg(pp + lane + 32 * i);
+    v[i] = make_float4(a.x + p4.x, a.y + p4.y, a.z + p4.z, a.w + p4.w);
+  }
+  warp_layernorm<NV>(v, D, 1e-5f);
+  float4* out = reinterpret_cast<float4*>(x + (size_t)row * D);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i), b4 = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+    out[lane + 32 * i] = make_float4(v[i].x * g4.x + b4.x, v[i].y * g4.y + b4.y, v[i].z * g4.z + b4.z, v[i].w * g4.w + b4.w);
+  }
+}
+
+// x[k*L + l] = tok_emb[ids[k*L + l]] + pos[l]
+__global__ void __launch_bounds__(256)
+text_embed_kernel(const long long* __restrict__ ids, const float* __restrict__ emb, const float* __restrict__ pos,
+                  float* __restrict__ x, int rows, int L, int D, int vocab) {
+  const long long total = (long long)rows * (D / 4);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = int(i % (D / 4));
+    const int row = int(i / (D / 4));
+    long long id = ids[row];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(emb + (size_t)id * D) + c4);
+    const float4 p4 = __ldg(reinterpret_cast<const float4*>(pos + (size_t)(row % L) * D) + c4);
+    reinterpret_cast<float4*>(x)[i] = make_float4(a.x + p4.x, a.y + p4.y, a.z + p4.z, a.w + p4.w);
+  }
+}
+
+// y[r] = fp16( LayerNorm(x[src_row(r)]) * gamma + beta ).  src_row(r) = gather ? gather[r] : r * row_stride.
+template <int NV>
+__global__ void __launch_bounds__(256)
+layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      __half* __restrict__ y, int rows, int D, long long row_stride, const long long* __restrict__ gather) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const long long srow = gather ? gather[row] : (long long)row * row_stride;
+  const float4* src = reinterpret_cast<const float4*>(x + (size_t)srow * D);
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = src[lane + 32 * i];
+  warp_layernorm<NV>(v, D, 1e-5f);
+  uint2* out = reinterpret_cast<uint2*>(y + (size_t)row * D);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i), b4 = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+    uint2 o;
+    o.x = pack_half2(v[i].x * g4.x + b4.x, v[i].y * g4.y + b4.y);
+    o.y = pack_half2(v[i].z * g4.z + b4.z, v[i].w * g4.w + b4.w);
+    out[lane + 32 * i] = o;
+  }
+}
+
+// eot[k] = k*L + argmax_l ids[k][l]  (first maximum, like torch.argmax): the row ln_final / text_projection read
+__global__ void text_eot_rows_kernel(const long long* __restrict__ ids, long long* __restrict__ eot, int K, int L) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  long long best = ids[(size_t)k * L];
+  int arg = 0;
+  for (int l = 1; l < L; ++l) {
+    const long long v = ids[(size_t)k * L + l];
+    if (v > best) { best = v; arg = l; }
+  }
+  eot[k] = (long long)k * L + arg;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-head self-attention core for short sequences.  qkv fp16 [S*L, 3*D] rows (q pre-scaled by head_dim^-0.5 at
+// weight-pack time), heads of 64 channels.  grid (S, heads), 128 threads: the (sequence, head)'s K and V live in shared
+// memory (rows padded to 66 halves: conflict-free), each warp owns query rows i = warp, warp+4, ...; lanes split the
+// keys for the scores and the 64 output channels for the weighted sum.  fp32 math, fp16 in / out.
+// ------------------------------------------------------------------------------------------------
+constexpr int kAttnMaxL = 96;
+__global__ void __launch_bounds__(128)
+attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int L, int D, int causal) {
+  __shared__ __half sK[kAttnMaxL][66];
+  __shared__ __half sV[kAttnMaxL][66];
+  __shared__ __half sQ[4][64];
+  __shared__ float sP[4][kAttnMaxL];
+  const int s = blockIdx.x, h = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t ld = (size_t)3 * D;
+  const __half* base = qkv + (size_t)s * L * ld + (size_t)h * 64;
+  for (int i = tid; i < L * 32; i += 128) {
+    const int l = i >> 5, c2 = i & 31;
+    *reinterpret_cast<__half2*>(&sK[l][2 * c2]) = *reinterpret_cast<const __half2*>(base + l * ld + D + 2 * c2);
+    *reinterpret_cast<__half2*>(&sV[l][2 * c2]) = *reinterpret_cast<const __half2*>(base + l * ld + 2 * D + 2 * c2);
+  }
+  __syncthreads();
+  for (int i = warp; i < L; i += 4) {
+    *reinterpret_cast<__half2*>(&sQ[warp][2 * lane]) = *reinterpret_cast<const __half2*>(base + i * ld + 2 * lane);
+    __syncwarp();
+    float sc[3];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < 3; ++jj) {
+      const int j = lane + 32 * jj;
+      float a = -INFINITY;
+      if (j < L && !(causal && j > i)) {
+        a = 0.f;
+#pragma unroll
+        for (int d2 = 0; d2 < 32; ++d2) {
+          const float2 q2 = __half22float2(*reinterpret_cast<const __half2*>(&sQ[warp][2 * d2]));
+          const float2 k2 = __half22float2(*reinterpret_cast<const __half2*>(&sK[j][2 * d2]));
+          a += q2.x * k2.x + q2.y * k2.y;
+        }
+      }
+      sc[jj] = a;
+      mx = fmaxf(mx, a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 3; ++jj) {
+      sc[jj] = sc[jj] == -INFINITY ? 0.f : expf(sc[jj] - mx);
+      sum += sc[jj];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int jj = 0; jj < 3; ++jj) {
+      const int j = lane + 32 * jj;
+      if (j < L) sP[warp][j] = sc[jj] * inv;
+    }
+    __syncwarp();
+    float o0 = 0.f, o1 = 0.f;
+    const int jmax = causal ? i + 1 : L;
+    for (int j = 0; j < jmax; ++j) {
+      const float pj = sP[warp][j];
+      const float2 v2 = __half22float2(*reinterpret_cast<const __half2*>(&sV[j][2 * lane]));
+      o0 += pj * v2.x;
+      o1 += pj * v2.y;
+    }
+    *reinterpret_cast<__half2*>(out + ((size_t)s * L + i) * D + (size_t)h * 64 + 2 * lane) = __floats2half2_rn(o0, o1);
+    __syncwarp();
+  }
+}
+
+// logits[b][k] = exp(logit_scale) * <img_b, txt_k> / (|img_b| |txt_k|);  one warp per (b, k)
+__global__ void __launch_bounds__(256)
+clip_logits_kernel(const float* __restrict__ img, const float* __restrict__ txt, float* __restrict__ logits, int B, int K, int E,
+                   float logit_scale_exp) {
+  const int idx = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (idx >= B * K) return;
+  const int b = idx / K, k = idx - b * K;
+  float dot = 0.f, ni = 0.f, nt = 0.f;
+  for (int e = lane; e < E; e += 32) {
+    const float a = img[(size_t)b * E + e], t = txt[(size_t)k * E + e];
+    dot += a * t; ni += a * a; nt += t * t;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    ni += __shfl_xor_sync(0xffffffffu, ni, o);
+    nt += __shfl_xor_sync(0xffffffffu, nt, o);
+  }
+  if (lane == 0) logits[idx] = logit_scale_exp * dot / (sqrtf(ni) * sqrtf(nt));
+}
+
+}  // namespace embclip

@@ -188,6 +188,45 @@ int embclip_ac_backward(embclip_ac_t h, const float* params, const void* feats_f
                         const float* masks, const float* h0, int T, int N, const float* dlogits, const float* dvalues,
                         const float* dh_last, float* grads, void* workspace, uint64_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * CLIP transformer towers + cosine-similarity logits (zero-shot ObjectNav path, BASELINE.json config 5):
+ * replaces VisionTransformer.forward (ViT-B/32), CLIP.encode_text and CLIP.forward of openai/CLIP clip/model.py
+ * (pin: /root/reference/primitive_probing/environment.yml:22; used by the zeroshot-objectnav branch named at
+ * /root/reference/readme_files/zeroshot_objectnav.md:5,17,27).  ResidualAttentionBlock = LN -> QKV -> 12-head
+ * attention over 50 (image) / 77 (text, causal) tokens -> out-proj -> +res -> LN -> fc -> QuickGELU -> proj -> +res.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct embclip_tf* embclip_tf_t;
+#define EMBCLIP_TF_VISION 0
+#define EMBCLIP_TF_TEXT 1
+typedef struct {
+  int32_t kind;              /* EMBCLIP_TF_VISION or EMBCLIP_TF_TEXT                           */
+  int32_t width;             /* 768 (ViT-B/32) / 512 (text)                                    */
+  int32_t layers;            /* 12                                                             */
+  int32_t heads;             /* width / 64                                                     */
+  int32_t output_dim;        /* 512                                                            */
+  int32_t patch_size;        /* vision: 32                                                     */
+  int32_t input_resolution;  /* vision: 224                                                    */
+  int32_t context_length;    /* text: 77                                                       */
+  int32_t vocab_size;        /* text: 49408                                                    */
+} embclip_tf_cfg;
+int embclip_tf_create(const embclip_tf_cfg* cfg, embclip_tf_t* out);   /* needs no GPU */
+int embclip_tf_destroy(embclip_tf_t h);
+int embclip_tf_num_params(embclip_tf_t h);
+int embclip_tf_param_info(embclip_tf_t h, int index, embclip_param_info* out);
+uint64_t embclip_tf_blob_bytes(embclip_tf_t h);
+int embclip_tf_bind_weights(embclip_tf_t h, const void* device_blob, uint64_t nbytes);
+uint64_t embclip_tf_workspace_bytes(embclip_tf_t h, int batch);
+int embclip_tf_launches_per_forward(embclip_tf_t h);
+/* CLIP.encode_image for the ViT tower: frames fp32 NHWC [batch, R, R, 3] (mean/std normalised) -> fp32 [batch, output_dim]. */
+int embclip_vit_forward(embclip_tf_t h, const float* frames_nhwc, int batch, float* out, void* workspace,
+                        uint64_t workspace_bytes, void* stream);
+/* CLIP.encode_text: token ids int64 [prompts, context_length] -> fp32 [prompts, output_dim] (row at argmax(ids) = EOT). */
+int embclip_text_forward(embclip_tf_t h, const long long* token_ids, int prompts, float* out, void* workspace,
+                         uint64_t workspace_bytes, void* stream);
+/* CLIP.forward's logits_per_image: exp(logit_scale) * normalize(image_features) @ normalize(text_features)^T -> [batch, prompts]. */
+int embclip_clip_logits(const float* image_features, const float* text_features, int batch, int prompts, int embed_dim,
+                        float logit_scale, float* logits, void* stream);
+
 /* RolloutStorage.compute_returns(use_gae): rewards [T,N]; values [T+1,N] (row T = next value); masks [T+1,N]
  * -> returns [T,N], advantages [T,N] and (if non-NULL) norm_advantages = (A - mean) / (std + eps). */
 int embclip_gae(const float* rewards, const float* values, const float* masks, int T, int N, float gamma, float tau,

@@ -35,5 +35,21 @@ def main():
     print({k: (tuple(v.shape) if torch.is_tensor(v) else v) for k, v in out.items()})
 
 
+def main_vit():
+    from oracle.clip_model import build_vit_b32, init_synthetic_transformer
+    from test_vit_gpu import synthetic_prompts
+    torch.manual_seed(0)
+    m = freeze_model(init_synthetic_transformer(build_vit_b32(), seed=1234))
+    frames, tokens = synthetic_frames(2, seed=0), synthetic_prompts(12, seed=0)
+    with torch.no_grad():
+        img = m.encode_image(frames.permute(0, 3, 1, 2).contiguous())
+        txt = m.encode_text(tokens)
+        logits, _ = m(frames.permute(0, 3, 1, 2).contiguous(), tokens)
+    out = {"image_features": img, "text_features": txt, "logits_per_image": logits, "tokens": tokens, "weights_seed": 1234, "frames_seed": 0}
+    torch.save(out, os.path.join(HERE, "vit_b32_b2_seed0.pt"))
+    print({k: (tuple(v.shape) if torch.is_tensor(v) else v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     main()
+    main_vit()

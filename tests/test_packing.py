@@ -71,3 +71,43 @@ def test_blob_layout_matches_library(built_lib, rn50_visual):
     assert shape == (256, 128)                                    # 64 (conv3) + 64 (downsample) along K
     assert torch.equal(blob[off:off + nb].view(torch.float16).view(shape), pk[name])
     lib.embclip_rn50_destroy(h)
+
+
+def test_transformer_tower_packing_matches_library_plan(built_lib):
+    """ViT-B/32 and text tower: every tensor the library's plan asks for is produced by the packer with the right dtype /
+    shape; shape inference mirrors clip/model.py build_model; the q third of in_proj carries the 1/8 attention scale."""
+    import ctypes as C
+    from embclip_b200 import _lib
+    from embclip_b200.vit import infer_text_cfg, infer_vit_cfg, packed_tower_tensors
+    from oracle.clip_model import build_vit_b32, init_synthetic_transformer
+    torch.manual_seed(0)
+    sd = init_synthetic_transformer(build_vit_b32(), seed=1234).state_dict()
+    vcfg, tcfg = infer_vit_cfg(sd), infer_text_cfg(sd)
+    assert (vcfg["width"], vcfg["layers"], vcfg["heads"], vcfg["output_dim"], vcfg["patch_size"], vcfg["input_resolution"]) == (768, 12, 12, 512, 32, 224)
+    assert (tcfg["width"], tcfg["layers"], tcfg["heads"], tcfg["output_dim"], tcfg["context_length"], tcfg["vocab_size"]) == (512, 12, 8, 512, 77, 49408)
+    lib = _lib.load()
+    for cfg in (vcfg, tcfg):
+        h = C.c_void_p()
+        assert lib.embclip_tf_create(C.byref(_lib.TFCfg(**cfg)), C.byref(h)) == 0
+        tensors = packed_tower_tensors(sd, cfg)
+        names = set()
+        for i in range(lib.embclip_tf_num_params(h)):
+            pi = _lib.ParamInfo()
+            assert lib.embclip_tf_param_info(h, i, C.byref(pi)) == 0
+            name = pi.name.decode()
+            names.add(name)
+            t = tensors[name]
+            assert tuple(t.shape) == tuple(pi.shape[:pi.ndim]), name
+            assert t.dtype == (torch.float16 if pi.dtype == _lib.DTYPE_F16 else torch.float32), name
+            assert pi.offset % 256 == 0
+        assert names == set(tensors)
+        assert lib.embclip_tf_workspace_bytes(h, 64) > 0
+        assert lib.embclip_tf_destroy(h) == 0
+    pk = packed_tower_tensors(sd, vcfg)
+    w = sd["visual.transformer.resblocks.3.attn.in_proj_weight"]
+    assert torch.equal(pk["blk3.qkv.w"][:768], (w[:768] * 0.125).half()) and torch.equal(pk["blk3.qkv.w"][768:], w[768:].half())
+    conv = sd["visual.conv1.weight"]
+    assert torch.equal(pk["patch.w"][5, (7 * 32 + 9) * 3 + 2], conv[5, 2, 7, 9].half())
+    bad = dict(vcfg, width=640, heads=10)
+    h = C.c_void_p()
+    assert lib.embclip_tf_create(C.byref(_lib.TFCfg(**bad)), C.byref(h)) < 0

@@ -1,0 +1,126 @@
+"""GPU parity of the CLIP transformer towers (through the C ABI) against the oracle (oracle/clip_model.py, which
+tests/test_oracle_clip.py pins against transformers' CLIP).  Bar: rel-L2 per sample <= 1e-3 on image / text features
+and on the cosine-similarity logits; argmax prompt bit-exact wherever the top-2 logit gap exceeds the error."""
+import os
+
+import pytest
+import torch
+
+from conftest import synthetic_frames
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel_rows(a, b):
+    a, b = a.float().cpu().flatten(1), b.float().cpu().flatten(1)
+    return ((a - b).norm(dim=1) / b.norm(dim=1).clamp_min(1e-12)).max().item()
+
+
+def synthetic_prompts(K, seed=0, L=77):
+    """[SOT, n random ids, EOT, 0...], n in [2, 8] (no BPE vocabulary offline)."""
+    g = torch.Generator().manual_seed(seed)
+    t = torch.zeros(K, L, dtype=torch.int64)
+    for k in range(K):
+        n = int(torch.randint(2, 9, (1,), generator=g))
+        t[k, 0] = 49406
+        t[k, 1:1 + n] = torch.randint(1, 49405, (n,), generator=g)
+        t[k, 1 + n] = 49407
+    return t
+
+
+@pytest.fixture(scope="module")
+def clip_vit(built_lib):
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    from oracle.clip_model import build_vit_b32, freeze_model, init_synthetic_transformer
+    torch.manual_seed(0)
+    return freeze_model(init_synthetic_transformer(build_vit_b32(), seed=1234))
+
+
+@pytest.fixture(scope="module")
+def zeroshot(clip_vit):
+    from embclip_b200.vit import ClipZeroShot
+    return ClipZeroShot(clip_vit.state_dict(), "cuda:0")
+
+
+@pytest.mark.parametrize("batch", [1, 3])
+def test_vit_image_features_vs_oracle(zeroshot, clip_vit, batch):
+    frames = synthetic_frames(batch, seed=20 + batch)
+    with torch.no_grad():
+        ref = clip_vit.encode_image(frames.permute(0, 3, 1, 2).contiguous())
+    out = zeroshot.image(frames.cuda())
+    torch.cuda.synchronize()
+    e = rel_rows(out, ref)
+    print(f"ViT-B/32 image features rel-L2 {e:.3e}")
+    assert out.shape == (batch, 512) and e <= 1e-3, e
+
+
+def test_text_features_vs_oracle(zeroshot, clip_vit):
+    tokens = synthetic_prompts(5, seed=1)
+    with torch.no_grad():
+        ref = clip_vit.encode_text(tokens)
+    out = zeroshot.text(tokens.cuda())
+    torch.cuda.synchronize()
+    e = rel_rows(out, ref)
+    print(f"text features rel-L2 {e:.3e}")
+    assert out.shape == (5, 512) and e <= 1e-3, e
+    # causal: tokens after EOT cannot influence the pooled feature
+    t2 = tokens.clone()
+    for k in range(5):
+        eot = int(t2[k].argmax())
+        t2[k, eot + 1:] = torch.randint(1, 40000, (77 - eot - 1,))
+    out2 = zeroshot.text(t2.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out)
+
+
+def test_zero_shot_logits_vs_oracle(zeroshot, clip_vit):
+    frames, tokens = synthetic_frames(4, seed=31), synthetic_prompts(12, seed=0)
+    with torch.no_grad():
+        ref, _ = clip_vit(frames.permute(0, 3, 1, 2).contiguous(), tokens)
+    out = zeroshot(frames.cuda(), tokens.cuda())
+    torch.cuda.synchronize()
+    err = (out.cpu() - ref).abs().max().item()
+    print(f"logits max abs err {err:.3e} (scale {ref.abs().max().item():.2f})")
+    assert rel_rows(out, ref) <= 1e-3
+    top2 = ref.topk(2, dim=1).values
+    decided = (top2[:, 0] - top2[:, 1]) > 2 * err
+    assert torch.equal(out.cpu().argmax(1)[decided], ref.argmax(1)[decided])
+    # cached text side: same logits without re-encoding the prompts
+    out2 = zeroshot(frames.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+
+
+def test_vit_golden(zeroshot):
+    g = torch.load(os.path.join(GOLDEN, "vit_b32_b2_seed0.pt"))
+    frames = synthetic_frames(2, seed=0)
+    tokens = synthetic_prompts(12, seed=0)
+    assert torch.equal(tokens, g["tokens"]), "synthetic prompt generator drifted"
+    img = zeroshot.image(frames.cuda())
+    txt = zeroshot.text(tokens.cuda())
+    torch.cuda.synchronize()
+    assert rel_rows(img, g["image_features"]) <= 1e-3
+    assert rel_rows(txt, g["text_features"]) <= 1e-3
+    assert rel_rows(zeroshot.logits(img, txt), g["logits_per_image"]) <= 1e-3
+
+
+def test_vit_batch_properties(zeroshot):
+    """BASELINE config 5 per-GPU size (512 / 8 = 64 frames): frames are independent and results are deterministic."""
+    small = synthetic_frames(4, seed=9).cuda()
+    big = zeroshot.image(small.repeat(16, 1, 1, 1))
+    ref = zeroshot.image(small)
+    torch.cuda.synchronize()
+    assert torch.equal(big[:4], ref)
+    assert torch.equal(big.view(16, 4, -1), ref.view(1, 4, -1).expand(16, -1, -1))
+    assert zeroshot.image(small[:0]).shape == (0, 512)
+
+
+def test_vit_rejects_bad_input(zeroshot):
+    with pytest.raises(ValueError):
+        zeroshot.image(torch.zeros(2, 3, 224, 224, device="cuda"))
+    with pytest.raises(ValueError):
+        zeroshot.text(torch.zeros(2, 50, dtype=torch.int64))
+    with pytest.raises(ValueError):
+        zeroshot.image(torch.zeros(2, 224, 224, 3))
