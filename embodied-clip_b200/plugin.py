@@ -172,3 +172,72 @@ class ClipResNetPreprocessor(_Base):
         if x.shape[-1] == 1:                             # depth: repeat across the 3 channels
             x = x.repeat(1, 1, 1, 3)
         return self.resnet.forward_nhwc(x.float().contiguous())
+
+
+class ClipViTEmbedder:
+    """Mirror of clip_preprocessors.py `ClipViTEmbedder`: NCHW frames [B,3,224,224] -> CLIP ViT image features [B,512]."""
+
+    def __init__(self, clip_state_dict: Dict[str, torch.Tensor], device: Any = "cuda:0"):
+        from .vit import ClipViTEncoder
+        self.encoder = ClipViTEncoder(clip_state_dict, device)
+
+    def eval(self) -> "ClipViTEmbedder":
+        return self
+
+    def forward_nhwc(self, x_nhwc: torch.Tensor) -> torch.Tensor:
+        return self.encoder(x_nhwc)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.forward_nhwc(x.permute(0, 2, 3, 1).contiguous().float())
+
+    __call__ = forward
+
+
+class ClipViTPreprocessor(_Base):
+    """Mirror of allenact_plugins/clip_plugin `ClipViTPreprocessor` (the zero-shot ObjectNav configs,
+    /root/reference/readme_files/zeroshot_objectnav.md:17,27): process(obs) -> float32 [B,512] image features."""
+
+    CLIP_RGB_MEANS = ClipResNetPreprocessor.CLIP_RGB_MEANS
+    CLIP_RGB_STDS = ClipResNetPreprocessor.CLIP_RGB_STDS
+    SUPPORTED = {"ViT-B/32": (512,)}
+
+    def __init__(self, rgb_input_uuid: str, clip_model_type: str = "ViT-B/32", device: Optional[torch.device] = None,
+                 device_ids: Optional[Sequence[Any]] = None, output_uuid: str = "rgb_clip_vit",
+                 clip_state_dict: Optional[Dict[str, torch.Tensor]] = None, weights_path: Optional[str] = None, **kwargs: Any):
+        if clip_model_type not in self.SUPPORTED:
+            raise AssertionError(f"clip_model_type '{clip_model_type}' not built for B200 (available: {sorted(self.SUPPORTED)})")
+        self.clip_model_type = clip_model_type
+        self.device = torch.device("cpu") if device is None else torch.device(device)
+        self.device_ids = list(device_ids) if device_ids is not None else list(range(torch.cuda.device_count()))
+        self._clip_state_dict, self._weights_path = clip_state_dict, weights_path
+        self._vit: Optional[ClipViTEmbedder] = None
+        super().__init__(input_uuids=[rgb_input_uuid], output_uuid=output_uuid,
+                         observation_space=_make_box(self.SUPPORTED[clip_model_type]), **kwargs)
+
+    @property
+    def vit(self) -> ClipViTEmbedder:
+        if self._vit is None:
+            if self.device.type != "cuda":
+                raise RuntimeError("ClipViTPreprocessor (embclip_b200): no CPU path -- call .to(cuda device) first")
+            if self._clip_state_dict is None and not (self._weights_path or os.environ.get("EMBCLIP_CLIP_WEIGHTS")):
+                try:                                    # pragma: no cover - package absent offline
+                    import clip
+                    self._clip_state_dict = clip.load(self.clip_model_type, device="cpu")[0].state_dict()
+                except ImportError:
+                    raise RuntimeError("ClipViTPreprocessor: pass clip_state_dict=..., set $EMBCLIP_CLIP_WEIGHTS or install openai/CLIP")
+            sd = load_clip_visual_state_dict(self.clip_model_type, self._clip_state_dict, self._weights_path)
+            self._vit = ClipViTEmbedder(sd, device=self.device)
+        return self._vit
+
+    def to(self, device: torch.device) -> "ClipViTPreprocessor":
+        device = torch.device(device)
+        if self._vit is not None and device != self.device:
+            self._vit = None
+        self.device = device
+        return self
+
+    def process(self, obs: Dict[str, Any], *args: Any, **kwargs: Any) -> Any:
+        x = obs[self.input_uuids[0]].to(self.device)
+        if x.shape[-1] == 1:
+            x = x.repeat(1, 1, 1, 3)
+        return self.vit.forward_nhwc(x.float().contiguous())

@@ -62,3 +62,28 @@ def test_depth_input_is_repeated(built_lib, rn50_visual):
     a = p.process({"depth": d})
     b = p.process({"depth": d.repeat(1, 1, 1, 3)})
     assert torch.equal(a, b)
+
+
+def test_vit_surface():
+    from embclip_b200.plugin import ClipViTPreprocessor
+    p = ClipViTPreprocessor("rgb_lowres", "ViT-B/32")
+    assert p.input_uuids == ["rgb_lowres"] and p.uuid == "rgb_clip_vit" and tuple(p.observation_space.shape) == (512,)
+    with pytest.raises(AssertionError):
+        ClipViTPreprocessor("rgb", "ViT-L/14")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        p.process({"rgb": torch.zeros(1, 224, 224, 3)})
+
+
+@pytest.mark.gpu
+def test_vit_process_matches_oracle(built_lib):
+    from embclip_b200.plugin import ClipViTPreprocessor
+    from oracle.clip_model import build_vit_b32, freeze_model, init_synthetic_transformer
+    torch.manual_seed(0)
+    m = freeze_model(init_synthetic_transformer(build_vit_b32(), seed=1234))
+    p = ClipViTPreprocessor("rgb", "ViT-B/32", clip_state_dict=m.state_dict()).to(torch.device("cuda:0"))
+    frames = synthetic_frames(2, seed=4)
+    out = p.process({"rgb": frames})
+    with torch.no_grad():
+        ref = m.encode_image(frames.permute(0, 3, 1, 2).contiguous())
+    err = ((out.cpu() - ref).norm(dim=1) / ref.norm(dim=1)).max().item()
+    assert out.shape == (2, 512) and err <= 1e-3, err

@@ -10,8 +10,8 @@ timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/bench_$TAG.json 2
 tail -c 600 gpurun_out/bench_$TAG.json
 # launch list: 1 warm-up step skipped, then the launches of ~one step (cold-cache, serialised: compare shares)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-    --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 1 --warmup 3 --no-cpu --no-ppo > gpurun_out/ncu_launch_$TAG.log 2>&1
+    --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 1 --warmup 3 --no-cpu --no-ppo --no-vit > gpurun_out/ncu_launch_$TAG.log 2>&1
 # dominant kernel, full set, 3 launches from the middle of the network
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_gemm -s 60 -c 3 \
-    -o gpurun_out/prof_conv_gemm_$TAG -f python bench.py --steps 1 --warmup 3 --no-cpu --no-ppo > gpurun_out/ncu_full_$TAG.log 2>&1
+    -o gpurun_out/prof_conv_gemm_$TAG -f python bench.py --steps 1 --warmup 3 --no-cpu --no-ppo --no-vit > gpurun_out/ncu_full_$TAG.log 2>&1
 ls -la gpurun_out | tail -12
