@@ -71,7 +71,7 @@ def test_vit_surface():
     with pytest.raises(AssertionError):
         ClipViTPreprocessor("rgb", "ViT-L/14")
     with pytest.raises(RuntimeError, match="no CPU path"):
-        p.process({"rgb": torch.zeros(1, 224, 224, 3)})
+        p.process({"rgb_lowres": torch.zeros(1, 224, 224, 3)})
 
 
 @pytest.mark.gpu
