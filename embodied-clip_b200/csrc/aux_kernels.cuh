@@ -23,6 +23,7 @@ stem_conv1_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
   for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias[i];
   __syncthreads();
+  griddep_wait();                                  // (weights above are constants; the output buffer may still be read by the previous forward)
   const int Ro = R / 2;
   const long long total = (long long)B * Ro * Ro;
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(256)
 avgpool2_kernel(const __half* __restrict__ x, __half* __restrict__ y, int B, int H, int W, int C) {
   const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
   const long long total = (long long)B * Ho * Wo * C8;
+  griddep_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c8 = int(i % C8);
     long long r = i / C8;
@@ -117,6 +119,7 @@ attnpool_tokens_kernel(const float* __restrict__ x, const float* __restrict__ po
                        int P, int C) {
   const int b = blockIdx.y;
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  griddep_wait();
   if (c >= C) return;
   const float* xb = x + (size_t)b * P * C + c;
   __half* tb = tok + (size_t)b * (P + 1) * C + c;
@@ -160,6 +163,7 @@ attnpool_core_kernel(const __half* __restrict__ qt,   // [B, heads, C]
   const int h0 = blockIdx.y * HG;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int C8 = C / 8;
+  griddep_wait();
 
   const uint4* gq = reinterpret_cast<const uint4*>(qt + ((size_t)b * heads + h0) * C);
   for (int i = tid; i < HG * C8; i += 256) reinterpret_cast<uint4*>(sq)[i] = __ldg(gq + i);
@@ -264,6 +268,7 @@ __global__ void __launch_bounds__(256)
 avg_head_kernel(const float* __restrict__ x, float* __restrict__ y, int P, int C) {
   const int b = blockIdx.y;
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  griddep_wait();
   if (c >= C) return;
   const float* xb = x + (size_t)b * P * C + c;
   float4 s = make_float4(0, 0, 0, 0);
@@ -280,6 +285,7 @@ __global__ void __launch_bounds__(256)
 nhwc_to_nchw_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int P, int C) {
   extern __shared__ float tile[];   // [P][33]
   const int b = blockIdx.y, c0 = blockIdx.x * 32;
+  griddep_wait();
   const float* xb = x + (size_t)b * P * C + c0;
   for (int i = threadIdx.x; i < P * 32; i += blockDim.x) {
     const int p = i >> 5, c = i & 31;

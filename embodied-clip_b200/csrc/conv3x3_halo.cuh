@@ -42,6 +42,7 @@ struct Conv3Params {
   uint32_t plane_rows_alloc;
   int relu;
   int N;                       // Cout
+  int reverse;                 // 1: walk the tiles last-to-first (snake order across layers)
   int pool;                    // 1: write avgpool2(relu(conv)) [B, H/2, W/2, N] instead of the full-resolution map
   const float* bias;
   __half* out;
@@ -103,8 +104,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  griddep_launch_dependents();
+  griddep_wait();                                  // the previous kernel's outputs (our input planes) are complete below here
 
-  auto tile_coords = [&](int t, int& n_blk, int& img0, int& h0) {
+  auto tile_coords = [&](int t_, int& n_blk, int& img0, int& h0) {
+    const int t = p.reverse ? num_tiles - 1 - t_ : t_;
     n_blk = t % p.num_n_blks;
     const int m_tile = t / p.num_n_blks;
     if (p.strips_per_image) { img0 = m_tile / p.strips_per_image; h0 = (m_tile - img0 * p.strips_per_image) * p.R; }
@@ -117,7 +121,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int n_blk = t % p.num_n_blks;
+        const int n_blk = (p.reverse ? num_tiles - 1 - t : t) % p.num_n_blks;
         for (int c = 0; c < p.chunks; ++c) {
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(bar_bempty + 8 * stage, phase ^ 1u);

@@ -39,6 +39,7 @@ struct ConvGemmParams {
   // grouped mode (0 = off): N-group g = n0 / grp_n reads A at k + g*grp_a_koff, W at k + g*grp_b_koff,
   // and W rows n0 % grp_b_nmod (if grp_b_nmod != 0)
   int grp_n, grp_a_koff, grp_b_koff, grp_b_nmod;
+  int reverse;                  // 1: walk the tiles last-to-first (snake order: start where the previous layer's output is still in L2)
 };
 
 template <int BN, int BK, bool kRes = false>
@@ -122,6 +123,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  griddep_launch_dependents();
+  griddep_wait();                                  // the previous kernel's outputs (our A / residual) are complete below here
 
   if (warp == 0) {
     // ============================ TMA producer ============================
@@ -129,8 +132,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int n_blk = t % p.num_n_blks;
-        const int m_blk = t / p.num_n_blks;
+        const int tt = p.reverse ? num_tiles - 1 - t : t;
+        const int n_blk = tt % p.num_n_blks;
+        const int m_blk = tt / p.num_n_blks;
         const int tw = m_blk % p.tiles_w;
         const int th = (m_blk / p.tiles_w) % p.tiles_h;
         const int ng = m_blk / (p.tiles_w * p.tiles_h);
@@ -211,7 +215,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     int cbuf = 0;                                              // staging buffer of this tile (kRes: alternates)
     uint32_t res_phase = 0;
     // residual tile of tile `tt` -> staging buffer `buf` (TMA, one tile ahead of its use)
-    auto prefetch_residual = [&](int tt, int buf) {
+    auto prefetch_residual = [&](int t_, int buf) {
+      const int tt = p.reverse ? num_tiles - 1 - t_ : t_;
       const int nb = tt % p.num_n_blks, mb = tt / p.num_n_blks;
       const uint32_t bar = bar_res + 8 * buf;
       mbar_arrive_expect_tx(bar, Cfg::kCBytes);
@@ -221,8 +226,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     };
     if (kRes && store_leader && int(blockIdx.x) < num_tiles) prefetch_residual(blockIdx.x, 0);
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int n_blk = t % p.num_n_blks;
-      const int m_blk = t / p.num_n_blks;
+      const int tt = p.reverse ? num_tiles - 1 - t : t;
+      const int n_blk = tt % p.num_n_blks;
+      const int m_blk = tt / p.num_n_blks;
       const int tw = m_blk % p.tiles_w;
       const int th = (m_blk / p.tiles_w) % p.tiles_h;
       const int ng = m_blk / (p.tiles_w * p.tiles_h);

@@ -15,6 +15,7 @@
 #include "aux_kernels.cuh"
 #include "conv_gemm.cuh"
 #include "conv3x3_halo.cuh"
+#include "gemm2sm.cuh"
 
 using namespace embclip;
 
@@ -92,6 +93,10 @@ int embclip::make_map_2d(CUtensorMap* m, const void* base, int rows, int cols, i
 // conv_gemm launcher
 // =============================================================================================
 static int g_num_sms = 0;
+bool embclip::pdl_enabled() {
+  static const bool on = getenv("EMBCLIP_NO_PDL") == nullptr;
+  return on;
+}
 int embclip::num_sms() {
   if (!g_num_sms) {
     int dev = 0;
@@ -177,11 +182,50 @@ static int launch_cfg(const GemmOp& op, cudaStream_t st) {
   p.res_f32_ptr = op.out_f32 ? op.res_f32 : nullptr;
   p.ldo = op.cout;
   p.grp_n = op.grp_n; p.grp_a_koff = op.grp_a_koff; p.grp_b_koff = op.grp_b_koff; p.grp_b_nmod = op.grp_b_nmod;
+  p.reverse = op.reverse;
   const long long tiles = (long long)p.num_m_blks * p.num_n_blks;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   if (grid <= 0) return 0;
-  conv_gemm_kernel<BN, BK, kRes><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmA0, tmA1, tmB, tmC, tmR, p);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(launch_pdl(conv_gemm_kernel<BN, BK, kRes>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, tmA0, tmA1, tmB, tmC, tmR, p));
+  return 0;
+}
+
+// CTA-pair (cta_group::2) variant for plain 2-D GEMMs: 256 x 256 tiles
+template <int BN>
+static int launch_gemm2sm(const GemmOp& op, cudaStream_t st) {
+  using Cfg = Gemm2Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(gemm2sm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const long long M = (long long)op.n * op.h * op.w;
+  if (M > 0x7fffffffLL) return fail(EMBCLIP_EINVAL, "M too large");
+  CUtensorMap tmA0, tmA1, tmB, tmC;
+  int rc;
+  if ((rc = make_map_nhwc(&tmA0, op.a0, 1, 1, (int)M, op.c0, op.lda0, 64, 128, 1, 1))) return rc;
+  if (op.a1) { if ((rc = make_map_nhwc(&tmA1, op.a1, 1, 1, (int)M, op.c1, op.c1, 64, 128, 1, 1))) return rc; }
+  else tmA1 = tmA0;
+  if ((rc = make_map_2d(&tmB, op.wgt, op.w_rows, op.ldw, op.ldw, 64, BN / 2))) return rc;
+  if (!op.out_f32) { if ((rc = make_map_nhwc(&tmC, op.out, 1, 1, (int)M, op.cout, op.cout, 64, 128, 1, 1))) return rc; }
+  else tmC = tmA0;
+  Gemm2Params p;
+  memset(&p, 0, sizeof p);
+  p.num_m_pairs = int((M + 255) / 256);
+  p.num_n_blks = op.cout / BN;
+  p.kb_src0 = op.c0 / 64;
+  p.kb_total = p.kb_src0 + op.c1 / 64;
+  p.relu = op.relu; p.out_f32 = op.out_f32; p.M = (int)M; p.N = op.cout;
+  p.bias = op.bias;
+  p.residual = reinterpret_cast<const __half*>(op.residual); p.res_mode = op.res_mode;
+  p.out_f32_ptr = reinterpret_cast<float*>(op.out);
+  p.res_f32_ptr = op.out_f32 ? op.res_f32 : nullptr;
+  p.reverse = op.reverse;
+  const long long tiles = (long long)p.num_m_pairs * p.num_n_blks;
+  const int max_pairs = num_sms() / 2;
+  const int pairs = (int)(tiles < max_pairs ? tiles : max_pairs);
+  if (pairs <= 0) return 0;
+  CUDA_TRY(launch_pdl(gemm2sm_kernel<BN>, dim3(2 * pairs), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, tmA0, tmA1, tmB, tmC, p));
   return 0;
 }
 
@@ -196,6 +240,15 @@ int embclip::launch_gemm(const GemmOp& op, cudaStream_t st, int force_bn) {
   if (op.c0 % 32 || op.c1 % 32 || op.cout % 32) return fail(EMBCLIP_EINVAL, "channels must be multiples of 32 (c0 %d c1 %d cout %d)", op.c0, op.c1, op.cout);
   if (op.taps != 1 && op.taps != 9) return fail(EMBCLIP_EINVAL, "taps must be 1 or 9");
   if (op.taps == 9 && (op.a1 || op.residual || op.out_f32 || op.grp_n)) return fail(EMBCLIP_EINVAL, "3x3 mode supports bias+relu only");
+  {
+    // large plain GEMMs run on CTA pairs: half the L2 -> smem traffic per FLOP (gemm2sm.cuh)
+    static const int use_2sm = getenv("EMBCLIP_2SM") ? atoi(getenv("EMBCLIP_2SM")) : 1;
+    static const int min_k = getenv("EMBCLIP_2SM_MINK") ? atoi(getenv("EMBCLIP_2SM_MINK")) : 256;
+    const long long M = (long long)op.n * op.h * op.w;
+    if (use_2sm && !force_bn && op.taps == 1 && !op.grp_n && op.c0 % 64 == 0 && op.c1 % 64 == 0 && op.cout % 256 == 0 &&
+        (op.a_cols == 0 || op.a_cols == op.c0) && op.lda0 == op.c0 && op.c0 + op.c1 >= min_k && M >= 2048)
+      return launch_gemm2sm<256>(op, st);
+  }
   const int bk = (op.c0 % 64 == 0 && op.c1 % 64 == 0) ? 64 : 32;
   int bn = force_bn ? force_bn : pick_bn(op.cout);
   if (op.grp_n && op.grp_n % bn) bn = op.grp_n % 64 == 0 ? 64 : 32;
@@ -259,6 +312,7 @@ static bool c3_geometry(int B, int H, int W, int MS, bool pool, C3Geom* g) {
 struct Conv3Op {
   const void* in; const void* wgt; const float* bias; void* out;
   int B, H, W, C, N, relu, pool;
+  int reverse = 0;
 };
 
 template <int BN, int MS, int KC, bool kPool>
@@ -297,13 +351,12 @@ static int launch_c3_cfg(const Conv3Op& op, const C3Geom& g, cudaStream_t st) {
   p.n_a = n_a; p.n_b = n_b;
   p.plane_bytes = plane_bytes; p.plane_tx_bytes = g.rows_tma * SWZ;
   p.plane_rows_tma = g.rows_tma; p.plane_rows_alloc = plane_bytes / SWZ;
-  p.relu = op.relu; p.N = op.N; p.pool = op.pool;
+  p.relu = op.relu; p.N = op.N; p.pool = op.pool; p.reverse = op.reverse;
   p.bias = op.bias; p.out = reinterpret_cast<__half*>(op.out);
   const long long tiles = (long long)p.num_m_tiles * p.num_n_blks;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   if (grid <= 0) return 0;
-  conv3x3_halo_kernel<BN, MS, KC, kPool><<<grid, kC3Threads, smem, st>>>(tmA, tmB, p);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(launch_pdl(conv3x3_halo_kernel<BN, MS, KC, kPool>, dim3(grid), dim3(kC3Threads), smem, st, tmA, tmB, p));
   return 0;
 }
 
@@ -385,8 +438,7 @@ static int launch_avgpool2(const void* in, void* out, int B, int H, int W, int C
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   if (blocks <= 0) return 0;
-  avgpool2_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), B, H, W, C);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(launch_pdl(avgpool2_kernel, dim3((int)blocks), dim3(256), 0, st, reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), B, H, W, C));
   return 0;
 }
 extern "C" int embclip_avgpool2_f16(const void* in, void* out, int B, int H, int W, int C, void* stream) {
@@ -400,7 +452,7 @@ static int launch_stem_conv1(const float* x, const float* w, const float* b, voi
   const int blocks = (int)((total + 127) / 128);
   if (blocks <= 0) return 0;
   if (Cout == 32)
-    stem_conv1_kernel<32><<<blocks, 128, 0, st>>>(x, w, b, reinterpret_cast<__half*>(y), B, R);
+    CUDA_TRY(launch_pdl(stem_conv1_kernel<32>, dim3(blocks), dim3(128), 0, st, x, w, b, reinterpret_cast<__half*>(y), B, R));
   else
     return fail(EMBCLIP_EINVAL, "stem conv1: only Cout == 32 (width 64) is built");
   CUDA_TRY(cudaGetLastError());
@@ -440,6 +492,7 @@ struct Op {
   int lda0 = 0, a_cols = 0, ldw = 0, w_rows = 0;
   int grp_n = 0, grp_a_koff = 0, grp_b_koff = 0, grp_b_nmod = 0;
   int force_bn = 0;
+  int reverse = 0;               // tile walk direction (alternates layer to layer: snake order through L2)
 };
 
 }  // namespace
@@ -615,6 +668,12 @@ extern "C" int embclip_rn50_create(const embclip_rn50_cfg* cfg, embclip_rn50_t* 
     c.out = -4;
     m->ops.push_back(c);
   }
+  // snake order: consecutive tensor-core layers walk their tiles in opposite directions, so each starts on the part
+  // of its input that the previous layer wrote last (still resident in the 126 MB L2)
+  static const bool snake = getenv("EMBCLIP_NO_SNAKE") == nullptr;
+  int dir = 0;
+  for (Op& op : m->ops)
+    if (op.kind == K_GEMM && op.rows_mode == 0) { op.reverse = snake ? dir : 0; dir ^= 1; }
   *out = m;
   return 0;
 }
@@ -680,6 +739,7 @@ static int run_op(embclip_rn50* m, const Op& op, const std::vector<uint64_t>& of
       const Act& a = m->acts[op.in0];
       if (op.taps == 9) {
         Conv3Op c{act_ptr(op.in0), param_ptr(op.wp), (const float*)param_ptr(op.bp), act_ptr(op.out), B, a.h, a.w, op.c0, op.cout, op.relu, op.pool};
+        c.reverse = op.reverse;
         return launch_conv3x3_halo(c, st);
       }
       GemmOp g;
@@ -695,13 +755,13 @@ static int run_op(embclip_rn50* m, const Op& op, const std::vector<uint64_t>& of
       g.out = op.out == -4 ? (void*)o_attn : act_ptr(op.out);
       g.cout = op.cout; g.relu = op.relu; g.out_f32 = op.out_f32;
       g.grp_n = op.grp_n; g.grp_a_koff = op.grp_a_koff; g.grp_b_koff = op.grp_b_koff; g.grp_b_nmod = op.grp_b_nmod;
+      g.reverse = op.reverse;
       return launch_gemm(g, st, op.force_bn);
     }
     case K_TOKENS: {
       dim3 grid((m->embed / 4 + 255) / 256, B);
-      attnpool_tokens_kernel<<<grid, 256, 0, st>>>((const float*)act_ptr(op.in0), (const float*)param_ptr(op.wp),
-                                                   (__half*)act_ptr(op.out), P, m->embed);
-      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(launch_pdl(attnpool_tokens_kernel, grid, dim3(256), 0, st, (const float*)act_ptr(op.in0), (const float*)param_ptr(op.wp),
+                          (__half*)act_ptr(op.out), P, m->embed));
       return 0;
     }
     case K_ATTN_CORE: {
@@ -714,21 +774,18 @@ static int run_op(embclip_rn50* m, const Op& op, const std::vector<uint64_t>& of
         attr = true;
       }
       dim3 grid(B, m->cfg.heads / HG);
-      attnpool_core_kernel<HG><<<grid, 256, smem, st>>>((const __half*)act_ptr(op.in0), (const __half*)act_ptr(op.in1),
-                                                        (__half*)act_ptr(op.out), m->cfg.heads, m->tokens, m->embed);
-      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(launch_pdl(attnpool_core_kernel<HG>, grid, dim3(256), smem, st, (const __half*)act_ptr(op.in0), (const __half*)act_ptr(op.in1),
+                          (__half*)act_ptr(op.out), m->cfg.heads, m->tokens, m->embed));
       return 0;
     }
     case K_AVGHEAD: {
       dim3 grid((m->embed / 4 + 255) / 256, B);
-      avg_head_kernel<<<grid, 256, 0, st>>>((const float*)act_ptr(op.in0), o_avg, P, m->embed);
-      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(launch_pdl(avg_head_kernel, grid, dim3(256), 0, st, (const float*)act_ptr(op.in0), o_avg, P, m->embed));
       return 0;
     }
     case K_NCHW: {
       dim3 grid(m->embed / 32, B);
-      nhwc_to_nchw_f32_kernel<<<grid, 256, (size_t)P * 33 * 4, st>>>((const float*)act_ptr(op.in0), o_nchw, P, m->embed);
-      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(launch_pdl(nhwc_to_nchw_f32_kernel, grid, dim3(256), (size_t)P * 33 * 4, st, (const float*)act_ptr(op.in0), o_nchw, P, m->embed));
       return 0;
     }
   }

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 #include "../../include/embclip_b200.h"
 
 namespace embclip {
@@ -17,6 +19,21 @@ int fail(int code, const char* fmt, ...);
   } while (0)
 
 int num_sms();
+bool pdl_enabled();   // false when $EMBCLIP_NO_PDL is set
+
+// Launch with programmatic stream serialization: the kernel MUST execute griddepcontrol.wait before touching global
+// memory written by earlier kernels in the stream (see ptx.cuh).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 // fp16 tensor maps; dims fastest-first, `pitch[i]` = byte stride of dim i+1; swizzle follows the box's inner bytes
 int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* pitch, const uint32_t* box);
 int make_map_2d(CUtensorMap* m, const void* base, int rows, int cols, int ld, int box_cols, int box_rows);
@@ -40,6 +57,7 @@ struct GemmOp {
   int relu = 0, out_f32 = 0;        // relu: activation code (0 none, 1 ReLU, 2 QuickGELU)
   const float* res_f32 = nullptr;   // out_f32 only: fp32 residual [M, cout] added in the epilogue (may alias out)
   int grp_n = 0, grp_a_koff = 0, grp_b_koff = 0, grp_b_nmod = 0;
+  int reverse = 0;                  // walk the output tiles last-to-first
   int a_cols = 0;                   // logical width of an A0 row for the tensor map (>= c0; grouped mode: full row)
 };
 int launch_gemm(const GemmOp& op, cudaStream_t st, int force_bn = 0);

@@ -85,6 +85,13 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while their predecessor in the
+// stream is still draining: everything before griddep_wait() (barrier init, TMEM alloc, descriptor prefetch) overlaps
+// the predecessor's tail; no global memory written by it may be touched before the wait returns.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -101,6 +101,26 @@ def test_gemm_k_concat(lib):
     _gemm_case(lib, 98, 2048, 512, K1=1024, relu=True, out_f32=True)
 
 
+@pytest.mark.parametrize("M,N,K", [
+    (2048, 256, 256),          # smallest shape routed to the CTA-pair kernel: 8 pair tiles, 4 k-blocks
+    (4096 + 37, 512, 1024),    # partial last pair tile, 2 N tiles, pipeline wraps
+    (256 * 80, 256, 512),      # more pair tiles than CTA pairs: persistent loop + accumulator double-buffering
+    (12544, 2048, 512),        # layer4 conv3 shape
+    (25600, 768, 3072),        # ViT-B/32 mlp.c_proj at B = 512
+])
+def test_gemm_cta_pair(lib, M, N, K):
+    """shapes launch_gemm routes to gemm2sm_kernel (cta_group::2): N % 256 == 0, K >= 256, M >= 2048"""
+    _gemm_case(lib, M, N, K, relu=True, seed=M % 97)
+
+
+def test_gemm_cta_pair_epilogues(lib):
+    _gemm_case(lib, 3000, 256, 256, res=True, relu=True)                 # fp16 residual read in the epilogue
+    _gemm_case(lib, 3000, 512, 256, bias=False)
+    _gemm_case(lib, 3000, 256, 512, out_f32=True, relu=True)             # fp32 rows stored directly
+    _gemm_case(lib, 2500, 1024, 256, K1=512, relu=True)                  # K-concat second source (conv3 + downsample)
+    _gemm_case(lib, 2500, 256, 320)                                      # K not a multiple of 64 -> stays on the 1-CTA kernel
+
+
 def test_gemm_grouped(lib):
     """per-head contractions of AttentionPool2d"""
     torch.manual_seed(1)

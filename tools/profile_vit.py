@@ -1,0 +1,16 @@
+"""One ViT-B/32 forward at B=512 for ncu launch lists (and a CUDA-event total)."""
+import os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from embclip_b200.vit import ClipViTEncoder
+from oracle.clip_model import build_vit_b32, init_synthetic_transformer
+torch.manual_seed(0)
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+enc = ClipViTEncoder(init_synthetic_transformer(build_vit_b32(), seed=1234).state_dict(), "cuda:0")
+x = torch.randn(B, 224, 224, 3, device="cuda")
+for _ in range(2):
+    enc(x)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); enc(x); e1.record(); torch.cuda.synchronize()
+print(f"B={B} forward {e0.elapsed_time(e1):.3f} ms")
