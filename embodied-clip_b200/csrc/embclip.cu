@@ -191,21 +191,23 @@ static int launch_cfg(const GemmOp& op, cudaStream_t st) {
 }
 
 // CTA-pair (cta_group::2) variant for plain 2-D GEMMs: 256 x 256 tiles
-template <int BN>
+template <int BN, bool kRes>
 static int launch_gemm2sm(const GemmOp& op, cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(gemm2sm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(gemm2sm_kernel<BN, kRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
     attr_set = true;
   }
   const long long M = (long long)op.n * op.h * op.w;
   if (M > 0x7fffffffLL) return fail(EMBCLIP_EINVAL, "M too large");
-  CUtensorMap tmA0, tmA1, tmB, tmC;
+  CUtensorMap tmA0, tmA1, tmB, tmC, tmR;
   int rc;
   if ((rc = make_map_nhwc(&tmA0, op.a0, 1, 1, (int)M, op.c0, op.lda0, 64, 128, 1, 1))) return rc;
   if (op.a1) { if ((rc = make_map_nhwc(&tmA1, op.a1, 1, 1, (int)M, op.c1, op.c1, 64, 128, 1, 1))) return rc; }
   else tmA1 = tmA0;
+  if (kRes) { if ((rc = make_map_nhwc(&tmR, op.residual, 1, 1, (int)M, op.cout, op.cout, 64, 128, 1, 1))) return rc; }
+  else tmR = tmA0;
   if ((rc = make_map_2d(&tmB, op.wgt, op.w_rows, op.ldw, op.ldw, 64, BN / 2))) return rc;
   if (!op.out_f32) { if ((rc = make_map_nhwc(&tmC, op.out, 1, 1, (int)M, op.cout, op.cout, 64, 128, 1, 1))) return rc; }
   else tmC = tmA0;
@@ -217,7 +219,7 @@ static int launch_gemm2sm(const GemmOp& op, cudaStream_t st) {
   p.kb_total = p.kb_src0 + op.c1 / 64;
   p.relu = op.relu; p.out_f32 = op.out_f32; p.M = (int)M; p.N = op.cout;
   p.bias = op.bias;
-  p.residual = reinterpret_cast<const __half*>(op.residual); p.res_mode = op.res_mode;
+  p.res_mode = op.res_mode;
   p.out_f32_ptr = reinterpret_cast<float*>(op.out);
   p.res_f32_ptr = op.out_f32 ? op.res_f32 : nullptr;
   p.reverse = op.reverse;
@@ -225,7 +227,7 @@ static int launch_gemm2sm(const GemmOp& op, cudaStream_t st) {
   const int max_pairs = num_sms() / 2;
   const int pairs = (int)(tiles < max_pairs ? tiles : max_pairs);
   if (pairs <= 0) return 0;
-  CUDA_TRY(launch_pdl(gemm2sm_kernel<BN>, dim3(2 * pairs), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, tmA0, tmA1, tmB, tmC, p));
+  CUDA_TRY(launch_pdl(gemm2sm_kernel<BN, kRes>, dim3(2 * pairs), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, tmA0, tmA1, tmB, tmC, tmR, p));
   return 0;
 }
 
@@ -246,8 +248,9 @@ int embclip::launch_gemm(const GemmOp& op, cudaStream_t st, int force_bn) {
     static const int min_k = getenv("EMBCLIP_2SM_MINK") ? atoi(getenv("EMBCLIP_2SM_MINK")) : 256;
     const long long M = (long long)op.n * op.h * op.w;
     if (use_2sm && !force_bn && op.taps == 1 && !op.grp_n && op.c0 % 64 == 0 && op.c1 % 64 == 0 && op.cout % 256 == 0 &&
-        (op.a_cols == 0 || op.a_cols == op.c0) && op.lda0 == op.c0 && op.c0 + op.c1 >= min_k && M >= 2048)
-      return launch_gemm2sm<256>(op, st);
+        (op.a_cols == 0 || op.a_cols == op.c0) && op.lda0 == op.c0 && op.c0 + op.c1 >= (op.residual ? 2 * min_k : min_k) &&
+        M >= 2048 && !(op.residual && op.out_f32))      // (short-K residual GEMMs are epilogue-bound: measured slower on pairs)
+      return op.residual ? launch_gemm2sm<256, true>(op, st) : launch_gemm2sm<256, false>(op, st);
   }
   const int bk = (op.c0 % 64 == 0 && op.c1 % 64 == 0) ? 64 : 32;
   int bn = force_bn ? force_bn : pick_bn(op.cout);

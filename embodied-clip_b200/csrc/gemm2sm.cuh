@@ -16,6 +16,8 @@
 //   * warps 2..9 (both CTAs): epilogue of the CTA's own 128 accumulator rows; the peer's warps arrive remotely
 //     (mapa + mbarrier.arrive.shared::cluster) on the leader's accumulator-empty barrier.
 //   Accumulators are double buffered (2 x 256 TMEM columns), so tile i's epilogue overlaps tile i+1's MMAs.
+//   The epilogue walks a tile in 128-column units through two 32 KB staging buffers: unit u's TMA store drains while
+//   unit u+1 is computed, and (kRes) unit u+1's residual tile is TMA-prefetched into the other buffer.
 #pragma once
 #include "ptx.cuh"
 
@@ -28,8 +30,7 @@ struct Gemm2Params {
   int out_f32;
   int M, N;
   const float* bias;
-  const __half* residual;       // fp16 [M, N] added before the activation (or ReLU-mask source), or null
-  int res_mode;                 // 0 add, 1 mask (out = residual > 0 ? out : 0)
+  int res_mode;                 // kRes: 0 add the fp16 residual tile, 1 mask (out = residual > 0 ? out : 0)
   float* out_f32_ptr;           // [M, N]
   const float* res_f32_ptr;     // out_f32: fp32 residual [M, N] (may alias out_f32_ptr)
   int reverse;
@@ -44,13 +45,15 @@ struct Gemm2Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kCS = 64;
   static constexpr int kCChunkBytes = 128 * kCS * 2;
-  static constexpr int kCBytes = 128 * BN * 2;
-  static constexpr int kCBufs = BN <= 128 ? 2 : 1;
+  static constexpr int kUnitN = 128;                         // the epilogue walks the tile in 128-column units
+  static constexpr int kUnits = BN / kUnitN;
+  static constexpr int kCBytes = 128 * kUnitN * 2;           // one staging buffer = one unit (32 KB)
+  static constexpr int kCBufs = 2;
   static constexpr int kEpiWarps = 8;
   static constexpr int kEpiThreads = kEpiWarps * 32;
   static constexpr int kThreads = 64 + kEpiThreads;
   static constexpr int kBarBytes = 256;
-  static constexpr int kBiasBytes = BN * 4;
+  static constexpr int kBiasBytes = 128 * 4;
   static constexpr int kBudget = 227 * 1024 - 1024 - kCBufs * kCBytes - kBiasBytes - kBarBytes;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -111,10 +114,11 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(kCols) : "memory");
 }
 
-template <int BN>
+template <int BN, bool kRes>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 8 * 32, 1)
 gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const Gemm2Params p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+               const __grid_constant__ CUtensorMap tmR, const Gemm2Params p) {
   using Cfg = Gemm2Cfg<BN>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -128,7 +132,8 @@ gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t bar_empty = sBar + 8 * S;        // S x 8 B   (per CTA)
   const uint32_t bar_tfull = sBar + 16 * S;       // 2 x 8 B   (per CTA)
   const uint32_t bar_tempty = bar_tfull + 16;     // 2 x 8 B   (used in the leader)
-  const uint32_t tmem_slot = bar_tempty + 16;
+  const uint32_t bar_res = bar_tempty + 16;       // 2 x 8 B   (per CTA: residual unit landed in staging buffer i)
+  const uint32_t tmem_slot = bar_res + 16;
   uint8_t* const gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   float* const sBias_ptr = reinterpret_cast<float*>(gen_base + (sBias - smem_base));
 
@@ -143,6 +148,7 @@ gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
     if (p.kb_src0 < p.kb_total) tma_prefetch_desc(&tmA1);
+    if (kRes) tma_prefetch_desc(&tmR);
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
@@ -150,6 +156,7 @@ gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, 2 * Cfg::kEpiWarps);   // epilogue warps of both CTAs
+      mbar_init(bar_res + 8 * a, 1);
     }
     fence_barrier_init();
   }
@@ -221,114 +228,140 @@ gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // ============================ epilogue (warps 2..9, both CTAs: own 128 rows) ============================
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    constexpr int kColsPerWarp = BN / 2;
-    const int col_base = ((warp - 2) >> 2) * kColsPerWarp;
-    constexpr int CH = 32, NP = 4;
+    const int col_base = ((warp - 2) >> 2) * 64;               // this warp's half of a 128-column unit
+    constexpr int CH = 32, NP = 4, U = Cfg::kUnits;
     const int epi_tid = threadIdx.x - 64;
     const bool store_leader = (threadIdx.x == 64);
     int acc = 0, cbuf = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, res_phase = 0;
+    // residual unit (tile t_, unit hh) -> staging buffer `buf` (TMA, one unit ahead of its use)
+    auto prefetch_residual = [&](int t_, int hh, int buf) {
+      const int tt = p.reverse ? num_tiles - 1 - t_ : t_;
+      const int nb = tt % p.num_n_blks, mp = tt / p.num_n_blks;
+      const uint32_t bar = bar_res + 8 * buf;
+      mbar_arrive_expect_tx(bar, Cfg::kCBytes);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc)
+        tma_load_4d(&tmR, bar, sC + buf * Cfg::kCBytes + cc * Cfg::kCChunkBytes, nb * BN + hh * 128 + cc * 64, mp * 256 + int(rank) * 128, 0, 0);
+    };
+    if (kRes && store_leader && pair < num_tiles) prefetch_residual(pair, 0, 0);
     for (int t = pair; t < num_tiles; t += num_pairs) {
       const int tt = p.reverse ? num_tiles - 1 - t : t;
       const int n_blk = tt % p.num_n_blks;
       const int m_pair = tt / p.num_n_blks;
       const int m0 = m_pair * 256 + int(rank) * 128;
-      const int n0 = n_blk * BN;
       const int grow = m0 + row;
       const bool row_ok = grow < p.M;
-      const uint32_t sCt = sC + uint32_t(cbuf) * Cfg::kCBytes;
-      if (store_leader) {
-        if (Cfg::kCBufs == 2) tma_store_wait_read1(); else tma_store_wait_read0();
-      }
-      for (int i = epi_tid; i < BN; i += Cfg::kEpiThreads) sBias_ptr[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
-      named_bar_sync(1, Cfg::kEpiThreads);
-
-      mbar_wait(bar_tfull + 8 * acc, acc_phase);
-      tcgen05_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < kColsPerWarp / CH; ++c) {
-        const int col = col_base + c * CH;
-        uint32_t v[CH];
-        tmem_ld_32x32b<CH>(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + col), v);
-        uint4 rres[NP];
-        if (p.residual && row_ok) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + size_t(grow) * p.N + n0 + col);
-#pragma unroll
-          for (int i = 0; i < NP; ++i) rres[i] = __ldg(rp + i);
+      for (int hh = 0; hh < U; ++hh) {
+        const int n0 = n_blk * BN + hh * 128;
+        const uint32_t sCt = sC + uint32_t(cbuf) * Cfg::kCBytes;
+        if (store_leader) {
+          if (kRes) {
+            // buffer cbuf^1 (the previous unit's output) must be drained before the next unit's residual lands in it
+            tma_store_wait_read0();
+            if (hh + 1 < U) prefetch_residual(t, hh + 1, cbuf ^ 1);
+            else if (t + num_pairs < num_tiles) prefetch_residual(t + num_pairs, 0, cbuf ^ 1);
+          } else {
+            tma_store_wait_read1();                            // only the store from two units ago used this buffer
+          }
         }
-        tmem_ld_wait();
-        float f[CH];
+        for (int i = epi_tid; i < 128; i += Cfg::kEpiThreads) sBias_ptr[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+        named_bar_sync(1, Cfg::kEpiThreads);
+        if (hh == 0) {
+          mbar_wait(bar_tfull + 8 * acc, acc_phase);
+          tcgen05_fence_after();
+        }
+        if (kRes) mbar_wait(bar_res + 8 * cbuf, res_phase);
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          const int col = col_base + c * CH;                   // column inside the unit
+          uint32_t v[CH];
+          tmem_ld_32x32b<CH>(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + hh * 128 + col), v);
+          const uint32_t chunk_base = sCt + uint32_t(col / 64) * Cfg::kCChunkBytes;
+          const int piece0 = (col % 64) / 8;
+          uint4 rres[NP];
+          if (kRes) {
 #pragma unroll
-        for (int i = 0; i < CH; ++i) f[i] = __uint_as_float(v[i]) + sBias_ptr[col + i];
-        if (p.residual && row_ok) {
+            for (int i = 0; i < NP; ++i) {
+              const uint32_t a = chunk_base + swizzle_off<128>(uint32_t(row), uint32_t(piece0 + i));
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rres[i].x), "=r"(rres[i].y), "=r"(rres[i].z), "=r"(rres[i].w) : "r"(a));
+            }
+          }
+          tmem_ld_wait();
+          float f[CH];
 #pragma unroll
-          for (int i = 0; i < NP; ++i) {
-            const __half2* h = reinterpret_cast<const __half2*>(&rres[i]);
+          for (int i = 0; i < CH; ++i) f[i] = __uint_as_float(v[i]) + sBias_ptr[col + i];
+          if (kRes) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 r2 = __half22float2(h[j]);
-              if (p.res_mode == 0) {
-                f[i * 8 + j * 2] += r2.x;
-                f[i * 8 + j * 2 + 1] += r2.y;
-              } else {
-                f[i * 8 + j * 2] = r2.x > 0.f ? f[i * 8 + j * 2] : 0.f;
-                f[i * 8 + j * 2 + 1] = r2.y > 0.f ? f[i * 8 + j * 2 + 1] : 0.f;
+            for (int i = 0; i < NP; ++i) {
+              const __half2* h = reinterpret_cast<const __half2*>(&rres[i]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 r2 = __half22float2(h[j]);
+                if (p.res_mode == 0) {
+                  f[i * 8 + j * 2] += r2.x;
+                  f[i * 8 + j * 2 + 1] += r2.y;
+                } else {
+                  f[i * 8 + j * 2] = r2.x > 0.f ? f[i * 8 + j * 2] : 0.f;
+                  f[i * 8 + j * 2 + 1] = r2.y > 0.f ? f[i * 8 + j * 2 + 1] : 0.f;
+                }
               }
             }
           }
-        }
-        if (p.relu == 1) {
+          if (p.relu == 1) {
 #pragma unroll
-          for (int i = 0; i < CH; ++i) f[i] = fmaxf(f[i], 0.f);
-        } else if (p.relu == 2) {
+            for (int i = 0; i < CH; ++i) f[i] = fmaxf(f[i], 0.f);
+          } else if (p.relu == 2) {
 #pragma unroll
-          for (int i = 0; i < CH; ++i) f[i] = f[i] / (1.f + __expf(-1.702f * f[i]));
-        }
-        if (p.out_f32) {
-          if (row_ok) {
-            float4* op = reinterpret_cast<float4*>(p.out_f32_ptr + size_t(grow) * p.N + n0 + col);
-            if (p.res_f32_ptr) {
-              const float4* rp = reinterpret_cast<const float4*>(p.res_f32_ptr + size_t(grow) * p.N + n0 + col);
+            for (int i = 0; i < CH; ++i) f[i] = f[i] / (1.f + __expf(-1.702f * f[i]));
+          }
+          if (p.out_f32) {
+            if (row_ok) {
+              float4* op = reinterpret_cast<float4*>(p.out_f32_ptr + size_t(grow) * p.N + n0 + col);
+              if (p.res_f32_ptr) {
+                const float4* rp = reinterpret_cast<const float4*>(p.res_f32_ptr + size_t(grow) * p.N + n0 + col);
 #pragma unroll
-              for (int i = 0; i < CH / 4; ++i) {
-                const float4 r = rp[i];
-                f[4 * i] += r.x; f[4 * i + 1] += r.y; f[4 * i + 2] += r.z; f[4 * i + 3] += r.w;
+                for (int i = 0; i < CH / 4; ++i) {
+                  const float4 r = rp[i];
+                  f[4 * i] += r.x; f[4 * i + 1] += r.y; f[4 * i + 2] += r.z; f[4 * i + 3] += r.w;
+                }
               }
+#pragma unroll
+              for (int i = 0; i < CH / 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
             }
+          } else {
 #pragma unroll
-            for (int i = 0; i < CH / 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-          }
-        } else {
-          const uint32_t chunk_base = sCt + uint32_t(col / Cfg::kCS) * Cfg::kCChunkBytes;
-          const int piece0 = (col % Cfg::kCS) / 8;
-#pragma unroll
-          for (int i = 0; i < NP; ++i) {
-            const uint32_t a = chunk_base + swizzle_off<128>(uint32_t(row), uint32_t(piece0 + i));
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
-                         "r"(pack_half2(f[8 * i], f[8 * i + 1])), "r"(pack_half2(f[8 * i + 2], f[8 * i + 3])),
-                         "r"(pack_half2(f[8 * i + 4], f[8 * i + 5])), "r"(pack_half2(f[8 * i + 6], f[8 * i + 7]))
-                         : "memory");
+            for (int i = 0; i < NP; ++i) {
+              const uint32_t a = chunk_base + swizzle_off<128>(uint32_t(row), uint32_t(piece0 + i));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
+                           "r"(pack_half2(f[8 * i], f[8 * i + 1])), "r"(pack_half2(f[8 * i + 2], f[8 * i + 3])),
+                           "r"(pack_half2(f[8 * i + 4], f[8 * i + 5])), "r"(pack_half2(f[8 * i + 6], f[8 * i + 7]))
+                           : "memory");
+            }
           }
         }
-      }
-      // accumulator drained -> the leader's MMA warp may overwrite it
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (rank == 0) mbar_arrive(bar_tempty + 8 * acc);
-        else mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-
-      if (!p.out_f32) fence_proxy_async_smem();
-      named_bar_sync(1, Cfg::kEpiThreads);
-      if (!p.out_f32 && store_leader) {
+        if (hh == U - 1) {
+          // accumulator drained -> the leader's MMA warp may overwrite it
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (rank == 0) mbar_arrive(bar_tempty + 8 * acc);
+            else mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+        if (!p.out_f32) fence_proxy_async_smem();
+        named_bar_sync(1, Cfg::kEpiThreads);
+        if (!p.out_f32 && store_leader) {
 #pragma unroll
-        for (int cc = 0; cc < BN / Cfg::kCS; ++cc)
-          tma_store_4d(&tmC, sCt + cc * Cfg::kCChunkBytes, n0 + cc * Cfg::kCS, m0, 0, 0);
-        tma_store_commit();
+          for (int cc = 0; cc < 2; ++cc)
+            tma_store_4d(&tmC, sCt + cc * Cfg::kCChunkBytes, n0 + cc * 64, m0, 0, 0);
+          tma_store_commit();
+        }
+        cbuf ^= 1;
+        if (cbuf == 0) res_phase ^= 1u;
       }
-      if (Cfg::kCBufs == 2) cbuf ^= 1;
     }
     if (store_leader) tma_store_wait_all0();
   }
