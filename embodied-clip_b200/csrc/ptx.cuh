@@ -173,6 +173,17 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
   return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (sbo << 32) |
          (uint64_t(1) << 46) | (layout << 61);
 }
+// MN-major operand tile: rows of kRowBytes (= box width * 2) along MN, 8-row K groups kRowBytes*8 apart (SBO),
+// `lbo_bytes` between successive boxes along MN.
+template <int kRowBytes>
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  static_assert(kRowBytes == 128 || kRowBytes == 64, "swizzle");
+  constexpr uint64_t layout = kRowBytes == 128 ? 2 : 4;
+  constexpr uint64_t sbo = (8 * kRowBytes) >> 4;
+  return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(lbo_bytes >> 4) << 16) | (sbo << 32) |
+         (uint64_t(1) << 46) | (layout << 61);
+}
+
 // Split form for hot issue loops: the high word is a compile-time constant and the low word is
 // (addr >> 4) | LBO, so stepping an operand by `bytes` is a plain 32-bit add of (bytes >> 4) -- shared-memory
 // addresses stay below 256 KB, so the add never carries out of the 14-bit address field.

@@ -205,6 +205,161 @@ attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int L
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same attention on the tensor cores.  One CTA = one head of a 128-row tile of the qkv matrix, i.e. floor(128 / L)
+// whole sequences (2 images of 50 tokens, or 1 prompt of 77):
+//   TMA: Q, K, V head slices [128 rows][64] (128-B rows, 128B swizzle) -> smem
+//   S = Q K^T            tcgen05.mma 128 x 128 x 64 (both operands K-major)            -> TMEM, 128 fp32 columns
+//   P = exp(S - rowmax)  thread <-> row; keys outside the row's own sequence (and, causal, after it) are exactly 0;
+//                        written fp16 to smem in the K-major swizzled layout the next MMA reads
+//   O = P V              tcgen05.mma 128 x 64 x 128; V is the MN-major operand (keys are its K dimension)  -> TMEM
+//   out = O / rowsum     fp16, 128 B per row
+// The cross-sequence quarter of S is computed and discarded: the tensor pipe is ~30x faster than the CUDA-core loop above,
+// so the waste is free.  ~82 KB smem and 256 TMEM columns per CTA: two CTAs per SM hide the load -> MMA -> softmax -> MMA chain.
+// ------------------------------------------------------------------------------------------------
+struct AttnTcParams {
+  int rows;        // S * L rows of qkv
+  int L, D;
+  int nseq;        // sequences per tile = 128 / L
+  int causal;
+  __half* out;     // [rows][D]
+};
+constexpr int kAttnTcSmem = 1024 + 3 * 16384 + 32768 + 64;
+
+__global__ void __launch_bounds__(128, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base, sK = base + 16384, sV = base + 32768, sP = base + 49152;
+  const uint32_t bar_load = sP + 32768, bar_s = bar_load + 8, bar_o = bar_load + 16, tmem_slot = bar_load + 24;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, h = blockIdx.y;
+  const int r0 = tile * p.nseq * p.L;
+  const int rows_valid = min(p.nseq * p.L, p.rows - r0);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar_load, 3 * 16384);
+    tma_load_2d(&tmQKV, bar_load, sQ, h * 64, r0);
+    tma_load_2d(&tmQKV, bar_load, sK, p.D + h * 64, r0);
+    tma_load_2d(&tmQKV, bar_load, sV, 2 * p.D + h * 64, r0);
+    mbar_wait(bar_load, 0);
+    tcgen05_fence_after();
+    constexpr uint32_t idesc = make_idesc_f16_f32(128, 128);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_f16_ss(tS, make_kmajor_desc<128>(sQ + 32 * k), make_kmajor_desc<128>(sK + 32 * k), idesc, k != 0);
+    umma_commit(bar_s);
+  }
+  __syncwarp();
+
+  // ---- softmax: thread <-> row
+  const int r = warp * 32 + lane;
+  const int seq = r / p.L;
+  const int j0 = seq * p.L;
+  int j1 = j0 + p.L;
+  if (p.causal) j1 = min(j1, r + 1);
+  const bool live = r < rows_valid;
+  mbar_wait(bar_s, 0);
+  tcgen05_fence_after();
+  const uint32_t trow = tS + (uint32_t(warp * 32) << 16);
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32b<32>(trow + uint32_t(32 * c), v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int j = 32 * c + i;
+      if (j >= j0 && j < j1) mx = fmaxf(mx, __uint_as_float(v[i]));
+    }
+  }
+  float sum = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32b<32>(trow + uint32_t(32 * c), v);
+    tmem_ld_wait();
+    uint32_t h2[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const int j = 32 * c + i;
+      const float a = (live && j >= j0 && j < j1) ? __expf(__uint_as_float(v[i]) - mx) : 0.f;
+      const float b = (live && j + 1 >= j0 && j + 1 < j1) ? __expf(__uint_as_float(v[i + 1]) - mx) : 0.f;
+      sum += a + b;
+      h2[i >> 1] = pack_half2(a, b);
+    }
+    // 32 keys = 4 pieces of 16 B in chunk (32c / 64), pieces ((32c % 64) / 8) .. +3
+    const uint32_t chunk = sP + uint32_t((32 * c) / 64) * 16384u;
+    const int piece0 = ((32 * c) % 64) / 8;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t a = chunk + swizzle_off<128>(uint32_t(r), uint32_t(piece0 + q));
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(h2[4 * q]), "r"(h2[4 * q + 1]), "r"(h2[4 * q + 2]), "r"(h2[4 * q + 3]) : "memory");
+    }
+  }
+  fence_proxy_async_smem();                        // P (generic-proxy stores) -> visible to the tensor core's smem reads
+  tcgen05_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tcgen05_fence_after();
+    constexpr uint32_t idesc = make_idesc_f16_f32(128, 64) | (1u << 16);      // B (= V) is MN-major
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {               // 16 keys per MMA
+      const uint64_t da = make_kmajor_desc<128>(sP + uint32_t(ks / 4) * 16384u + 32u * uint32_t(ks % 4));
+      const uint64_t db = make_mnmajor_desc<128>(sV + uint32_t(ks) * 2048u, 16384u);
+      umma_f16_ss(tO, da, db, idesc, ks != 0);
+    }
+    umma_commit(bar_o);
+  }
+  __syncwarp();
+  mbar_wait(bar_o, 0);
+  tcgen05_fence_after();
+  {
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    __half* orow = p.out + (size_t)(r0 + r) * p.D + (size_t)h * 64;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32b<32>(tO + (uint32_t(warp * 32) << 16) + uint32_t(32 * c), v);
+      tmem_ld_wait();
+      if (live) {
+        uint4* o4 = reinterpret_cast<uint4*>(orow + 32 * c);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = pack_half2(__uint_as_float(v[8 * q]) * inv, __uint_as_float(v[8 * q + 1]) * inv);
+          o.y = pack_half2(__uint_as_float(v[8 * q + 2]) * inv, __uint_as_float(v[8 * q + 3]) * inv);
+          o.z = pack_half2(__uint_as_float(v[8 * q + 4]) * inv, __uint_as_float(v[8 * q + 5]) * inv);
+          o.w = pack_half2(__uint_as_float(v[8 * q + 6]) * inv, __uint_as_float(v[8 * q + 7]) * inv);
+          o4[q] = o;
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
 // logits[b][k] = exp(logit_scale) * <img_b, txt_k> / (|img_b| |txt_k|);  one warp per (b, k)
 __global__ void __launch_bounds__(256)
 clip_logits_kernel(const float* __restrict__ img, const float* __restrict__ txt, float* __restrict__ logits, int B, int K, int E,

@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -178,6 +179,30 @@ int tf_layernorm(const embclip_tf* m, const float* x, int wid, int bid, __half* 
   return 0;
 }
 
+int tf_attention(embclip_tf* m, const TfWs& w, int S, int causal, cudaStream_t st) {
+  const int D = m->cfg.width, L = m->L, rows = S * L;
+  static const bool cuda_core = getenv("EMBCLIP_ATTN_CUDA_CORE") != nullptr;      // first version, kept for A/B timing
+  if (cuda_core || L > 128) {
+    attention_kernel<<<dim3(S, m->cfg.heads), 128, 0, st>>>(w.qkv, w.attn, L, D, causal);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnTcSmem));
+    attr = true;
+  }
+  CUtensorMap tm;
+  int rc;
+  if ((rc = make_map_2d(&tm, w.qkv, rows, 3 * D, 3 * D, 64, 128))) return rc;
+  AttnTcParams p;
+  p.rows = rows; p.L = L; p.D = D; p.nseq = 128 / L; p.causal = causal; p.out = w.attn;
+  const int tiles = (S + p.nseq - 1) / p.nseq;
+  attention_tc_kernel<<<dim3(tiles, m->cfg.heads), 128, kAttnTcSmem, st>>>(tm, p);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 // the 12 (or `layers`) ResidualAttentionBlocks on the fp32 stream w.x, then ln_post / ln_final of the pooled rows and the head GEMM
 int tf_blocks_and_head(embclip_tf* m, const TfWs& w, int S, int causal, long long pool_stride, const long long* pool_rows, float* out,
                        cudaStream_t st) {
@@ -186,8 +211,7 @@ int tf_blocks_and_head(embclip_tf* m, const TfWs& w, int S, int causal, long lon
   for (const TfBlock& b : m->blocks) {
     if ((rc = tf_layernorm(m, w.x, b.ln1w, b.ln1b, w.xn, M, 1, nullptr, st))) return rc;
     if ((rc = tf_gemm(w.xn, D, TP<__half>(m, b.qkvw), TP<float>(m, b.qkvb), w.qkv, M, 3 * D, 0, 0, nullptr, st))) return rc;
-    attention_kernel<<<dim3(S, m->cfg.heads), 128, 0, st>>>(w.qkv, w.attn, m->L, D, causal);
-    CUDA_TRY(cudaGetLastError());
+    if ((rc = tf_attention(m, w, S, causal, st))) return rc;
     if ((rc = tf_gemm(w.attn, D, TP<__half>(m, b.outw), TP<float>(m, b.outb), w.x, M, D, 0, 1, w.x, st))) return rc;
     if ((rc = tf_layernorm(m, w.x, b.ln2w, b.ln2b, w.xn, M, 1, nullptr, st))) return rc;
     if ((rc = tf_gemm(w.xn, D, TP<__half>(m, b.fcw), TP<float>(m, b.fcb), w.hid, M, 4 * D, 2, 0, nullptr, st))) return rc;

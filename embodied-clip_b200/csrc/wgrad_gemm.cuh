@@ -53,17 +53,6 @@ struct WgradCfg {
   static_assert(kBBox % 1024 == 0, "boxes keep 1024-B alignment");
 };
 
-// MN-major operand tile: rows of kRowBytes (= box width * 2) along MN, 8-row K groups kRowBytes*8 apart (SBO),
-// `lbo_bytes` between successive boxes along MN.
-template <int kRowBytes>
-__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
-  static_assert(kRowBytes == 128 || kRowBytes == 64, "swizzle");
-  constexpr uint64_t layout = kRowBytes == 128 ? 2 : 4;
-  constexpr uint64_t sbo = (8 * kRowBytes) >> 4;
-  return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(lbo_bytes >> 4) << 16) | (sbo << 32) |
-         (uint64_t(1) << 46) | (layout << 61);
-}
-
 template <int BN>
 __global__ void __launch_bounds__(192, 1)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradParams p) {
