@@ -276,6 +276,17 @@ def run_vit_block(dev, rank, world, steps, warmup, max_over_ranks, barrier, tota
     }
 
 
+def committed_traffic():
+    """DRAM bytes of the tensor-core conv kernels of one B=256 step, from the newest committed ncu capture
+    (profiles/*_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the step's launches)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    return d["tensor_core_conv_kernels"]["dram_bytes_per_step"], os.path.relpath(files[-1], ROOT)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -421,6 +432,7 @@ def run_ours(args, rank, local_rank, world):
     achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12
     step_tflops = (FLOP_TRUNK + FLOP_ATTNPOOL_MIN) * BATCH / (ms_step * 1e-3) / 1e12
     top = sorted(prof, key=lambda x: -x[1])[:8]
+    traffic, traffic_src = committed_traffic()
 
     cpu_fps, cpu_sec = (None, None) if args.no_cpu else time_cpu_oracle(oracle_model(), 32, 4, 1)
     line_ppo = ppo
@@ -435,9 +447,11 @@ def run_ours(args, rank, local_rank, world):
                 "ms_per_step": e2e_ms / K, "api": "ClipRN50Encoder.forward on pinned host frames, double-buffered H2D/D2H"},
         "gpu_launches": enc.launches_per_forward(HEADS) * K,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (all %d launches of a step)" % n_gemm,
+        "roofline": {"bound": "tensor", "kernel": "tcgen05 conv kernels: conv_gemm + gemm2sm + conv3x3_halo (all %d launches of a step)" % n_gemm,
                      "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
-                     "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src})",
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_bytes_per_step": int((154.1 + 47.2 + 29.6 + 105.9) * 1e6),
+                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src})",
                      "frac_of_burst": achieved / burst, "gemm_ms_per_step": gemm_ms,
                      "whole_step_tflops": step_tflops, "whole_step_frac": step_tflops / sustained},
         "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
