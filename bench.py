@@ -35,10 +35,15 @@ HEADS = ("trunk", "avgpool", "attnpool")
 METRIC = "frames/sec CLIP-RN50 encode (224x224, batch 256/GPU): trunk[2048,7,7] + attnpool-1024 + avgpool-2048"
 
 
-def synthetic_frames(batch, seed=0):
+def synthetic_frames_u8(batch, seed=0):
     import torch
     g = torch.Generator().manual_seed(seed)
-    u8 = torch.randint(0, 256, (batch, RES, RES, 3), generator=g, dtype=torch.uint8)
+    return torch.randint(0, 256, (batch, RES, RES, 3), generator=g, dtype=torch.uint8)
+
+
+def synthetic_frames(batch, seed=0):
+    import torch
+    u8 = synthetic_frames_u8(batch, seed)
     mean = torch.tensor([0.48145466, 0.4578275, 0.40821073])
     std = torch.tensor([0.26862954, 0.26130258, 0.27577711])
     return (u8.float() / 255.0 - mean) / std
@@ -139,8 +144,8 @@ def run_ppo_block(enc, dev, rank, world, rollouts, max_over_ranks, barrier, T=12
     model = ResnetTensorNavActorCritic(device=dev, seed=1)
     trainer = PPOTrainer(model, lr=3e-4, max_grad_norm=0.5, update_repeats=4)
     stepper = SyntheticPPOStep(enc, model, trainer, T=T, N=N, seed=10 + rank)
-    host = synthetic_frames(N, seed=200 + rank).pin_memory()
-    frames = host.to(dev)
+    host = synthetic_frames_u8(N, seed=200 + rank).pin_memory()     # e2e leg: raw uint8 frames, normalised in the stem kernel
+    frames = synthetic_frames(N, seed=200 + rank).to(dev)           # device-resident leg: fp32 normalised (the AllenAct boundary dtype)
     grows = T * N * world
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
@@ -165,7 +170,7 @@ def run_ppo_block(enc, dev, rank, world, rollouts, max_over_ranks, barrier, T=12
     # the loss terms are read back to the host after every update
     copy = torch.cuda.Stream(dev)
     main = torch.cuda.current_stream(dev)
-    slots = [torch.empty_like(frames) for _ in range(2)]
+    slots = [torch.empty(host.shape, dtype=torch.uint8, device=dev) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     used = [torch.cuda.Event() for _ in range(2)]
 
@@ -210,8 +215,8 @@ def run_ppo_block(enc, dev, rank, world, rollouts, max_over_ranks, barrier, T=12
         "config": {"workload": "objectnav_ppo_step", "steps": T, "samplers_per_gpu": N, "update_repeats": 4, "num_mini_batch": 1,
                    "global_rows": grows, "collective": "1 flat fp32 gradient all-reduce (13.9 MB) per update pass" if world > 1 else "none (1 GPU)"},
         "e2e": {"value": frames_per_step / (e2e_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": T * host.numel() * 4, "d2h_bytes_per_step": 5 * 4,
-                "api": "ClipRN50Encoder.forward + ResnetTensorNavActorCritic act + PPOTrainer.update, frames from pinned host memory"},
+                "h2d_bytes_per_step": T * host.numel(), "d2h_bytes_per_step": 5 * 4, "input": "uint8 NHWC raw RGB",
+                "api": "ClipRN50Encoder.forward(uint8) + ResnetTensorNavActorCritic act + PPOTrainer.update, frames from pinned host memory"},
         "gpu_launches": stepper.launches_per_step() * rollouts,
         "last_loss": last,
     }
@@ -413,6 +418,21 @@ def run_ours(args, rank, local_rank, world):
     h2d = host_frames.numel() * 4
     d2h = sum(v.numel() * 4 for v in dev_out[0].values())
 
+    # same end-to-end loop from RAW uint8 frames (section 8f item 1): 4x fewer H2D bytes, normalisation in the stem kernel
+    host_u8 = synthetic_frames_u8(BATCH, seed=100 + rank).pin_memory()
+    host_f32, dev_in_f32 = host_frames, dev_in
+    host_frames, dev_in = host_u8, [torch.empty(host_u8.shape, dtype=torch.uint8, device=dev) for _ in range(2)]
+    e2e_steps(max(W, 2))
+    barrier()
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u0.record(main)
+    e2e_steps(K)
+    main.wait_stream(copy_out)
+    u1.record(main)
+    barrier()
+    e2e_u8_ms = max_over_ranks(u0.elapsed_time(u1))
+    host_frames, dev_in = host_f32, dev_in_f32
+
     # ---------------- BASELINE configs 3 / 4: end-to-end PPO step (all ranks: the update all-reduces gradients)
     ppo = None if args.no_ppo else run_ppo_block(enc, dev, rank, world, args.ppo_rollouts, max_over_ranks, barrier)
     vit = None if args.no_vit else run_vit_block(dev, rank, world, max(10, K // 4), 5, max_over_ranks, barrier)
@@ -445,6 +465,8 @@ def run_ours(args, rank, local_rank, world):
                    "l2": "per-step working set (154 MB frames + 6.6 GB activations) exceeds the 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / K, "api": "ClipRN50Encoder.forward on pinned host frames, double-buffered H2D/D2H"},
+        "e2e_u8": {"value": world * BATCH * K / (e2e_u8_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": host_u8.numel(),
+                   "d2h_bytes_per_step": d2h, "ms_per_step": e2e_u8_ms / K, "input": "uint8 NHWC raw RGB, normalised in the stem kernel"},
         "gpu_launches": enc.launches_per_forward(HEADS) * K,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "tcgen05 conv kernels: conv_gemm + gemm2sm + conv3x3_halo (all %d launches of a step)" % n_gemm,

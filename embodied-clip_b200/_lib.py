@@ -52,6 +52,7 @@ SIGNATURES = {
     "embclip_rn50_bind_weights": (_I, [_VP, _VP, _U64]),
     "embclip_rn50_workspace_bytes": (_U64, [_VP, _I]),
     "embclip_rn50_forward": (_I, [_VP, _FP, _I, _FP, _FP, _FP, _VP, _U64, _VP]),
+    "embclip_rn50_forward_u8": (_I, [_VP, _VP, C.POINTER(C.c_float), C.POINTER(C.c_float), _I, _FP, _FP, _FP, _VP, _U64, _VP]),
     "embclip_rn50_num_acts": (_I, [_VP]),
     "embclip_rn50_act_info": (_I, [_VP, _I, _I, C.POINTER(ActInfo)]),
     "embclip_rn50_profile": (_I, [_VP, _FP, _I, _FP, _FP, _FP, _VP, _U64, _VP, _VP, _VP, _I]),

@@ -449,13 +449,17 @@ extern "C" int embclip_avgpool2_f16(const void* in, void* out, int B, int H, int
   return launch_avgpool2(in, out, B, H, W, C, (cudaStream_t)stream);
 }
 
-static int launch_stem_conv1(const float* x, const float* w, const float* b, void* y, int B, int R, int Cout, cudaStream_t st) {
-  if (R % 2) return fail(EMBCLIP_EINVAL, "stem: resolution must be even");
-  const long long total = (long long)B * (R / 2) * (R / 2);
+static int launch_stem_conv1(const void* x, int x_u8, const float* norm6, const float* w, const float* b, void* y, int B, int R, int Cout, cudaStream_t st) {
+  if (R % 4) return fail(EMBCLIP_EINVAL, "stem: resolution must be a multiple of 4");
+  const long long total = (long long)B * (R / 2) * (R / 4);      // one thread per PAIR of output pixels
   const int blocks = (int)((total + 127) / 128);
   if (blocks <= 0) return 0;
-  if (Cout == 32)
-    CUDA_TRY(launch_pdl(stem_conv1_kernel<32>, dim3(blocks), dim3(128), 0, st, x, w, b, reinterpret_cast<__half*>(y), B, R));
+  StemNorm nm;
+  for (int c = 0; c < 3; ++c) { nm.scale[c] = norm6 ? norm6[c] : 1.f; nm.offset[c] = norm6 ? norm6[3 + c] : 0.f; }
+  if (Cout == 32 && x_u8)
+    CUDA_TRY(launch_pdl(stem_conv1_kernel<32, uint8_t>, dim3(blocks), dim3(128), 0, st, reinterpret_cast<const uint8_t*>(x), w, b, reinterpret_cast<__half*>(y), B, R, nm));
+  else if (Cout == 32)
+    CUDA_TRY(launch_pdl(stem_conv1_kernel<32, float>, dim3(blocks), dim3(128), 0, st, reinterpret_cast<const float*>(x), w, b, reinterpret_cast<__half*>(y), B, R, nm));
   else
     return fail(EMBCLIP_EINVAL, "stem conv1: only Cout == 32 (width 64) is built");
   CUDA_TRY(cudaGetLastError());
@@ -464,7 +468,7 @@ static int launch_stem_conv1(const float* x, const float* w, const float* b, voi
 extern "C" int embclip_stem_conv1(const float* frames, const float* w, const float* bias, void* out, int B, int R, int Cout,
                                   void* stream) {
   if (!frames || !w || !bias || !out) return fail(EMBCLIP_EINVAL, "stem_conv1: null pointer");
-  return launch_stem_conv1(frames, w, bias, out, B, R, Cout, (cudaStream_t)stream);
+  return launch_stem_conv1(frames, 0, nullptr, w, bias, out, B, R, Cout, (cudaStream_t)stream);
 }
 
 // =============================================================================================
@@ -725,15 +729,16 @@ extern "C" int embclip_rn50_act_info(embclip_rn50_t h, int batch, int index, emb
   return 0;
 }
 
-static int run_op(embclip_rn50* m, const Op& op, const std::vector<uint64_t>& offs, const float* frames, int B,
+struct FramesIn { const void* ptr; int u8; float norm[6]; };
+static int run_op(embclip_rn50* m, const Op& op, const std::vector<uint64_t>& offs, const FramesIn& frames, int B,
                   float* o_nchw, float* o_avg, float* o_attn, uint8_t* ws, cudaStream_t st) {
   auto act_ptr = [&](int id) -> void* { return id >= 0 ? (void*)(ws + offs[id]) : nullptr; };
   auto param_ptr = [&](int id) -> const void* { return id >= 0 ? (const void*)(m->blob + m->params[id].info.offset) : nullptr; };
   const int P = m->fres * m->fres;
   switch (op.kind) {
     case K_STEM1:
-      return launch_stem_conv1(frames, (const float*)param_ptr(op.wp), (const float*)param_ptr(op.bp), act_ptr(op.out), B,
-                               m->cfg.input_resolution, op.cout, st);
+      return launch_stem_conv1(frames.ptr, frames.u8, frames.u8 ? frames.norm : nullptr, (const float*)param_ptr(op.wp),
+                               (const float*)param_ptr(op.bp), act_ptr(op.out), B, m->cfg.input_resolution, op.cout, st);
     case K_POOL: {
       const Act& a = m->acts[op.in0];
       return launch_avgpool2(act_ptr(op.in0), act_ptr(op.out), B, a.h, a.w, a.c, st);
@@ -795,9 +800,9 @@ static int run_op(embclip_rn50* m, const Op& op, const std::vector<uint64_t>& of
   return fail(EMBCLIP_EINVAL, "unknown op kind");
 }
 
-static int forward_impl(embclip_rn50* m, const float* frames, int B, float* o_nchw, float* o_avg, float* o_attn, void* ws,
+static int forward_impl(embclip_rn50* m, const FramesIn& frames, int B, float* o_nchw, float* o_avg, float* o_attn, void* ws,
                         uint64_t ws_bytes, cudaStream_t st, float* op_ms, char* names, int max_ops) {
-  if (!m || !frames || !ws || B <= 0) return fail(EMBCLIP_EINVAL, "forward: null argument or empty batch");
+  if (!m || !frames.ptr || !ws || B <= 0) return fail(EMBCLIP_EINVAL, "forward: null argument or empty batch");
   if (!m->blob) return fail(EMBCLIP_ESTATE, "forward: weights not bound (call embclip_rn50_bind_weights first)");
   const uint64_t need = embclip_rn50_workspace_bytes(m, B);
   if (ws_bytes < need) return fail(EMBCLIP_ENOSPC, "forward: workspace %llu B < required %llu B", (unsigned long long)ws_bytes, (unsigned long long)need);
@@ -836,7 +841,22 @@ static int forward_impl(embclip_rn50* m, const float* frames, int B, float* o_nc
 extern "C" int embclip_rn50_forward(embclip_rn50_t h, const float* frames_nhwc, int batch, float* out_trunk_nchw,
                                     float* out_avgpool, float* out_attnpool, void* workspace, uint64_t workspace_bytes,
                                     void* stream) {
-  const int rc = forward_impl(h, frames_nhwc, batch, out_trunk_nchw, out_avgpool, out_attnpool, workspace, workspace_bytes,
+  const FramesIn in{frames_nhwc, 0, {1, 1, 1, 0, 0, 0}};
+  const int rc = forward_impl(h, in, batch, out_trunk_nchw, out_avgpool, out_attnpool, workspace, workspace_bytes,
+                              (cudaStream_t)stream, nullptr, nullptr, 0);
+  return rc < 0 ? rc : 0;
+}
+extern "C" int embclip_rn50_forward_u8(embclip_rn50_t h, const uint8_t* frames_nhwc_u8, const float* mean3, const float* std3, int batch,
+                                       float* out_trunk_nchw, float* out_avgpool, float* out_attnpool, void* workspace,
+                                       uint64_t workspace_bytes, void* stream) {
+  if (!mean3 || !std3) return fail(EMBCLIP_EINVAL, "forward_u8: mean / std required");
+  FramesIn in{frames_nhwc_u8, 1, {0, 0, 0, 0, 0, 0}};
+  for (int c = 0; c < 3; ++c) {
+    if (!(std3[c] > 0.f)) return fail(EMBCLIP_EINVAL, "forward_u8: std must be positive");
+    in.norm[c] = 1.f / (255.f * std3[c]);
+    in.norm[3 + c] = -mean3[c] / std3[c];
+  }
+  const int rc = forward_impl(h, in, batch, out_trunk_nchw, out_avgpool, out_attnpool, workspace, workspace_bytes,
                               (cudaStream_t)stream, nullptr, nullptr, 0);
   return rc < 0 ? rc : 0;
 }
@@ -844,7 +864,8 @@ extern "C" int embclip_rn50_profile(embclip_rn50_t h, const float* frames_nhwc, 
                                     float* out_avgpool, float* out_attnpool, void* workspace, uint64_t workspace_bytes,
                                     void* stream, float* op_ms, char* names, int max_ops) {
   if (!op_ms || max_ops <= 0) return fail(EMBCLIP_EINVAL, "profile: need op_ms buffer");
-  return forward_impl(h, frames_nhwc, batch, out_trunk_nchw, out_avgpool, out_attnpool, workspace, workspace_bytes,
+  const FramesIn in{frames_nhwc, 0, {1, 1, 1, 0, 0, 0}};
+  return forward_impl(h, in, batch, out_trunk_nchw, out_avgpool, out_attnpool, workspace, workspace_bytes,
                       (cudaStream_t)stream, op_ms, names, max_ops);
 }
 extern "C" int embclip_rn50_launches_per_forward(embclip_rn50_t h, int want_trunk, int want_avgpool, int want_attnpool) {

@@ -16,13 +16,16 @@ from .packing import infer_rn_cfg, pack_blob
 
 
 class ClipRN50Encoder:
-    """Frozen CLIP ModifiedResNet forward: frames fp32 NHWC [B,R,R,3] (already mean/std normalised) ->
+    """Frozen CLIP ModifiedResNet forward: frames fp32 NHWC [B,R,R,3] (already mean/std normalised) or uint8 NHWC (raw
+    RGB, normalised in the stem kernel) ->
     'trunk' fp32 [B,2048,7,7] | 'avgpool' fp32 [B,2048] | 'attnpool' fp32 [B,1024].
 
     Replaces ``clip_model.visual`` as used at
     primitive_probing/generate_data/thor_image_features.py:57-67,109-113."""
 
     HEADS = ("trunk", "avgpool", "attnpool")
+    CLIP_RGB_MEANS = (0.48145466, 0.4578275, 0.40821073)
+    CLIP_RGB_STDS = (0.26862954, 0.26130258, 0.27577711)
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device: torch.device | str = "cuda:0"):
         self.lib = _lib.load()
@@ -102,8 +105,8 @@ class ClipRN50Encoder:
         R = self.cfg["input_resolution"]
         if frames.device != self.device:
             raise ValueError(f"frames on {frames.device}, encoder on {self.device}")
-        if frames.dtype != torch.float32 or frames.dim() != 4 or tuple(frames.shape[1:]) != (R, R, 3):
-            raise ValueError(f"frames must be float32 NHWC [B,{R},{R},3], got {frames.dtype} {tuple(frames.shape)}")
+        if frames.dtype not in (torch.float32, torch.uint8) or frames.dim() != 4 or tuple(frames.shape[1:]) != (R, R, 3):
+            raise ValueError(f"frames must be float32 (normalised) or uint8 (raw) NHWC [B,{R},{R},3], got {frames.dtype} {tuple(frames.shape)}")
         return frames.contiguous()
 
     def forward(self, frames: torch.Tensor, want: Iterable[str] = ("trunk",),
@@ -118,8 +121,13 @@ class ClipRN50Encoder:
         ptr = lambda k: outs[k].data_ptr() if k in outs else None
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            _lib.check(self.lib.embclip_rn50_forward(self._h, frames.data_ptr(), B, ptr("trunk"), ptr("avgpool"),
-                                                     ptr("attnpool"), ws.data_ptr(), ws.numel(), stream))
+            if frames.dtype == torch.uint8:       # raw RGB: mean/std normalisation happens inside the stem kernel
+                mean, std = (C.c_float * 3)(*self.CLIP_RGB_MEANS), (C.c_float * 3)(*self.CLIP_RGB_STDS)
+                _lib.check(self.lib.embclip_rn50_forward_u8(self._h, frames.data_ptr(), mean, std, B, ptr("trunk"), ptr("avgpool"),
+                                                            ptr("attnpool"), ws.data_ptr(), ws.numel(), stream))
+            else:
+                _lib.check(self.lib.embclip_rn50_forward(self._h, frames.data_ptr(), B, ptr("trunk"), ptr("avgpool"),
+                                                         ptr("attnpool"), ws.data_ptr(), ws.numel(), stream))
         return outs
 
     __call__ = forward

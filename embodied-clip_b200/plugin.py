@@ -171,6 +171,8 @@ class ClipResNetPreprocessor(_Base):
         x = obs[self.input_uuids[0]].to(self.device)     # bhwc, kept channels-last: the kernels are NHWC
         if x.shape[-1] == 1:                             # depth: repeat across the 3 channels
             x = x.repeat(1, 1, 1, 3)
+        if x.dtype == torch.uint8:                       # raw RGB from an un-normalised sensor: normalised in the stem kernel
+            return self.resnet.forward_nhwc(x.contiguous())
         return self.resnet.forward_nhwc(x.float().contiguous())
 
 

@@ -81,6 +81,12 @@ uint64_t embclip_rn50_workspace_bytes(embclip_rn50_t h, int batch);
 int embclip_rn50_forward(embclip_rn50_t h, const float* frames_nhwc, int batch, float* out_trunk_nchw,
                          float* out_avgpool, float* out_attnpool, void* workspace, uint64_t workspace_bytes,
                          void* stream);
+/* Same, from RAW frames: uint8 NHWC [batch, R, R, 3]; (v / 255 - mean[c]) / std[c] -- the normalisation the AllenAct
+ * RGB sensor does on the host (ClipResNetPreprocessor.CLIP_RGB_MEANS / CLIP_RGB_STDS) -- is applied inside the stem
+ * kernel, so the host-to-device copy is 4x smaller.  mean3 / std3: host arrays. */
+int embclip_rn50_forward_u8(embclip_rn50_t h, const uint8_t* frames_nhwc_u8, const float* mean3, const float* std3, int batch,
+                            float* out_trunk_nchw, float* out_avgpool, float* out_attnpool, void* workspace,
+                            uint64_t workspace_bytes, void* stream);
 /* Introspection for layer-by-layer parity tests: intermediate activations live in the workspace. */
 typedef struct {
   char name[64];

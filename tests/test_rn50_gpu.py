@@ -114,3 +114,24 @@ def test_rn50_large_batch_properties(encoder):
     for k in ("trunk", "attnpool"):
         assert torch.equal(big[k][:8], ref[k]), k
         assert torch.equal(big[k].view(B // 8, 8, -1), ref[k].view(1, 8, -1).expand(B // 8, -1, -1)), k
+
+
+def test_rn50_uint8_frames(encoder, rn50_visual):
+    """Raw uint8 frames: the stem kernel applies (v / 255 - mean) / std itself.  Same
+    result as handing over host-normalised fp32 frames, up to the rounding of the normalisation (one FMA on the device,
+    div-sub-div on the host) -- and within the north-star bar of the fp32 oracle."""
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (3, 224, 224, 3), generator=g, dtype=torch.uint8)
+    mean, std = torch.tensor(encoder.CLIP_RGB_MEANS), torch.tensor(encoder.CLIP_RGB_STDS)
+    f32 = (u8.float() / 255.0 - mean) / std
+    a = encoder(u8.cuda(), want=("trunk", "attnpool"))
+    a = {k: v.clone() for k, v in a.items()}
+    b = encoder(f32.cuda(), want=("trunk", "attnpool"))
+    torch.cuda.synchronize()
+    for k in ("trunk", "attnpool"):
+        assert rel_l2(a[k].cpu(), b[k].cpu()) <= 5e-4, k
+    with torch.no_grad():
+        t = rn50_visual.trunk(f32.permute(0, 3, 1, 2).contiguous())
+    assert rel_l2(a["trunk"].cpu(), t) <= 1e-3
+    with pytest.raises(ValueError):
+        encoder(torch.zeros(2, 224, 224, 3, device="cuda", dtype=torch.int32))
