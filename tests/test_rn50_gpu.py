@@ -128,8 +128,17 @@ def test_rn50_uint8_frames(encoder, rn50_visual):
     a = {k: v.clone() for k, v in a.items()}
     b = encoder(f32.cuda(), want=("trunk", "attnpool"))
     torch.cuda.synchronize()
+    # stem.conv1 differs by 9e-6 (0.06 % of its fp16 roundings flip); the flips cascade through 50 fp16 layers exactly as
+    # they do between any two fp16 pipelines with different summation order (oracle/fp16_path.py): bound it the same way
     for k in ("trunk", "attnpool"):
-        assert rel_l2(a[k].cpu(), b[k].cpu()) <= 5e-4, k
+        assert rel_l2(a[k].cpu(), b[k].cpu()) <= 1.5e-3, k
+    acts_u8 = encoder.activations(3)          # (second forward overwrote the workspace: re-run the raw path for its stem)
+    encoder(u8.cuda(), want=("trunk",))
+    torch.cuda.synchronize()
+    stem_u8 = encoder.activations(3)["stem.conv1"].clone()
+    encoder(f32.cuda(), want=("trunk",))
+    torch.cuda.synchronize()
+    assert rel_l2(stem_u8.cpu(), encoder.activations(3)["stem.conv1"].cpu()) <= 5e-5
     with torch.no_grad():
         t = rn50_visual.trunk(f32.permute(0, 3, 1, 2).contiguous())
     assert rel_l2(a["trunk"].cpu(), t) <= 1e-3
