@@ -249,7 +249,8 @@ int embclip::launch_gemm(const GemmOp& op, cudaStream_t st, int force_bn) {
     const long long M = (long long)op.n * op.h * op.w;
     if (use_2sm && !force_bn && op.taps == 1 && !op.grp_n && op.c0 % 64 == 0 && op.c1 % 64 == 0 && op.cout % 256 == 0 &&
         (op.a_cols == 0 || op.a_cols == op.c0) && op.lda0 == op.c0 && op.c0 + op.c1 >= (op.residual ? 2 * min_k : min_k) &&
-        M >= 2048 && !(op.residual && op.out_f32))      // (short-K residual GEMMs are epilogue-bound: measured slower on pairs)
+        M >= 2048 && !(op.residual && op.out_f32) &&    // (short-K residual GEMMs are epilogue-bound: measured slower on pairs)
+        ((M + 255) / 256) * (op.cout / 256) >= num_sms() / 2)                       // enough pair tiles for every SM pair
       return op.residual ? launch_gemm2sm<256, true>(op, st) : launch_gemm2sm<256, false>(op, st);
   }
   const int bk = (op.c0 % 64 == 0 && op.c1 % 64 == 0) ? 64 : 32;
@@ -453,13 +454,14 @@ static int launch_stem_conv1(const void* x, int x_u8, const float* norm6, const 
   if (R % 4) return fail(EMBCLIP_EINVAL, "stem: resolution must be a multiple of 4");
   const long long total = (long long)B * (R / 2) * (R / 4);      // one thread per PAIR of output pixels
   const int blocks = (int)((total + 127) / 128);
+  const size_t smem = 0;
   if (blocks <= 0) return 0;
   StemNorm nm;
   for (int c = 0; c < 3; ++c) { nm.scale[c] = norm6 ? norm6[c] : 1.f; nm.offset[c] = norm6 ? norm6[3 + c] : 0.f; }
   if (Cout == 32 && x_u8)
-    CUDA_TRY(launch_pdl(stem_conv1_kernel<32, uint8_t>, dim3(blocks), dim3(128), 0, st, reinterpret_cast<const uint8_t*>(x), w, b, reinterpret_cast<__half*>(y), B, R, nm));
+    CUDA_TRY(launch_pdl(stem_conv1_kernel<32, uint8_t>, dim3(blocks), dim3(128), smem, st, reinterpret_cast<const uint8_t*>(x), w, b, reinterpret_cast<__half*>(y), B, R, nm));
   else if (Cout == 32)
-    CUDA_TRY(launch_pdl(stem_conv1_kernel<32, float>, dim3(blocks), dim3(128), 0, st, reinterpret_cast<const float*>(x), w, b, reinterpret_cast<__half*>(y), B, R, nm));
+    CUDA_TRY(launch_pdl(stem_conv1_kernel<32, float>, dim3(blocks), dim3(128), smem, st, reinterpret_cast<const float*>(x), w, b, reinterpret_cast<__half*>(y), B, R, nm));
   else
     return fail(EMBCLIP_EINVAL, "stem conv1: only Cout == 32 (width 64) is built");
   CUDA_TRY(cudaGetLastError());
