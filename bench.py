@@ -226,11 +226,9 @@ def run_vit_block(dev, rank, world, steps, warmup, max_over_ranks, barrier, tota
     """BASELINE config 5: zero-shot ObjectNav path -- CLIP ViT-B/32 image tower + cached text tower + cosine-sim logits,
     512 frames per step split across the ranks (strong scaling; no collective: per-image logits are independent)."""
     import torch
+    from embclip_b200.synthetic import synthetic_clip_vit_b32_state_dict
     from embclip_b200.vit import ClipZeroShot
-    from oracle.clip_model import build_vit_b32, init_synthetic_transformer      # weight GENERATION only (seeded init)
-    torch.manual_seed(0)
-    sd = init_synthetic_transformer(build_vit_b32(), seed=1234).state_dict()
-    zs = ClipZeroShot(sd, dev)
+    zs = ClipZeroShot(synthetic_clip_vit_b32_state_dict(seed=1234), dev)
     per = (total_batch + world - 1) // world
     host = synthetic_frames(per, seed=300 + rank).pin_memory()
     frames = host.to(dev)

@@ -57,3 +57,47 @@ def synthetic_rn50_state_dict(seed: int = 1234, layers=(3, 4, 6, 3), width: int 
     linear("attnpool.v_proj", embed, embed)
     linear("attnpool.c_proj", output_dim, embed)
     return sd
+
+
+def synthetic_clip_vit_b32_state_dict(seed: int = 1234, width: int = 768, layers: int = 12, patch: int = 32, resolution: int = 224,
+                                      embed_dim: int = 512, text_width: int = 512, text_layers: int = 12, context: int = 77,
+                                      vocab: int = 49408) -> "OrderedDict[str, torch.Tensor]":
+    """Seeded synthetic CLIP ViT-B/32 weights (image tower + text tower + logit_scale) with the official state-dict key
+    names.  Matrices ~ N(0, 1/fan_in) (embeddings N(0, 0.02^2)), LayerNorm gains
+    1 + 0.1 N(0,1), biases 0.02 N(0,1), logit_scale = ln(100)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    rn = lambda *s: torch.randn(*s, generator=g)
+
+    def mat(name, *shape, emb=False):
+        sd[name] = rn(*shape) * (0.02 if emb else shape[-1] ** -0.5)
+
+    def ln(name, d):
+        sd[name + ".weight"] = 1.0 + 0.1 * rn(d)
+        sd[name + ".bias"] = 0.02 * rn(d)
+
+    def blocks(prefix, d, n):
+        for i in range(n):
+            p = f"{prefix}transformer.resblocks.{i}."
+            ln(p + "ln_1", d)
+            mat(p + "attn.in_proj_weight", 3 * d, d); sd[p + "attn.in_proj_bias"] = 0.02 * rn(3 * d)
+            mat(p + "attn.out_proj.weight", d, d); sd[p + "attn.out_proj.bias"] = 0.02 * rn(d)
+            ln(p + "ln_2", d)
+            mat(p + "mlp.c_fc.weight", 4 * d, d); sd[p + "mlp.c_fc.bias"] = 0.02 * rn(4 * d)
+            mat(p + "mlp.c_proj.weight", d, 4 * d); sd[p + "mlp.c_proj.bias"] = 0.02 * rn(d)
+
+    sd["visual.conv1.weight"] = rn(width, 3, patch, patch) * (3 * patch * patch) ** -0.5
+    sd["visual.class_embedding"] = 0.02 * rn(width)
+    mat("visual.positional_embedding", (resolution // patch) ** 2 + 1, width, emb=True)
+    ln("visual.ln_pre", width)
+    blocks("visual.", width, layers)
+    ln("visual.ln_post", width)
+    mat("visual.proj", width, embed_dim)
+    sd["visual.proj"] = rn(width, embed_dim) * width ** -0.5
+    mat("token_embedding.weight", vocab, text_width, emb=True)
+    mat("positional_embedding", context, text_width, emb=True)
+    blocks("", text_width, text_layers)
+    ln("ln_final", text_width)
+    sd["text_projection"] = rn(text_width, embed_dim) * text_width ** -0.5
+    sd["logit_scale"] = torch.tensor(4.605170185988092)
+    return sd

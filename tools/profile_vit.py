@@ -3,10 +3,9 @@ import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from embclip_b200.vit import ClipViTEncoder
-from oracle.clip_model import build_vit_b32, init_synthetic_transformer
-torch.manual_seed(0)
+from embclip_b200.synthetic import synthetic_clip_vit_b32_state_dict
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-enc = ClipViTEncoder(init_synthetic_transformer(build_vit_b32(), seed=1234).state_dict(), "cuda:0")
+enc = ClipViTEncoder(synthetic_clip_vit_b32_state_dict(seed=1234), "cuda:0")
 x = torch.randn(B, 224, 224, 3, device="cuda")
 for _ in range(2):
     enc(x)
