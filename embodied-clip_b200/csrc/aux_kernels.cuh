@@ -105,6 +105,155 @@ stem_conv1_kernel(const TIn* __restrict__ x, const float* __restrict__ w, const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Stem conv1 on the tensor cores.  K = 27 is thin, and fp16 operands would cost first-layer precision, so every fp32 input
+// value v and weight w is split into fp16 halves (v = v_hi + v_lo, w = w_hi + w_lo, each exact to 2^-22) and the im2col row
+// of an output pixel is laid out as  [v_hi(27) 0(5) | v_lo(27) 0(5) | v_hi(27) 0(5) | 0(32)]  against weight rows
+// [w_hi | w_hi | w_lo | 0]:  sum = v_hi w_hi + v_lo w_hi + v_hi w_lo, every product exact in the fp32 accumulator.
+// One tile = 128 output pixels: thread <-> pixel gathers its 27 inputs (3 runs of 9 contiguous values; raw uint8 frames are
+// normalised here), writes its 256-B row into the two swizzled K-major k-blocks, one thread issues 8 UMMAs (128 x 32 x 16),
+// and the same threads read their accumulator row back: bias, ReLU, fp16, one 64-B store per pixel.  ~150 instructions
+// per pixel instead of ~1100 on the CUDA cores.  Persistent CTAs (TMEM allocated once), several per SM; the next tile's
+// gather is issued before the current tile's MMA is awaited.
+// ------------------------------------------------------------------------------------------------
+constexpr int kStemTcSmem = 1024 + 2 * 16384 + 2 * 4096 + 64;
+template <typename TIn>
+__global__ void __launch_bounds__(128)
+stem_conv1_tc_kernel(const TIn* __restrict__ x, const __half* __restrict__ wtc, const float* __restrict__ bias,
+                     __half* __restrict__ y, int B, int R, const StemNorm norm) {
+  constexpr int COUT = 32;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base;                        // 2 k-blocks x [128 rows][128 B]
+  const uint32_t sW = base + 32768;                // 2 k-blocks x [32 rows][128 B]
+  const uint32_t bar = sW + 8192, tmem_slot = bar + 8;
+  uint8_t* const gen = smem_raw + (base - smem_u32(smem_raw));
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr bool kRaw = sizeof(TIn) == 1;
+
+  // weights [32][128] fp16 (row n: k-block 0 = cols 0..63, k-block 1 = cols 64..127) -> swizzled K-major tiles
+  for (int i = tid; i < 32 * 16; i += 128) {
+    const int n = i >> 4, piece = i & 15;          // 16-B pieces of the 256-B row
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(wtc + n * 128) + piece);
+    *reinterpret_cast<uint4*>(gen + 32768 + (piece >> 3) * 4096 + swizzle_off<128>(uint32_t(n), uint32_t(piece & 7))) = v;
+  }
+  if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<32>(tmem_slot);
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  griddep_wait();
+
+  const int Ro = R / 2;
+  const long long total = (long long)B * Ro * Ro;
+  const long long num_tiles = (total + 127) / 128;
+  float bv[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) bv[c] = __ldg(bias + c);
+
+  auto gather = [&](long long pix, float (&v)[27]) {
+    if (pix >= total) {
+#pragma unroll
+      for (int i = 0; i < 27; ++i) v[i] = 0.f;
+      return;
+    }
+    const int ow = int(pix % Ro);
+    const int oh = int((pix / Ro) % Ro);
+    const int b = int(pix / ((long long)Ro * Ro));
+    const TIn* xb = x + (size_t)b * R * R * 3;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = 2 * oh - 1 + kh;
+      const bool rok = ih >= 0 && ih < R;
+      const TIn* row = xb + ((size_t)(rok ? ih : 0) * R + 2 * ow) * 3 - 3;     // -> input column 2*ow - 1
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const bool ok = rok && (ow > 0 || j >= 3);                             // column -1 is the zero pad
+        float t = 0.f;
+        if (ok) {
+          t = float(__ldg(row + j));
+          if (kRaw) t = t * norm.scale[j % 3] + norm.offset[j % 3];
+        }
+        v[kh * 9 + j] = t;
+      }
+    }
+  };
+
+  float cur[27];
+  long long tile = blockIdx.x;
+  if (tile < num_tiles) gather(tile * 128 + tid, cur);
+  uint32_t phase = 0;
+  for (; tile < num_tiles; tile += gridDim.x) {
+    // ---- im2col row -> smem (hi / lo split)
+    uint32_t hi[16], lo[16];                       // 32 halves each, pairs packed
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float a = 2 * i < 27 ? cur[2 * i] : 0.f, b2 = 2 * i + 1 < 27 ? cur[2 * i + 1] : 0.f;
+      const __half ha = __float2half_rn(a), hb = __float2half_rn(b2);
+      const __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b2 - __half2float(hb));
+      hi[i] = uint32_t(__half_as_ushort(ha)) | (uint32_t(__half_as_ushort(hb)) << 16);
+      lo[i] = uint32_t(__half_as_ushort(la)) | (uint32_t(__half_as_ushort(lb)) << 16);
+    }
+#pragma unroll
+    for (int piece = 0; piece < 8; ++piece) {      // k-block 0: [hi | lo]
+      const uint32_t* src = piece < 4 ? hi + 4 * piece : lo + 4 * (piece - 4);
+      const uint32_t a = sA + swizzle_off<128>(uint32_t(tid), uint32_t(piece));
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(src[0]), "r"(src[1]), "r"(src[2]), "r"(src[3]) : "memory");
+    }
+#pragma unroll
+    for (int piece = 0; piece < 8; ++piece) {      // k-block 1: [hi | 0]
+      const uint32_t a = sA + 16384 + swizzle_off<128>(uint32_t(tid), uint32_t(piece));
+      if (piece < 4)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hi[4 * piece]), "r"(hi[4 * piece + 1]), "r"(hi[4 * piece + 2]), "r"(hi[4 * piece + 3]) : "memory");
+      else
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory");
+    }
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();                               // all rows written; all accumulator reads of the previous tile done
+    if (tid == 0) {
+      tcgen05_fence_after();
+      constexpr uint32_t idesc = make_idesc_f16_f32(128, COUT);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_f16_ss(tmem_base, make_kmajor_desc<128>(sA + uint32_t(k >> 2) * 16384u + 32u * uint32_t(k & 3)),
+                    make_kmajor_desc<128>(sW + uint32_t(k >> 2) * 4096u + 32u * uint32_t(k & 3)), idesc, k != 0);
+      umma_commit(bar);
+    }
+    __syncwarp();
+    // ---- next tile's inputs are requested while the MMA runs
+    const long long pix = tile * 128 + tid;
+    if (tile + gridDim.x < num_tiles) gather((tile + gridDim.x) * 128 + tid, cur);
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    tcgen05_fence_after();
+    uint32_t v[32];
+    tmem_ld_32x32b<32>(tmem_base + (uint32_t(warp * 32) << 16), v);
+    tmem_ld_wait();
+    if (pix < total) {
+      uint4* out = reinterpret_cast<uint4*>(y + (size_t)pix * COUT);
+#pragma unroll
+      for (int i = 0; i < COUT / 8; ++i) {
+        uint4 o;
+        o.x = pack_half2(fmaxf(__uint_as_float(v[8 * i + 0]) + bv[8 * i + 0], 0.f), fmaxf(__uint_as_float(v[8 * i + 1]) + bv[8 * i + 1], 0.f));
+        o.y = pack_half2(fmaxf(__uint_as_float(v[8 * i + 2]) + bv[8 * i + 2], 0.f), fmaxf(__uint_as_float(v[8 * i + 3]) + bv[8 * i + 3], 0.f));
+        o.z = pack_half2(fmaxf(__uint_as_float(v[8 * i + 4]) + bv[8 * i + 4], 0.f), fmaxf(__uint_as_float(v[8 * i + 5]) + bv[8 * i + 5], 0.f));
+        o.w = pack_half2(fmaxf(__uint_as_float(v[8 * i + 6]) + bv[8 * i + 6], 0.f), fmaxf(__uint_as_float(v[8 * i + 7]) + bv[8 * i + 7], 0.f));
+        out[i] = o;
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc<32>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // nn.AvgPool2d(2) on NHWC fp16; one thread = 8 channels of one output pixel (16-B vectors).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void acc8(float (&a)[8], const uint4 v) {

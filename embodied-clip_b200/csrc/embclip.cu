@@ -450,6 +450,30 @@ extern "C" int embclip_avgpool2_f16(const void* in, void* out, int B, int H, int
   return launch_avgpool2(in, out, B, H, W, C, (cudaStream_t)stream);
 }
 
+// tensor-core version (hi/lo-split im2col rows); wtc = fp16 [32][128]
+static int launch_stem_conv1_tc(const void* x, int x_u8, const float* norm6, const void* wtc, const float* b, void* y, int B, int R, cudaStream_t st) {
+  if (R % 2) return fail(EMBCLIP_EINVAL, "stem: resolution must be even");
+  StemNorm nm;
+  for (int c = 0; c < 3; ++c) { nm.scale[c] = norm6 ? norm6[c] : 1.f; nm.offset[c] = norm6 ? norm6[3 + c] : 0.f; }
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(cudaFuncSetAttribute(stem_conv1_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemTcSmem));
+    CUDA_TRY(cudaFuncSetAttribute(stem_conv1_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemTcSmem));
+    attr = true;
+  }
+  const long long tiles = ((long long)B * (R / 2) * (R / 2) + 127) / 128;
+  long long grid = (long long)num_sms() * 4;
+  if (grid > tiles) grid = tiles;
+  if (grid <= 0) return 0;
+  if (x_u8)
+    CUDA_TRY(launch_pdl(stem_conv1_tc_kernel<uint8_t>, dim3((unsigned)grid), dim3(128), (size_t)kStemTcSmem, st, reinterpret_cast<const uint8_t*>(x),
+                        reinterpret_cast<const __half*>(wtc), b, reinterpret_cast<__half*>(y), B, R, nm));
+  else
+    CUDA_TRY(launch_pdl(stem_conv1_tc_kernel<float>, dim3((unsigned)grid), dim3(128), (size_t)kStemTcSmem, st, reinterpret_cast<const float*>(x),
+                        reinterpret_cast<const __half*>(wtc), b, reinterpret_cast<__half*>(y), B, R, nm));
+  return 0;
+}
+
 static int launch_stem_conv1(const void* x, int x_u8, const float* norm6, const float* w, const float* b, void* y, int B, int R, int Cout, cudaStream_t st) {
   if (R % 4) return fail(EMBCLIP_EINVAL, "stem: resolution must be a multiple of 4");
   const long long total = (long long)B * (R / 2) * (R / 4);      // one thread per PAIR of output pixels
@@ -515,6 +539,7 @@ struct embclip_rn50 {
   const uint8_t* blob = nullptr;
   int embed = 0, fres = 0, tokens = 0;
   int act_trunk_f32 = -1;
+  int p_stem_wtc = -1;
 };
 
 static int add_act(embclip_rn50* m, const std::string& name, int dtype, int h, int w, int c) {
@@ -591,6 +616,7 @@ extern "C" int embclip_rn50_create(const embclip_rn50_cfg* cfg, embclip_rn50_t* 
     op.cout = width / 2;
     op.wp = add_param(m, "stem.conv1.w", EMBCLIP_DTYPE_F32, {27, width / 2});
     op.bp = add_param(m, "stem.conv1.b", EMBCLIP_DTYPE_F32, {width / 2});
+    m->p_stem_wtc = add_param(m, "stem.conv1.wtc", EMBCLIP_DTYPE_F16, {width / 2, 128});   // hi/lo-split rows for the tensor-core stem
     op.out = add_act(m, "stem.conv1", EMBCLIP_DTYPE_F16, R / 2, R / 2, width / 2);
     m->ops.push_back(op);
   }
@@ -738,9 +764,14 @@ static int run_op(embclip_rn50* m, const Op& op, const std::vector<uint64_t>& of
   auto param_ptr = [&](int id) -> const void* { return id >= 0 ? (const void*)(m->blob + m->params[id].info.offset) : nullptr; };
   const int P = m->fres * m->fres;
   switch (op.kind) {
-    case K_STEM1:
+    case K_STEM1: {
+      static const bool cuda_core = getenv("EMBCLIP_STEM_CUDA_CORE") != nullptr;       // first version, kept for A/B timing
+      if (!cuda_core && op.cout == 32)
+        return launch_stem_conv1_tc(frames.ptr, frames.u8, frames.u8 ? frames.norm : nullptr, param_ptr(m->p_stem_wtc),
+                                    (const float*)param_ptr(op.bp), act_ptr(op.out), B, m->cfg.input_resolution, st);
       return launch_stem_conv1(frames.ptr, frames.u8, frames.u8 ? frames.norm : nullptr, (const float*)param_ptr(op.wp),
                                (const float*)param_ptr(op.bp), act_ptr(op.out), B, m->cfg.input_resolution, op.cout, st);
+    }
     case K_POOL: {
       const Act& a = m->acts[op.in0];
       return launch_avgpool2(act_ptr(op.in0), act_ptr(op.out), B, a.h, a.w, a.c, st);

@@ -67,6 +67,13 @@ def packed_tensors(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     w, b = fold_bn(sd, "conv1", "bn1")
     out["stem.conv1.w"] = w.permute(2, 3, 1, 0).reshape(27, -1).contiguous()         # [(kh,kw,ci), co] fp32
     out["stem.conv1.b"] = b
+    # tensor-core stem: weight rows [w_hi | w_hi | w_lo | 0] against im2col rows [v_hi | v_lo | v_hi | 0] (32-wide slots, 27 used)
+    w27 = out["stem.conv1.w"].t().contiguous()                                        # [co, 27]
+    w_hi = w27.half()
+    w_lo = (w27 - w_hi.float()).half()
+    wtc = torch.zeros(w27.shape[0], 128, dtype=torch.float16)
+    wtc[:, 0:27], wtc[:, 32:59], wtc[:, 64:91] = w_hi, w_hi, w_lo
+    out["stem.conv1.wtc"] = wtc
     for i in (2, 3):
         w, b = fold_bn(sd, f"conv{i}", f"bn{i}")
         out[f"stem.conv{i}.w"] = _kmajor(w).half()

@@ -56,7 +56,7 @@ def test_plan_queries_without_gpu(built_lib):
         names.append(pi.name.decode())
     assert lib.embclip_rn50_blob_bytes(h) >= end
     # 1 stem conv1 + 2 stem convs + 16 blocks x 3 convs, each (w, b); attnpool: pos, q(w,b), kT, v(w,b), c(w,b)
-    assert n == 2 * (3 + 48) + 8
+    assert n == 2 * (3 + 48) + 8 + 1          # + stem.conv1.wtc (tensor-core stem weights)
     assert "layer4.2.conv3.w" in names and "attnpool.kT.w" in names
     # workspace scales linearly with batch (up to 1 KiB alignment per tensor)
     w1, w8 = lib.embclip_rn50_workspace_bytes(h, 1), lib.embclip_rn50_workspace_bytes(h, 8)
