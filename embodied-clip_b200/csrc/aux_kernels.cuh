@@ -445,6 +445,191 @@ attnpool_core_kernel(const __half* __restrict__ qt,   // [B, heads, C]
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same two contractions on the tensor cores (one CTA = 4 images = 128 (image, head) rows):
+//   S[128 x 256]   = QT[128 rows x C] . T[256 token rows x C]^T      K-loop over C in 64-channel TMA stages (both K-major)
+//   P              = softmax over the row's OWN image's L tokens (other images' columns are exactly 0), fp16, K-major smem
+//   XBAR[128 x C]  = P[128 x 256] . T[256 x C]                        per 128-channel chunk; T is the MN-major operand
+// The 4x4 cross-image blocks of S are computed and discarded (free on the tensor pipe).  Tokens are read twice from L2
+// (once per phase), qt once; 192 KB smem (phase-1 stages overlaid with P + the phase-3 token tiles), all 512 TMEM columns.
+// ------------------------------------------------------------------------------------------------
+struct AttnPoolTcParams {
+  int B, heads, L, C;      // heads * 4 == 128, 4 * L <= 256, C % 128 == 0
+  __half* xbar;            // [B * heads][C]
+};
+constexpr int kApStages = 3;
+constexpr int kApStageBytes = 16384 + 32768;
+constexpr int kApSmem = 1024 + 196608 + 128;
+__global__ void __launch_bounds__(128, 1)
+attnpool_tc_kernel(const __grid_constant__ CUtensorMap tmQT, const __grid_constant__ CUtensorMap tmTokK,
+                   const __grid_constant__ CUtensorMap tmTokMN, const AttnPoolTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // phase 1: stages [A 16 KB | B 32 KB] x 3 ; phases 2-3: P 64 KB at +0, token tiles 2 x 64 KB at +64 KB
+  const uint32_t sP = base, sT = base + 65536;
+  const uint32_t bars = base + 196608;
+  const uint32_t bar_full = bars, bar_empty = bars + 24, bar_s = bars + 48, bar_tfull = bars + 56, bar_o = bars + 72, tmem_slot = bars + 88;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tile = blockIdx.x;
+  const int rq0 = tile * 128;                      // first (image, head) row
+  const int rt0 = tile * 4 * p.L;                  // first token row
+  const int nkb = p.C / 64, nchunks = p.C / 128;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQT); tma_prefetch_desc(&tmTokK); tma_prefetch_desc(&tmTokMN);
+    for (int s = 0; s < kApStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_s, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_o + 8 * i, 1); }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  griddep_wait();
+  const uint32_t tS = tmem_base, tO = tmem_base + 256;
+
+  // ---------------- phase 1: scores
+  if (tid == 0) {
+    constexpr uint32_t idesc = make_idesc_f16_f32(128, 256);
+    auto load = [&](int kb) {
+      const int s = kb % kApStages;
+      const uint32_t full = bar_full + 8 * s, a = base + s * kApStageBytes;
+      mbar_arrive_expect_tx(full, kApStageBytes);
+      tma_load_2d(&tmQT, full, a, kb * 64, rq0);
+      tma_load_2d(&tmTokK, full, a + 16384, kb * 64, rt0);
+    };
+    for (int kb = 0; kb < kApStages && kb < nkb; ++kb) load(kb);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kApStages;
+      const uint32_t ph = uint32_t(kb / kApStages) & 1u;
+      mbar_wait(bar_full + 8 * s, ph);
+      tcgen05_fence_after();
+      const uint32_t a = base + s * kApStageBytes;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_f16_ss(tS, make_kmajor_desc<128>(a + 32 * k), make_kmajor_desc<128>(a + 16384 + 32 * k), idesc, (kb | k) != 0);
+      umma_commit(bar_empty + 8 * s);
+      if (kb + kApStages < nkb) {
+        mbar_wait(bar_empty + 8 * s, ph);          // the MMAs reading this stage have retired
+        load(kb + kApStages);
+      }
+    }
+    umma_commit(bar_s);
+  }
+  __syncwarp();
+
+  // ---------------- phase 2: softmax, thread <-> (image, head) row
+  const int r = tid;
+  const int img = r / p.heads;                     // image of this row inside the tile
+  const int j0 = img * p.L, j1 = j0 + p.L;
+  const bool live = rq0 + r < p.B * p.heads;
+  mbar_wait(bar_s, 0);
+  tcgen05_fence_after();
+  const uint32_t trow = tS + (uint32_t(warp * 32) << 16);
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {
+    if (32 * c + 31 < j0 || 32 * c >= j1) continue;
+    uint32_t v[32];
+    tmem_ld_32x32b<32>(trow + uint32_t(32 * c), v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int j = 32 * c + i;
+      if (j >= j0 && j < j1) mx = fmaxf(mx, __uint_as_float(v[i]));
+    }
+  }
+  float sum = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {
+    uint32_t h2[16];
+    if (32 * c + 31 < j0 || 32 * c >= j1) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) h2[i] = 0u;
+    } else {
+      uint32_t v[32];
+      tmem_ld_32x32b<32>(trow + uint32_t(32 * c), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const int j = 32 * c + i;
+        const float a = (j >= j0 && j < j1) ? __expf(__uint_as_float(v[i]) - mx) : 0.f;
+        const float b = (j + 1 >= j0 && j + 1 < j1) ? __expf(__uint_as_float(v[i + 1]) - mx) : 0.f;
+        sum += a + b;
+        h2[i >> 1] = pack_half2(a, b);
+      }
+    }
+    const uint32_t chunk = sP + uint32_t((32 * c) / 64) * 16384u;
+    const int piece0 = ((32 * c) % 64) / 8;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t a = chunk + swizzle_off<128>(uint32_t(r), uint32_t(piece0 + q));
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(h2[4 * q]), "r"(h2[4 * q + 1]), "r"(h2[4 * q + 2]), "r"(h2[4 * q + 3]) : "memory");
+    }
+  }
+  const float inv = sum > 0.f ? 1.f / sum : 0.f;
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();                                 // P complete; phase-1 stages are dead (their MMAs retired before bar_s)
+
+  // ---------------- phase 3: XBAR chunks of 128 channels
+  auto load_t = [&](int c) {
+    const uint32_t bar = bar_tfull + 8 * (c & 1), dst = sT + uint32_t(c & 1) * 65536u;
+    mbar_arrive_expect_tx(bar, 65536);
+    tma_load_2d(&tmTokMN, bar, dst, c * 128, rt0);
+    tma_load_2d(&tmTokMN, bar, dst + 32768, c * 128 + 64, rt0);
+  };
+  if (tid == 0) { load_t(0); if (nchunks > 1) load_t(1); }
+  for (int c = 0; c <= nchunks; ++c) {
+    if (tid == 0 && c < nchunks) {
+      mbar_wait(bar_tfull + 8 * (c & 1), uint32_t(c >> 1) & 1u);
+      tcgen05_fence_after();
+      constexpr uint32_t idesc = make_idesc_f16_f32(128, 128) | (1u << 16);    // B (tokens) is MN-major
+      const uint32_t t = sT + uint32_t(c & 1) * 65536u;
+#pragma unroll
+      for (int ks = 0; ks < 16; ++ks)
+        umma_f16_ss(tO + uint32_t(c & 1) * 128u, make_kmajor_desc<128>(sP + uint32_t(ks >> 2) * 16384u + 32u * uint32_t(ks & 3)),
+                    make_mnmajor_desc<128>(t + uint32_t(ks) * 2048u, 32768u), idesc, ks != 0);
+      umma_commit(bar_o + 8 * (c & 1));
+    }
+    __syncwarp();
+    if (c >= 1) {                                  // epilogue of chunk c-1 while chunk c's MMAs run
+      const int e = c - 1;
+      mbar_wait(bar_o + 8 * (e & 1), uint32_t(e >> 1) & 1u);
+      tcgen05_fence_after();
+      if (tid == 0 && e + 2 < nchunks) load_t(e + 2);          // its token tile is free again
+      __half* orow = p.xbar + (size_t)(rq0 + r) * p.C + (size_t)e * 128;
+#pragma unroll 1
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint32_t v[32];
+        tmem_ld_32x32b<32>(tO + uint32_t(e & 1) * 128u + (uint32_t(warp * 32) << 16) + uint32_t(32 * q4), v);
+        tmem_ld_wait();
+        if (live) {
+          uint4* o4 = reinterpret_cast<uint4*>(orow + 32 * q4);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = pack_half2(__uint_as_float(v[8 * q]) * inv, __uint_as_float(v[8 * q + 1]) * inv);
+            o.y = pack_half2(__uint_as_float(v[8 * q + 2]) * inv, __uint_as_float(v[8 * q + 3]) * inv);
+            o.z = pack_half2(__uint_as_float(v[8 * q + 4]) * inv, __uint_as_float(v[8 * q + 5]) * inv);
+            o.w = pack_half2(__uint_as_float(v[8 * q + 6]) * inv, __uint_as_float(v[8 * q + 7]) * inv);
+            o4[q] = o;
+          }
+        }
+      }
+      tcgen05_fence_before();
+    }
+    __syncthreads();                               // accumulator e drained by every row before chunk e+2's MMAs overwrite it
+  }
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Output heads from the fp32 NHWC trunk result [B, P, C].
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

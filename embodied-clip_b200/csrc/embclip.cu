@@ -806,6 +806,23 @@ static int run_op(embclip_rn50* m, const Op& op, const std::vector<uint64_t>& of
       return 0;
     }
     case K_ATTN_CORE: {
+      static const bool cuda_core = getenv("EMBCLIP_ATTNPOOL_CUDA_CORE") != nullptr;   // first version, kept for A/B timing
+      if (!cuda_core && m->cfg.heads == 32 && 4 * m->tokens <= 256 && m->embed % 128 == 0) {
+        static bool attr_tc = false;
+        if (!attr_tc) {
+          CUDA_TRY(cudaFuncSetAttribute(attnpool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kApSmem));
+          attr_tc = true;
+        }
+        CUtensorMap tq, tk, tmn;
+        int rc;
+        if ((rc = make_map_2d(&tq, act_ptr(op.in0), B * m->cfg.heads, m->embed, m->embed, 64, 128))) return rc;
+        if ((rc = make_map_2d(&tk, act_ptr(op.in1), B * m->tokens, m->embed, m->embed, 64, 256))) return rc;
+        if ((rc = make_map_2d(&tmn, act_ptr(op.in1), B * m->tokens, m->embed, m->embed, 64, 256))) return rc;
+        AttnPoolTcParams ap;
+        ap.B = B; ap.heads = m->cfg.heads; ap.L = m->tokens; ap.C = m->embed; ap.xbar = (__half*)act_ptr(op.out);
+        CUDA_TRY(launch_pdl(attnpool_tc_kernel, dim3((B + 3) / 4), dim3(128), (size_t)kApSmem, st, tq, tk, tmn, ap));
+        return 0;
+      }
       constexpr int HG = 8;
       if (m->cfg.heads % HG) return fail(EMBCLIP_EINVAL, "attention pool: heads must be a multiple of %d", HG);
       const size_t smem = (size_t)HG * m->embed * 2 + HG * 64 * 4;

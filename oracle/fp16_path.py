@@ -63,7 +63,7 @@ def rn50_fp16_path(m: ModifiedResNet, frames_nchw: torch.Tensor, quantize: bool 
             y = F.relu(y)
         return q(y) if round_out else y
 
-    # stem conv1 runs on CUDA cores from the fp32 frames with fp32 weights; only its output is rounded
+    # stem conv1: hi/lo-split fp16 operands on the tensor cores = fp32 inputs x fp32 weights to 2^-22; only its output is rounded
     x = put("stem.conv1", cbr(frames_nchw, m.conv1, m.bn1, round_w=False))
     x = put("stem.conv2", cbr(x, m.conv2, m.bn2))
     # AvgPool2d(2) is fused into conv3's epilogue: the full-resolution map is rounded to fp16, averaged in fp32
@@ -107,8 +107,11 @@ def rn50_fp16_path(m: ModifiedResNet, frames_nchw: torch.Tensor, quantize: bool 
     qv = put2("attnpool.q", q(tok[:, 0] @ q(ap.q_proj.weight * s).t() + ap.q_proj.bias * s), (B, 1, 1, E))
     wk = q(ap.k_proj.weight).view(heads, hd, E)
     qt = put2("attnpool.qk", q(torch.einsum("bhd,hdc->bhc", qv.view(B, heads, hd), wk)), (B, 1, heads, E))
-    p = torch.softmax(torch.einsum("bhc,bjc->bhj", qt, tok), dim=-1)
-    xbar = put2("attnpool.xbar", q(torch.einsum("bhj,bjc->bhc", p, tok)), (B, 1, heads, E))
+    # tensor-core core kernel: unnormalised exp(s - max) is rounded to fp16 (operand of the P.T contraction); the row sum
+    # that normalises the result is taken over the UNROUNDED values
+    sc = torch.einsum("bhc,bjc->bhj", qt, tok)
+    e = torch.exp(sc - sc.amax(dim=-1, keepdim=True))
+    xbar = put2("attnpool.xbar", q(torch.einsum("bhj,bjc->bhc", q(e), tok) / e.sum(dim=-1, keepdim=True)), (B, 1, heads, E))
     wv = q(ap.v_proj.weight).view(heads, hd, E)
     o = put2("attnpool.v", q(torch.einsum("bhc,hdc->bhd", xbar, wv).reshape(B, E) + ap.v_proj.bias), (B, 1, 1, E))
     acts["attnpool"] = o @ q(ap.c_proj.weight).t() + ap.c_proj.bias
