@@ -16,6 +16,7 @@
 #include "conv_gemm.cuh"
 #include "conv3x3_halo.cuh"
 #include "gemm2sm.cuh"
+#include "bneck_tail.cuh"
 
 using namespace embclip;
 
@@ -395,6 +396,65 @@ static int launch_conv3x3_halo(const Conv3Op& op, cudaStream_t st) {
 }
 
 // =============================================================================================
+// bneck_tail launcher: conv3 (+ K-concat downsample | + identity residual) + ReLU, then the next block's conv1
+// =============================================================================================
+struct TailOp {
+  const void* a0 = nullptr;        // y2 [M, 64]
+  const void* a1 = nullptr;        // block input [M, 64] for the K-concatenated downsample conv (or null)
+  const void* w3 = nullptr;        // [256, 64 (+64)]
+  const float* b3 = nullptr;
+  const void* residual = nullptr;  // identity [M, 256] (or null)
+  void* out = nullptr;             // x' [M, 256]
+  const void* w1 = nullptr;        // next conv1 [N1, 256]
+  const float* b1 = nullptr;
+  void* y1 = nullptr;              // [M, N1]
+  long long M = 0;
+  int n1 = 0;
+  int reverse = 0;
+};
+template <int K3C, int N1, bool kRes>
+static int launch_tail_cfg(const TailOp& op, cudaStream_t st) {
+  using Cfg = TailCfg<K3C, N1>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(bneck_tail_kernel<K3C, N1, kRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int M = (int)op.M;
+  CUtensorMap tmA0, tmA1, tmW3, tmW1, tmR, tmC;
+  int rc;
+  if ((rc = make_map_2d(&tmA0, op.a0, M, 64, 64, 64, 128))) return rc;
+  if (K3C == 2) { if ((rc = make_map_2d(&tmA1, op.a1, M, 64, 64, 64, 128))) return rc; }
+  else tmA1 = tmA0;
+  if ((rc = make_map_2d(&tmW3, op.w3, 256, 64 * K3C, 64 * K3C, 64, 256))) return rc;
+  if ((rc = make_map_2d(&tmW1, op.w1, N1, 256, 256, 64, N1))) return rc;
+  if ((rc = make_map_2d(&tmC, op.out, M, 256, 256, 64, 128))) return rc;
+  if (kRes) { if ((rc = make_map_2d(&tmR, op.residual, M, 256, 256, 64, 128))) return rc; }
+  else tmR = tmC;
+  TailParams p;
+  memset(&p, 0, sizeof p);
+  p.num_tiles = (M + 127) / 128;
+  p.M = M;
+  p.reverse = op.reverse;
+  p.bias3 = op.b3; p.bias1 = op.b1;
+  p.y1 = reinterpret_cast<__half*>(op.y1);
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  if (grid <= 0) return 0;
+  CUDA_TRY(launch_pdl(bneck_tail_kernel<K3C, N1, kRes>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, tmA0, tmA1, tmW3, tmW1, tmR, tmC, p));
+  return 0;
+}
+static int launch_bneck_tail(const TailOp& op, cudaStream_t st) {
+  if (op.M <= 0) return 0;
+  if (op.M > 0x7fffffffLL) return fail(EMBCLIP_EINVAL, "bneck_tail: M too large");
+  if (!op.a0 || !op.w3 || !op.b3 || !op.out || !op.w1 || !op.b1 || !op.y1) return fail(EMBCLIP_EINVAL, "bneck_tail: null argument");
+  if ((op.a1 != nullptr) == (op.residual != nullptr)) return fail(EMBCLIP_EINVAL, "bneck_tail: exactly one of downsample source / identity residual");
+  if (op.n1 != 64 && op.n1 != 128) return fail(EMBCLIP_EINVAL, "bneck_tail: next conv1 width must be 64 or 128 (got %d)", op.n1);
+  if (op.a1 && op.n1 != 64) return fail(EMBCLIP_EINVAL, "bneck_tail: the K-concatenated variant is built for a 64-wide next conv1 only");
+  if (op.a1) return launch_tail_cfg<2, 64, false>(op, st);
+  return op.n1 == 64 ? launch_tail_cfg<1, 64, true>(op, st) : launch_tail_cfg<1, 128, true>(op, st);
+}
+
+// =============================================================================================
 // primitive-op entry points
 // =============================================================================================
 extern "C" int embclip_gemm_f16(const void* a0, const void* a1, const void* w, const float* bias, const void* residual,
@@ -433,6 +493,14 @@ extern "C" int embclip_conv3x3_f16(const void* in, const void* w, const float* b
   }
   Conv3Op op{in, w, bias, out, B, H, W, Cin, Cout, relu, pool};
   return launch_conv3x3_halo(op, (cudaStream_t)stream);
+}
+
+extern "C" int embclip_bneck_tail_f16(const void* y2, const void* x0, const void* w3, const float* b3, const void* residual, void* out,
+                                      const void* w1, const float* b1, void* y1, int64_t M, int n1, void* stream) {
+  TailOp op;
+  op.a0 = y2; op.a1 = x0; op.w3 = w3; op.b3 = b3; op.residual = residual; op.out = out;
+  op.w1 = w1; op.b1 = b1; op.y1 = y1; op.M = M; op.n1 = n1;
+  return launch_bneck_tail(op, (cudaStream_t)stream);
 }
 
 static int launch_avgpool2(const void* in, void* out, int B, int H, int W, int C, cudaStream_t st) {
@@ -526,6 +594,8 @@ struct Op {
   int grp_n = 0, grp_a_koff = 0, grp_b_koff = 0, grp_b_nmod = 0;
   int force_bn = 0;
   int reverse = 0;               // tile walk direction (alternates layer to layer: snake order through L2)
+  int fuse_next = -1;            // conv3 only: index of the next block's conv1 op, computed by the same launch (bneck_tail)
+  int fused_away = 0;            // conv1 only: produced by the previous block's bneck_tail launch, not launched itself
 };
 
 }  // namespace
@@ -705,10 +775,26 @@ extern "C" int embclip_rn50_create(const embclip_rn50_cfg* cfg, embclip_rn50_t* 
   }
   // snake order: consecutive tensor-core layers walk their tiles in opposite directions, so each starts on the part
   // of its input that the previous layer wrote last (still resident in the 126 MB L2)
+  // bneck_tail fusion (bneck_tail.cuh): a 64 -> 256 conv3 followed by the next block's 256 -> 64/128 conv1 on the same
+  // pixels is ONE launch; the 256-channel tensor is written once and not re-read by the conv1
+  static const bool tail_fuse = getenv("EMBCLIP_NO_TAILFUSE") == nullptr;
+  if (tail_fuse) {
+    for (size_t i = 0; i + 1 < m->ops.size(); ++i) {
+      Op& c3 = m->ops[i];
+      Op& c1 = m->ops[i + 1];
+      if (c3.kind != K_GEMM || c1.kind != K_GEMM || c3.rows_mode || c1.rows_mode || c3.head || c1.head) continue;
+      if (c3.taps != 1 || c3.c0 != 64 || c3.cout != 256 || !c3.relu || c3.out_f32 || c3.grp_n) continue;
+      if (!((c3.in1 >= 0 && c3.c1 == 64 && c3.res < 0) || (c3.in1 < 0 && c3.res >= 0))) continue;
+      if (c1.taps != 1 || c1.in0 != c3.out || c1.in1 >= 0 || c1.res >= 0 || !c1.relu || c1.out_f32 || c1.grp_n) continue;
+      if (c1.c0 != 256 || (c1.cout != 64 && c1.cout != 128) || (c3.in1 >= 0 && c1.cout != 64)) continue;
+      c3.fuse_next = (int)i + 1;
+      c1.fused_away = 1;
+    }
+  }
   static const bool snake = getenv("EMBCLIP_NO_SNAKE") == nullptr;
   int dir = 0;
   for (Op& op : m->ops)
-    if (op.kind == K_GEMM && op.rows_mode == 0) { op.reverse = snake ? dir : 0; dir ^= 1; }
+    if (op.kind == K_GEMM && op.rows_mode == 0 && !op.fused_away) { op.reverse = snake ? dir : 0; dir ^= 1; }
   *out = m;
   return 0;
 }
@@ -782,6 +868,15 @@ static int run_op(embclip_rn50* m, const Op& op, const std::vector<uint64_t>& of
         Conv3Op c{act_ptr(op.in0), param_ptr(op.wp), (const float*)param_ptr(op.bp), act_ptr(op.out), B, a.h, a.w, op.c0, op.cout, op.relu, op.pool};
         c.reverse = op.reverse;
         return launch_conv3x3_halo(c, st);
+      }
+      if (op.fuse_next >= 0) {
+        const Op& c1 = m->ops[op.fuse_next];
+        TailOp t;
+        t.a0 = act_ptr(op.in0); t.a1 = act_ptr(op.in1); t.w3 = param_ptr(op.wp); t.b3 = (const float*)param_ptr(op.bp);
+        t.residual = act_ptr(op.res); t.out = act_ptr(op.out);
+        t.w1 = param_ptr(c1.wp); t.b1 = (const float*)param_ptr(c1.bp); t.y1 = act_ptr(c1.out);
+        t.M = (long long)B * a.h * a.w; t.n1 = c1.cout; t.reverse = op.reverse;
+        return launch_bneck_tail(t, st);
       }
       GemmOp g;
       g.a0 = act_ptr(op.in0);
@@ -865,6 +960,7 @@ static int forward_impl(embclip_rn50* m, const FramesIn& frames, int B, float* o
   int nrun = 0;
   for (const Op& op : m->ops) {
     if (op.head && !(op.head & want)) continue;
+    if (op.fused_away) continue;
     if (op_ms) {
       cudaEvent_t e;
       CUDA_TRY(cudaEventCreate(&e));
@@ -923,6 +1019,6 @@ extern "C" int embclip_rn50_launches_per_forward(embclip_rn50_t h, int want_trun
   const int want = (want_trunk ? H_NCHW : 0) | (want_avgpool ? H_AVG : 0) | (want_attnpool ? H_ATTN : 0);
   int n = 0;
   for (const Op& op : h->ops)
-    if (!op.head || (op.head & want)) ++n;
+    if ((!op.head || (op.head & want)) && !op.fused_away) ++n;
   return n;
 }

@@ -125,6 +125,13 @@ int embclip_gemm_grouped_f16(const void* a, int lda, const void* w, int ldw, int
  * BatchNorm + ReLU (+ AvgPool2d) of clip/model.py Bottleneck / ModifiedResNet stem. */
 int embclip_conv3x3_f16(const void* in, const void* w, const float* bias, void* out, int B, int H, int W,
                         int Cin, int Cout, int relu, int pool, void* stream);
+/* Bottleneck tail + next head in one pass (clip/model.py Bottleneck.forward [UPSTREAM]: out = relu(bn3(conv3(y2)) + identity),
+ * then the next block's relu(bn1(conv1(out)))):
+ *   out[M,256] = relu([y2 | x0] . w3^T + b3 (+ residual));   y1[M,n1] = relu(out . w1^T + b1)
+ * y2 fp16 [M,64]; exactly one of x0 (fp16 [M,64]: downsample conv K-concatenated, w3 = [256,128]) and residual (fp16 [M,256],
+ * w3 = [256,64]) is non-null; w1 fp16 [n1,256], n1 = 64 or 128; biases fp32 (BN folded). */
+int embclip_bneck_tail_f16(const void* y2, const void* x0, const void* w3, const float* b3, const void* residual, void* out,
+                           const void* w1, const float* b1, void* y1, int64_t M, int n1, void* stream);
 /* 2x2 average pool, NHWC fp16 (nn.AvgPool2d(2) of clip/model.py). */
 int embclip_avgpool2_f16(const void* in, void* out, int B, int H, int W, int C, void* stream);
 /* Stem conv1: fp32 NHWC [B,R,R,3] -> fp16 NHWC [B,R/2,R/2,Cout]; w fp32 [27, Cout] (kh,kw,cin major), bias fp32. */

@@ -214,3 +214,54 @@ def test_error_paths(lib):
     rc = lib.embclip_gemm_f16(_ptr(a), None, _ptr(a), None, None, _ptr(a), 4, 48, 48, 0, 0, 0, _stream())
     assert rc == -1 and b"multiples of 32" in lib.embclip_last_error()
     assert lib.embclip_gemm_f16(None, None, None, None, None, None, 4, 64, 64, 0, 0, 0, _stream()) == -1
+
+
+def _tail_case(lib, M, n1, down, seed=0):
+    """bneck_tail: out = relu([y2 | x0] W3^T + b3 (+ res)) rounded to fp16; y1 = relu(out W1^T + b1) from that fp16 tile."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    y2 = rn(M, 64).relu().half()
+    x0 = rn(M, 64).relu().half() if down else None
+    k3 = 128 if down else 64
+    w3 = (rn(256, k3) * k3 ** -0.5).half()
+    b3 = rn(256)
+    res = None if down else rn(M, 256).relu().half()
+    w1 = (rn(n1, 256) * 256 ** -0.5).half()
+    b1 = rn(n1)
+    out = torch.full((M, 256), float("nan"), device="cuda", dtype=torch.float16)
+    y1 = torch.full((M, n1), float("nan"), device="cuda", dtype=torch.float16)
+    _check(lib, lib.embclip_bneck_tail_f16(_ptr(y2), _ptr(x0), _ptr(w3), _ptr(b3), _ptr(res), _ptr(out), _ptr(w1), _ptr(b1),
+                                           _ptr(y1), M, n1, _stream()))
+    torch.cuda.synchronize()
+    a = torch.cat([y2.float(), x0.float()], 1) if down else y2.float()
+    ref_out = a @ w3.float().t() + b3
+    if res is not None:
+        ref_out = ref_out + res.float()
+    ref_out = ref_out.relu()
+    _close(out, ref_out, f"bneck_tail out M{M} n1 {n1} down{down}")
+    ref_y1 = (out.float() @ w1.float().t() + b1).relu()          # fed with the kernel's own fp16 x' (its rounding point)
+    _close(y1, ref_y1, f"bneck_tail y1 M{M} n1 {n1} down{down}")
+
+
+@pytest.mark.parametrize("M,n1,down", [
+    (128, 64, False),            # one tile
+    (128, 64, True),             # K-concatenated downsample conv (layer1.0)
+    (128, 128, False),           # layer1.2 -> layer2.0.conv1
+    (3136, 64, False),           # one frame: partial last tile (3136 = 24.5 x 128)
+    (3136 * 5, 64, True),
+    (128 * 148 * 3 + 77, 128, False),   # three tiles per CTA + ragged tail: quarter-buffer recycling, accumulator parity
+    (128 * 148 * 4, 64, False),
+    (50, 64, True),              # fewer rows than one tile
+])
+def test_bneck_tail(lib, M, n1, down):
+    _tail_case(lib, M, n1, down, seed=M % 97)
+
+
+def test_bneck_tail_rejects_bad_arguments(lib):
+    z = torch.zeros(128, 256, device="cuda", dtype=torch.float16)
+    b = torch.zeros(256, device="cuda")
+    args = lambda x0, res, n1: (_ptr(z), x0, _ptr(z), _ptr(b), res, _ptr(z), _ptr(z), _ptr(b), _ptr(z), 128, n1, _stream())
+    assert lib.embclip_bneck_tail_f16(*args(None, None, 64)) != 0            # neither downsample source nor residual
+    assert lib.embclip_bneck_tail_f16(*args(_ptr(z), _ptr(z), 64)) != 0      # both
+    assert lib.embclip_bneck_tail_f16(*args(None, _ptr(z), 96)) != 0         # unsupported conv1 width
+    assert b"bneck_tail" in lib.embclip_last_error()
