@@ -595,6 +595,7 @@ struct Op {
   int force_bn = 0;
   int reverse = 0;               // tile walk direction (alternates layer to layer: snake order through L2)
   int fuse_next = -1;            // conv3 only: index of the next block's conv1 op, computed by the same launch (bneck_tail)
+  int side = 0;                  // independent of the ops that follow it: launched on the handle's side stream (fork / join)
   int fused_away = 0;            // conv1 only: produced by the previous block's bneck_tail launch, not launched itself
 };
 
@@ -610,6 +611,15 @@ struct embclip_rn50 {
   int embed = 0, fres = 0, tokens = 0;
   int act_trunk_f32 = -1;
   int p_stem_wtc = -1;
+  // fork / join plumbing for ops marked `side` (identity-branch pools, layout heads): they overlap the tensor-bound
+  // kernels that do not depend on them.  Created lazily on the device of the first forward.
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  ~embclip_rn50() {
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (side_stream) cudaStreamDestroy(side_stream);
+  }
 };
 
 static int add_act(embclip_rn50* m, const std::string& name, int dtype, int h, int w, int c) {
@@ -656,6 +666,7 @@ static int add_pool(embclip_rn50* m, const std::string& name, int in0) {
   op.kind = K_POOL;
   op.name = name;
   op.in0 = in0;
+  op.side = 1;
   op.out = add_act(m, name, EMBCLIP_DTYPE_F16, a.h / 2, a.w / 2, a.c);
   m->ops.push_back(op);
   return op.out;
@@ -707,10 +718,10 @@ extern "C" int embclip_rn50_create(const embclip_rn50_cfg* cfg, embclip_rn50_t* 
       snprintf(pfx, sizeof pfx, "layer%d.%d", li + 1, bi);
       const std::string P(pfx);
       const int x = t;
+      int xp = x;
+      if (stride == 2) xp = add_pool(m, P + ".xpool", x);   // identity-branch AvgPool2d: needs only x, so it is issued first (side stream)
       int a = add_conv(m, P + ".conv1", x, -1, -1, 1, planes, 1);
       int b = add_conv(m, P + ".conv2", a, -1, -1, 9, planes, 1, 0, /*pool=*/stride == 2);   // avgpool(stride) fused
-      int xp = x;
-      if (stride == 2) xp = add_pool(m, P + ".xpool", x);
       // conv3 (+ downsample conv fused along K when the block has one, else identity residual)
       if (down) t = add_conv(m, P + ".conv3", b, xp, -1, 1, planes * 4, 1, last ? 1 : 0);
       else      t = add_conv(m, P + ".conv3", b, -1, x, 1, planes * 4, 1, last ? 1 : 0);
@@ -723,10 +734,10 @@ extern "C" int embclip_rn50_create(const embclip_rn50_cfg* cfg, embclip_rn50_t* 
   // ---- heads
   {
     Op op;
-    op.kind = K_NCHW; op.name = "head.trunk_nchw"; op.head = H_NCHW; op.in0 = t; op.out = -2;
+    op.kind = K_NCHW; op.name = "head.trunk_nchw"; op.head = H_NCHW; op.in0 = t; op.out = -2; op.side = 1;
     m->ops.push_back(op);
     Op op2;
-    op2.kind = K_AVGHEAD; op2.name = "head.avgpool"; op2.head = H_AVG; op2.in0 = t; op2.out = -3;
+    op2.kind = K_AVGHEAD; op2.name = "head.avgpool"; op2.head = H_AVG; op2.in0 = t; op2.out = -3; op2.side = 1;
     m->ops.push_back(op2);
   }
   {
@@ -781,13 +792,15 @@ extern "C" int embclip_rn50_create(const embclip_rn50_cfg* cfg, embclip_rn50_t* 
   if (tail_fuse) {
     for (size_t i = 0; i + 1 < m->ops.size(); ++i) {
       Op& c3 = m->ops[i];
-      Op& c1 = m->ops[i + 1];
+      size_t j = i + 1;
+      if (m->ops[j].kind == K_POOL && j + 1 < m->ops.size()) ++j;     // the next block's identity pool sits between them
+      Op& c1 = m->ops[j];
       if (c3.kind != K_GEMM || c1.kind != K_GEMM || c3.rows_mode || c1.rows_mode || c3.head || c1.head) continue;
       if (c3.taps != 1 || c3.c0 != 64 || c3.cout != 256 || !c3.relu || c3.out_f32 || c3.grp_n) continue;
       if (!((c3.in1 >= 0 && c3.c1 == 64 && c3.res < 0) || (c3.in1 < 0 && c3.res >= 0))) continue;
       if (c1.taps != 1 || c1.in0 != c3.out || c1.in1 >= 0 || c1.res >= 0 || !c1.relu || c1.out_f32 || c1.grp_n) continue;
       if (c1.c0 != 256 || (c1.cout != 64 && c1.cout != 128) || (c3.in1 >= 0 && c1.cout != 64)) continue;
-      c3.fuse_next = (int)i + 1;
+      c3.fuse_next = (int)j;
       c1.fused_away = 1;
     }
   }
@@ -958,9 +971,42 @@ static int forward_impl(embclip_rn50* m, const FramesIn& frames, int B, float* o
   const int want = (o_nchw ? H_NCHW : 0) | (o_avg ? H_AVG : 0) | (o_attn ? H_ATTN : 0);
   std::vector<cudaEvent_t> ev;
   int nrun = 0;
+  // side-stream ops (not when profiling per op: the events would time an empty main stream)
+  static const bool side_ok = getenv("EMBCLIP_NO_SIDE") == nullptr;
+  const bool use_side = side_ok && !op_ms;
+  if (use_side && !m->side_stream) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+  }
+  bool forked = false;                     // side stream holds work the main stream has not joined yet
+  std::vector<int> side_outs;              // acts produced by that work
+  auto join = [&]() -> int {
+    CUDA_TRY(cudaEventRecord(m->ev_join, m->side_stream));
+    CUDA_TRY(cudaStreamWaitEvent(st, m->ev_join, 0));
+    forked = false;
+    side_outs.clear();
+    return 0;
+  };
   for (const Op& op : m->ops) {
     if (op.head && !(op.head & want)) continue;
     if (op.fused_away) continue;
+    if (use_side && op.side) {
+      // everything enqueued on `st` so far (in particular this op's input) precedes the side work
+      CUDA_TRY(cudaEventRecord(m->ev_fork, st));
+      CUDA_TRY(cudaStreamWaitEvent(m->side_stream, m->ev_fork, 0));
+      const int rc = run_op(m, op, offs, frames, B, o_nchw, o_avg, o_attn, reinterpret_cast<uint8_t*>(ws), m->side_stream);
+      if (rc) return rc;
+      forked = true;
+      if (op.out >= 0) side_outs.push_back(op.out);
+      ++nrun;
+      continue;
+    }
+    if (forked) {
+      bool dep = false;
+      for (int id : side_outs) dep = dep || id == op.in0 || id == op.in1 || id == op.res;
+      if (dep) { const int rc = join(); if (rc) return rc; }
+    }
     if (op_ms) {
       cudaEvent_t e;
       CUDA_TRY(cudaEventCreate(&e));
@@ -972,6 +1018,7 @@ static int forward_impl(embclip_rn50* m, const FramesIn& frames, int B, float* o
     if (rc) return rc;
     ++nrun;
   }
+  if (forked) { const int rc = join(); if (rc) return rc; }    // caller's stream order covers the side work
   if (op_ms) {
     cudaEvent_t e;
     CUDA_TRY(cudaEventCreate(&e));
