@@ -467,7 +467,7 @@ def run_ours(args, rank, local_rank, world):
                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_u8_ms / K, "input": "uint8 NHWC raw RGB, normalised in the stem kernel"},
         "gpu_launches": enc.launches_per_forward(HEADS) * K,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "tcgen05 conv kernels: conv_gemm + gemm2sm + conv3x3_halo (all %d launches of a step)" % n_gemm,
+        "roofline": {"bound": "tensor", "kernel": "tcgen05 conv kernels: conv_gemm + gemm2sm + conv3x3_halo + bneck_tail (all %d launches of a step)" % n_gemm,
                      "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
                      "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_step": int((154.1 + 47.2 + 29.6 + 105.9) * 1e6),

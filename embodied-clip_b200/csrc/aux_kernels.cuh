@@ -129,6 +129,7 @@ stem_conv1_tc_kernel(const TIn* __restrict__ x, const __half* __restrict__ wtc, 
   uint8_t* const gen = smem_raw + (base - smem_u32(smem_raw));
   const int tid = threadIdx.x, warp = tid >> 5;
   constexpr bool kRaw = sizeof(TIn) == 1;
+  const bool vec4 = !kRaw && (R % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0);
 
   // weights [32][128] fp16 (row n: k-block 0 = cols 0..63, k-block 1 = cols 64..127) -> swizzled K-major tiles
   for (int i = tid; i < 32 * 16; i += 128) {
@@ -163,6 +164,32 @@ stem_conv1_tc_kernel(const TIn* __restrict__ x, const __half* __restrict__ wtc, 
     const int oh = int((pix / Ro) % Ro);
     const int b = int(pix / ((long long)Ro * Ro));
     const TIn* xb = x + (size_t)b * R * R * 3;
+    if constexpr (!kRaw) {
+      if (vec4) {
+        // fp32 frames: the 9 values of a kernel row are 36 contiguous bytes starting 12 B past a 24-B pixel-pair boundary;
+        // three aligned 16-B loads cover them (window starts 1 float early for even ow, 3 floats early for odd ow)
+        const int odd = ow & 1;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const int ih = 2 * oh - 1 + kh;
+          const bool rok = ih >= 0 && ih < R;
+          float e[12];
+          if (rok) {
+            const float4* rp = reinterpret_cast<const float4*>(xb + (size_t)ih * R * 3 + 6 * ow - (odd ? 6 : 4));
+            const float4 a = ow > 0 ? __ldg(rp) : make_float4(0.f, 0.f, 0.f, 0.f);      // column -1 is the zero pad
+            const float4 b4 = __ldg(rp + 1), c4 = __ldg(rp + 2);
+            e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b4.x; e[5] = b4.y; e[6] = b4.z; e[7] = b4.w;
+            e[8] = c4.x; e[9] = c4.y; e[10] = c4.z; e[11] = c4.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) e[i] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 9; ++j) v[kh * 9 + j] = odd ? e[3 + j] : e[1 + j];
+        }
+        return;
+      }
+    }
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int ih = 2 * oh - 1 + kh;

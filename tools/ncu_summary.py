@@ -51,5 +51,50 @@ def full(src, dst):
     print(open(dst).read())
 
 
+def traffic(src, dst):
+    """Launch list with per-launch duration and DRAM bytes (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,
+    dram__bytes_write.sum): writes the text table `dst` and, next to it, <dst minus _launches.txt>_traffic.json (what
+    bench.py reports as roofline.traffic)."""
+    import json
+    rows = [r for r in csv.reader(open(src)) if len(r) > 10]
+    hdr = rows[0]
+    iid, ik, im, iu, iv = (hdr.index(k) for k in ("ID", "Kernel Name", "Metric Name", "Metric Unit", "Metric Value"))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "usecond": 1.0, "nsecond": 1e-3, "msecond": 1e3}
+    per = collections.OrderedDict()
+    for r in rows[1:]:
+        try:
+            v = float(r[iv].replace(",", "")) * scale.get(r[iu], 1.0)
+        except ValueError:
+            continue
+        d = per.setdefault(r[iid], {"k": r[ik].split("(")[0].replace("void ", "").replace("embclip::", "")[:64]})
+        d[r[im]] = v
+    tc = ("conv_gemm", "gemm2sm", "conv3x3_halo", "bneck_tail")
+    agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+    for d in per.values():
+        a = agg[d["k"]]
+        a[0] += 1
+        a[1] += d.get("gpu__time_duration.sum", 0.0)
+        a[2] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
+    tot_us = sum(a[1] for a in agg.values())
+    tot_b = sum(a[2] for a in agg.values())
+    with open(dst, "w") as f:
+        f.write(f"# {src}: one encoder step (B=256, all three heads): ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none\n")
+        f.write("# (cold-cache, serialised: compare SHARES; dram = read + write bytes summed over the kernel's launches)\n")
+        f.write(f"# {'kernel':62s} launches  total_us  share   dram_MB\n")
+        for k, (n, us, b) in sorted(agg.items(), key=lambda x: -x[1][1]):
+            f.write(f"{k:64s} {n:6d} {us:9.1f} {us / tot_us * 100:6.1f}% {b / 1e6:9.1f}\n")
+        f.write(f"# total {tot_us:.1f} us, {tot_b / 1e9:.2f} GB DRAM traffic per step\n# per launch, in order:\n")
+        for i, d in enumerate(per.values()):
+            f.write(f"{i:3d} {d['k']:64s} {d.get('gpu__time_duration.sum', 0):8.1f} us  rd {d.get('dram__bytes_read.sum', 0) / 1e6:8.1f} MB  wr {d.get('dram__bytes_write.sum', 0) / 1e6:8.1f} MB\n")
+    sel = [d for d in per.values() if any(t in d["k"] for t in tc)]
+    out = {"source": f"{dst} (ncu dram__bytes_read.sum + dram__bytes_write.sum, one B=256 step)",
+           "tensor_core_conv_kernels": {"launches": len(sel),
+                                        "dram_bytes_per_step": sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in sel),
+                                        "time_us_cold": sum(d.get("gpu__time_duration.sum", 0) for d in sel)},
+           "all_kernels": {"launches": len(per), "dram_bytes_per_step": tot_b}}
+    json.dump(out, open(dst.replace("_launches.txt", "_traffic.json"), "w"), indent=0)
+    print(open(dst).read())
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
