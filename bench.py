@@ -213,7 +213,9 @@ def run_ppo_block(enc, dev, rank, world, rollouts, max_over_ranks, barrier, T=12
         "value": frames_per_step / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms, "rollouts_timed": rollouts,
         "collect_ms": collect_ms, "update_ms": update_ms, "scaling": "weak",
         "config": {"workload": "objectnav_ppo_step", "steps": T, "samplers_per_gpu": N, "update_repeats": 4, "num_mini_batch": 1,
-                   "global_rows": grows, "collective": "1 flat fp32 gradient all-reduce (13.9 MB) per update pass" if world > 1 else "none (1 GPU)"},
+                   "global_rows": grows,
+                   "rollout_storage": "fp16 pixel rows on device (encode_rows -> act -> PackedFeatures); the AllenAct fp32 NCHW flow is SyntheticPPOStep(packed_rollout=False)",
+                   "collective": "1 flat fp32 gradient all-reduce (13.9 MB) per update pass" if world > 1 else "none (1 GPU)"},
         "e2e": {"value": frames_per_step / (e2e_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": T * host.numel(), "d2h_bytes_per_step": 5 * 4, "input": "uint8 NHWC raw RGB",
                 "api": "ClipRN50Encoder.forward(uint8) + ResnetTensorNavActorCritic act + PPOTrainer.update, frames from pinned host memory"},

@@ -57,6 +57,7 @@ SIGNATURES = {
     "embclip_rn50_act_info": (_I, [_VP, _I, _I, C.POINTER(ActInfo)]),
     "embclip_rn50_profile": (_I, [_VP, _FP, _I, _FP, _FP, _FP, _VP, _U64, _VP, _VP, _VP, _I]),
     "embclip_rn50_launches_per_forward": (_I, [_VP, _I, _I, _I]),
+    "embclip_rn50_export_rows_f16": (_I, [_VP, _I, _VP, _U64, _VP, _VP]),
     "embclip_gemm_f16": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "embclip_gemm_grouped_f16": (_I, [_VP, _I, _VP, _I, _I, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "embclip_conv3x3_f16": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
@@ -86,6 +87,7 @@ SIGNATURES = {
     "embclip_ac_act_info": (_I, [_VP, _I, _I, _I, C.POINTER(ActInfo)]),
     "embclip_ac_pack_features": (_I, [_VP, _FP, _LL, _VP, _VP]),
     "embclip_ac_forward": (_I, [_VP, _FP, _VP, _VP, _FP, _FP, _I, _I, _FP, _FP, _FP, _VP, _U64, _I, _VP]),
+    "embclip_ac_act": (_I, [_VP, _FP, _U64, _VP, _VP, _FP, _FP, _I, _FP, _VP, _FP, _FP, _FP, _FP, _VP, _U64, _VP]),
     "embclip_ac_ppo_loss": (_I, [_VP, _FP, _I, _I, _VP, _FP, _FP, _FP, _FP, _F, _F, _F, _F, _FP, _FP, _FP, _VP, _U64, _VP]),
     "embclip_ac_backward": (_I, [_VP, _FP, _VP, _VP, _FP, _FP, _I, _I, _FP, _FP, _FP, _FP, _VP, _U64, _VP]),
     "embclip_gae": (_I, [_FP, _FP, _FP, _I, _I, _F, _F, _FP, _FP, _FP, _F, _VP]),

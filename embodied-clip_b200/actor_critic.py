@@ -252,7 +252,9 @@ class ResnetTensorNavActorCritic(nn.Module):
         need = self._plan.workspace_bytes(T, N)
         if self._ws is None or self._ws.numel() < need or self._ws.device != self.flat_params.device:
             self._ws = None
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.flat_params.device)
+            raw = torch.empty(need + 1024, dtype=torch.uint8, device=self.flat_params.device)   # small blocks are only 512-B aligned
+            off = (-raw.data_ptr()) % 1024
+            self._ws = raw[off:off + need]
         return self._ws
 
     def activations(self, T: int, N: int) -> Dict[str, torch.Tensor]:
@@ -280,6 +282,57 @@ class ResnetTensorNavActorCritic(nn.Module):
         with torch.cuda.device(x.device):
             _lib.check(self._plan.lib.embclip_ac_pack_features(self._plan._h, x.data_ptr(), T * N, out.data_ptr(), _stream(x.device)))
         return PackedFeatures(out, T, N)
+
+    # ------------------------------------------------------------------ rollout step
+    def params_version(self) -> int:
+        """A number that changes whenever the parameter VALUES may have changed: torch's in-place counter of the flat tensor
+        (optimizers, load_state_dict, .data writes through views) plus ``_params_epoch``, which ``PPOTrainer`` bumps after its
+        raw-pointer Adam step.  ``act`` passes it to the library so the fp16 weight layouts are rebuilt once per update, not
+        once per rollout step."""
+        key = (self.flat_params._version, self.flat_params.data_ptr(), getattr(self, "_params_epoch", 0))
+        if key != getattr(self, "_ver_key", None):
+            self._ver_key = key
+            self._ver_id = getattr(self, "_ver_id", 0) + 1
+        return self._ver_id
+
+    def mark_params_changed(self) -> None:
+        self._params_epoch = getattr(self, "_params_epoch", 0) + 1
+
+    @torch.no_grad()
+    def act(self, feats_rows: torch.Tensor, goals: torch.Tensor, masks: torch.Tensor, memory: torch.Tensor, uniforms: torch.Tensor,
+            actions: Optional[torch.Tensor] = None, action_log_probs: Optional[torch.Tensor] = None,
+            values: Optional[torch.Tensor] = None, memory_out: Optional[torch.Tensor] = None):
+        """One rollout step in one library call (OnPolicyRLEngine.act [UPSTREAM]: forward with steps = 1, then
+        ``distributions.sample()`` and ``log_prob``): feats_rows fp16 [N*P, C] (``ClipRN50Encoder.encode_rows`` /
+        ``pack_features``), goals [N], masks [N] (0 = episode start), memory fp32 [N, H], uniforms fp32 [N] in [0, 1)
+        -> (actions int64 [N], log-probs [N], values [N], new memory [N, H], logits [N, A]).  No autograd."""
+        dev = self.flat_params.device
+        N, H, A = memory.reshape(-1, self.hidden_size).shape[0], self.hidden_size, self._plan.cfg["num_actions"]
+        C_, Hh, Ww = self.resnet_tensor_shape
+        if feats_rows.dtype != torch.float16 or feats_rows.numel() != N * Hh * Ww * C_ or not feats_rows.is_contiguous():
+            raise ValueError(f"feats_rows must be contiguous fp16 [{N * Hh * Ww}, {C_}], got {feats_rows.dtype} {tuple(feats_rows.shape)}")
+        for name, t in (("feats_rows", feats_rows), ("goals", goals), ("masks", masks), ("memory", memory), ("uniforms", uniforms)):
+            if t.device != dev:
+                raise ValueError(f"{name} on {t.device}, model on {dev}")
+        g = goals.reshape(N).to(torch.int64).contiguous()
+        m = _f32c(masks.reshape(N))
+        h0 = _f32c(memory.reshape(N, H))
+        u = _f32c(uniforms.reshape(N))
+        mk = lambda t, shape, dt: t if t is not None else torch.empty(*shape, dtype=dt, device=dev)
+        actions, action_log_probs = mk(actions, (N,), torch.int64), mk(action_log_probs, (N,), torch.float32)
+        values, memory_out = mk(values, (N,), torch.float32), mk(memory_out, (N, H), torch.float32)
+        for name, t, dt, n in (("actions", actions, torch.int64, N), ("action_log_probs", action_log_probs, torch.float32, N),
+                               ("values", values, torch.float32, N), ("memory_out", memory_out, torch.float32, N * H)):
+            if t.dtype != dt or t.numel() != n or not t.is_contiguous() or t.device != dev:
+                raise ValueError(f"{name} must be a contiguous {dt} tensor of {n} elements on {dev}")
+        logits = torch.empty(N, A, dtype=torch.float32, device=dev)
+        ws = self._workspace(1, N)
+        with torch.cuda.device(dev):
+            _lib.check(self._plan.lib.embclip_ac_act(self._plan._h, self.flat_params.data_ptr(), self.params_version(), feats_rows.data_ptr(),
+                                                     g.data_ptr(), m.data_ptr(), h0.data_ptr(), N, u.data_ptr(), actions.data_ptr(),
+                                                     action_log_probs.data_ptr(), values.data_ptr(), memory_out.data_ptr(),
+                                                     logits.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)))
+        return actions, action_log_probs, values, memory_out, logits
 
     def forward_tensors(self, feats, goals: torch.Tensor, memory: torch.Tensor, masks: torch.Tensor):
         """-> (logits [T,N,A], values [T,N], h_last [N,H]); differentiable w.r.t. the parameters."""
@@ -402,6 +455,7 @@ class PPOTrainer:
                 _lib.check(lib.embclip_adam_clip_step(P.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(),
                                                       self.exp_avg_sq.data_ptr(), P.numel(), self.sumsq.data_ptr(), self.max_grad_norm,
                                                       self.lr, self.betas[0], self.betas[1], self.eps, self.step_count, st))
+                mdl.mark_params_changed()                              # raw-pointer update: torch's version counter does not see it
         s = self.loss_sums / rows
         return {"action": s[0], "value": s[1], "entropy": -s[2],
                 "total": s[0] + self.value_loss_coef * s[1] - self.entropy_coef * s[2], "grad_norm": self.sumsq.sqrt()[0]}

@@ -409,4 +409,32 @@ adam_clip_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// CategoricalDistr(logits).sample() + log_prob(sample) for one rollout step (allenact distributions.py [UPSTREAM]): one thread
+// per sampler, inverse CDF on softmax(logits) with a caller-supplied uniform u in [0, 1).  Replaces torch's
+// softmax -> multinomial -> log_softmax -> gather chain (8 launches) of the rollout loop.
+// ------------------------------------------------------------------------------------------------
+__global__ void ac_sample_kernel(const float* __restrict__ logits, const float* __restrict__ uniforms, long long* __restrict__ actions,
+                                 float* __restrict__ log_probs, int N, int A) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* lg = logits + (size_t)n * A;
+  float mx = -INFINITY;
+  for (int j = 0; j < A; ++j) mx = fmaxf(mx, lg[j]);
+  float sum = 0.f;
+  for (int j = 0; j < A; ++j) sum += __expf(lg[j] - mx);
+  const float target = uniforms[n] * sum;
+  float cdf = 0.f;
+  int a = -1, last = 0;
+  for (int j = 0; j < A; ++j) {
+    const float e = __expf(lg[j] - mx);
+    if (e > 0.f) last = j;
+    cdf += e;
+    if (a < 0 && cdf > target) a = j;
+  }
+  if (a < 0) a = last;                                    // u * sum rounded up to the total: the last action with mass
+  actions[n] = a;
+  log_probs[n] = lg[a] - mx - logf(sum);
+}
+
 }  // namespace embclip

@@ -200,6 +200,12 @@ struct embclip_ac {
   embclip_ac_cfg cfg;
   embclip_param_info params[P_COUNT];
   uint64_t param_floats = 0;
+  // fp16 weight layouts left in a workspace by the last forward: (params version, params, workspace, T, N).  embclip_ac_act
+  // skips re-packing when its key equals this one; every other entry point that touches a workspace overwrites the key.
+  uint64_t packed_version = 0;
+  const void* packed_params = nullptr;
+  const void* packed_ws = nullptr;
+  int packed_T = 0, packed_N = 0;
 };
 
 static void ac_add_param(embclip_ac* m, int id, const char* name, std::initializer_list<int64_t> shape) {
@@ -382,9 +388,11 @@ extern "C" int embclip_ac_pack_features(embclip_ac_t h, const float* feats_nchw,
   return 0;
 }
 
-extern "C" int embclip_ac_forward(embclip_ac_t h, const float* params, const void* feats_f16, const long long* goals,
-                                  const float* masks, const float* h0, int T, int N, float* logits, float* values, float* h_last,
-                                  void* workspace, uint64_t workspace_bytes, int save_for_backward, void* stream) {
+// params_version != 0: the caller vouches that equal versions mean equal parameter values, so the forward-only fp16 layouts
+// already sitting in this workspace (same block shape) are reused instead of re-packed (rollout steps between two updates).
+static int ac_forward_impl(embclip_ac_t h, const float* params, uint64_t params_version, const void* feats_f16, const long long* goals,
+                           const float* masks, const float* h0, int T, int N, float* logits, float* values, float* h_last,
+                           void* workspace, uint64_t workspace_bytes, int save_for_backward, void* stream) {
   int rc;
   if ((rc = check_block(h, T, N, workspace, workspace_bytes))) return rc;
   if (!params || !feats_f16 || !goals || !masks || !h0 || !logits || !values) return fail(EMBCLIP_EINVAL, "ac_forward: null pointer");
@@ -395,12 +403,18 @@ extern "C" int embclip_ac_forward(embclip_ac_t h, const float* params, const voi
   const int F = T * N, Pp = c.feat_pixels, M = F * Pp, H = c.hidden, I = c.combine_out * Pp;
   const int KC = c.compress_out + c.goal_dims;
 
+  const bool packed = params_version != 0 && !save_for_backward && h->packed_version == params_version && h->packed_params == params &&
+                      h->packed_ws == workspace && h->packed_T == T && h->packed_N == N;
+  h->packed_version = save_for_backward ? 0 : params_version;     // (a training forward is followed by a backward that reuses the space)
+  h->packed_params = params; h->packed_ws = workspace; h->packed_T = T; h->packed_N = N;
   // fp16 GEMM layouts of the current fp32 master weights
+  if (!packed) {
   if ((rc = pack_w(P(h, params, P_C1W), w.W1, c.compress_hidden, c.feat_channels, 0, 0, 0, st))) return rc;
   if ((rc = pack_w(P(h, params, P_C2W), w.W2, c.compress_out, c.compress_hidden, 0, 0, 0, st))) return rc;
   if ((rc = pack_w(P(h, params, P_M1W), w.W3, c.combine_hidden, KC, 0, 0, 0, st))) return rc;
   if ((rc = pack_w(P(h, params, P_M2W), w.W4, c.combine_out, c.combine_hidden, 0, 0, 0, st))) return rc;
   if ((rc = pack_w(P(h, params, P_WIH), w.Wih, 3 * H, I, 2, Pp, c.combine_out, st))) return rc;
+  }
   if (save_for_backward) {
     if ((rc = pack_w(P(h, params, P_C2W), w.W2T, c.compress_out, c.compress_hidden, 1, 0, 0, st))) return rc;
     if ((rc = pack_w(P(h, params, P_M1W), w.W3T, c.combine_hidden, KC, 1, 0, 0, st))) return rc;
@@ -451,6 +465,26 @@ extern "C" int embclip_ac_forward(embclip_ac_t h, const float* params, const voi
   return 0;
 }
 
+extern "C" int embclip_ac_forward(embclip_ac_t h, const float* params, const void* feats_f16, const long long* goals,
+                                  const float* masks, const float* h0, int T, int N, float* logits, float* values, float* h_last,
+                                  void* workspace, uint64_t workspace_bytes, int save_for_backward, void* stream) {
+  return ac_forward_impl(h, params, 0, feats_f16, goals, masks, h0, T, N, logits, values, h_last, workspace, workspace_bytes,
+                         save_for_backward, stream);
+}
+
+extern "C" int embclip_ac_act(embclip_ac_t h, const float* params, uint64_t params_version, const void* feats_f16,
+                              const long long* goals, const float* masks, const float* h0, int N, const float* uniforms,
+                              long long* actions, float* action_log_probs, float* values, float* h_out, float* logits,
+                              void* workspace, uint64_t workspace_bytes, void* stream) {
+  if (!uniforms || !actions || !action_log_probs || !h_out || !logits) return fail(EMBCLIP_EINVAL, "ac_act: null pointer");
+  int rc = ac_forward_impl(h, params, params_version, feats_f16, goals, masks, h0, 1, N, logits, values, h_out, workspace,
+                           workspace_bytes, 0, stream);
+  if (rc) return rc;
+  ac_sample_kernel<<<blocks_for(N, 128), 128, 0, (cudaStream_t)stream>>>(logits, uniforms, actions, action_log_probs, N, h->cfg.num_actions);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int embclip_ac_ppo_loss(embclip_ac_t h, const float* params, int T, int N, const long long* actions,
                                    const float* old_action_log_probs, const float* norm_adv, const float* old_values,
                                    const float* returns, float clip_param, float value_loss_coef, float entropy_coef,
@@ -483,6 +517,7 @@ extern "C" int embclip_ac_backward(embclip_ac_t h, const float* params, const vo
                                    const float* dh_last, float* grads, void* workspace, uint64_t workspace_bytes, void* stream) {
   int rc;
   if ((rc = check_block(h, T, N, workspace, workspace_bytes))) return rc;
+  h->packed_version = 0;                                       // the backward pass reuses workspace regions
   if (!params || !feats_f16 || !goals || !masks || !h0 || !grads) return fail(EMBCLIP_EINVAL, "ac_backward: null pointer");
   if ((dlogits == nullptr) != (dvalues == nullptr)) return fail(EMBCLIP_EINVAL, "ac_backward: pass both dlogits and dvalues, or neither");
   cudaStream_t st = (cudaStream_t)stream;

@@ -694,4 +694,18 @@ nhwc_to_nchw_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fp32 -> fp16 copy (8 elements per thread): the trunk output as the actor-critic path's pixel rows.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cast_f32_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n8) {
+  griddep_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(in) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(in) + 2 * i + 1);
+    uint4 o;
+    o.x = pack_half2(a.x, a.y); o.y = pack_half2(a.z, a.w); o.z = pack_half2(b.x, b.y); o.w = pack_half2(b.z, b.w);
+    reinterpret_cast<uint4*>(out)[i] = o;
+  }
+}
+
 }  // namespace embclip

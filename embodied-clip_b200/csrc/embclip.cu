@@ -34,7 +34,7 @@ int embclip::fail(int code, const char* fmt, ...) {
   return code;
 }
 extern "C" const char* embclip_last_error(void) { return g_err.c_str(); }
-extern "C" int embclip_abi_version(void) { return 3; }
+extern "C" int embclip_abi_version(void) { return 4; }
 
 // =============================================================================================
 // TMA descriptors (driver entry point resolved at run time: the library links only against cudart)
@@ -1060,6 +1060,18 @@ extern "C" int embclip_rn50_profile(embclip_rn50_t h, const float* frames_nhwc, 
   const FramesIn in{frames_nhwc, 0, {1, 1, 1, 0, 0, 0}};
   return forward_impl(h, in, batch, out_trunk_nchw, out_avgpool, out_attnpool, workspace, workspace_bytes,
                       (cudaStream_t)stream, op_ms, names, max_ops);
+}
+extern "C" int embclip_rn50_export_rows_f16(embclip_rn50_t h, int batch, const void* workspace, uint64_t workspace_bytes,
+                                            void* out_rows_f16, void* stream) {
+  if (!h || !workspace || !out_rows_f16 || batch <= 0) return fail(EMBCLIP_EINVAL, "export_rows: null argument or empty batch");
+  if (workspace_bytes < embclip_rn50_workspace_bytes(h, batch)) return fail(EMBCLIP_ENOSPC, "export_rows: workspace too small for batch %d", batch);
+  if (reinterpret_cast<uintptr_t>(out_rows_f16) % 16) return fail(EMBCLIP_EINVAL, "export_rows: output must be 16-B aligned");
+  const float* src = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(workspace) + act_offset(h, batch, h->act_trunk_f32));
+  const long long n8 = (long long)batch * h->fres * h->fres * h->embed / 8;
+  long long blocks = (n8 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  CUDA_TRY(launch_pdl(cast_f32_f16_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, src, reinterpret_cast<__half*>(out_rows_f16), n8));
+  return 0;
 }
 extern "C" int embclip_rn50_launches_per_forward(embclip_rn50_t h, int want_trunk, int want_avgpool, int want_attnpool) {
   if (!h) return fail(EMBCLIP_EINVAL, "null handle");

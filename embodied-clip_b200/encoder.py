@@ -66,7 +66,9 @@ class ClipRN50Encoder:
         need = self.workspace_bytes(batch)
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            raw = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+            off = (-raw.data_ptr()) % 1024
+            self._ws = raw[off:off + need]
         return self._ws
 
     def launches_per_forward(self, want: Iterable[str]) -> int:
@@ -131,6 +133,26 @@ class ClipRN50Encoder:
         return outs
 
     __call__ = forward
+
+    def encode_rows(self, frames: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Trunk forward, returned as fp16 NHWC pixel rows [B * fres * fres, embed]: the layout (and rounding) of
+        ``ResnetTensorNavActorCritic.pack_features(trunk)``, without the fp32 NCHW round trip.  For rollout loops that keep
+        their feature storage on the device."""
+        frames = self._check_frames(frames)
+        B = frames.shape[0]
+        rows = B * self.fres * self.fres
+        if out is None:
+            out = torch.empty(rows, self.embed, dtype=torch.float16, device=self.device)
+        elif out.dtype != torch.float16 or out.numel() != rows * self.embed or not out.is_contiguous() or out.device != self.device:
+            raise ValueError(f"out must be a contiguous fp16 tensor of {rows} x {self.embed} elements on {self.device}")
+        if B == 0:
+            return out
+        self.forward(frames, want=())
+        ws = self._workspace(B)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(self.lib.embclip_rn50_export_rows_f16(self._h, B, ws.data_ptr(), ws.numel(), out.data_ptr(), stream))
+        return out
 
     def profile(self, frames: torch.Tensor, want: Iterable[str] = ("trunk",)) -> List[Tuple[str, float]]:
         """Per-op device time (ms) of one forward, CUDA events on the current stream."""

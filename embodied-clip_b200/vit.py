@@ -114,7 +114,9 @@ class _Tower:
         need = int(self.lib.embclip_tf_workspace_bytes(self._h, batch))
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            raw = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+            off = (-raw.data_ptr()) % 1024
+            self._ws = raw[off:off + need]
         return self._ws
 
     def launches_per_forward(self) -> int:

@@ -101,6 +101,11 @@ int embclip_rn50_act_info(embclip_rn50_t h, int batch, int index, embclip_act_in
 int embclip_rn50_profile(embclip_rn50_t h, const float* frames_nhwc, int batch, float* out_trunk_nchw,
                          float* out_avgpool, float* out_attnpool, void* workspace, uint64_t workspace_bytes,
                          void* stream, float* op_ms, char* names, int max_ops);
+/* fp16 copy of the trunk output of the LAST forward on this workspace, as NHWC pixel rows [batch * fres * fres, embed] -- the
+ * layout the actor-critic path consumes (embclip_ac_pack_features output), bit-identical to packing the fp32 NCHW trunk
+ * output.  Lets a rollout loop skip the fp32 NCHW round trip. */
+int embclip_rn50_export_rows_f16(embclip_rn50_t h, int batch, const void* workspace, uint64_t workspace_bytes, void* out_rows_f16,
+                                 void* stream);
 /* How many kernels one forward launches (for bench.py's gpu_launches). */
 int embclip_rn50_launches_per_forward(embclip_rn50_t h, int want_trunk, int want_avgpool, int want_attnpool);
 
@@ -185,6 +190,15 @@ int embclip_ac_pack_features(embclip_ac_t h, const float* feats_nchw, long long 
 int embclip_ac_forward(embclip_ac_t h, const float* params, const void* feats_f16, const long long* goals,
                        const float* masks, const float* h0, int T, int N, float* logits, float* values, float* h_last,
                        void* workspace, uint64_t workspace_bytes, int save_for_backward, void* stream);
+/* One rollout step (OnPolicyRLEngine.act: actor_critic(...) with steps = 1, then distributions.sample() and log_prob):
+ * embclip_ac_forward(T = 1, no save) followed by CategoricalDistr sampling by inverse CDF on `uniforms` fp32 [N] in [0,1).
+ * -> actions int64 [N], action_log_probs fp32 [N], values fp32 [N], h_out fp32 [N, hidden], logits fp32 [N, A].
+ * params_version: 0 = always rebuild the fp16 weight layouts; otherwise the caller promises that equal versions mean equal
+ * parameter values, and consecutive calls with the same (version, params, workspace, N) reuse the layouts in the workspace. */
+int embclip_ac_act(embclip_ac_t h, const float* params, uint64_t params_version, const void* feats_f16, const long long* goals,
+                   const float* masks, const float* h0, int N, const float* uniforms, long long* actions,
+                   float* action_log_probs, float* values, float* h_out, float* logits, void* workspace,
+                   uint64_t workspace_bytes, void* stream);
 /* PPO.loss_per_step on the block embclip_ac_forward just evaluated (reads its hidden states from the workspace):
  * loss_sums[3] <- sums over the block of {action loss, value loss, entropy}; the gradient of
  *   grad_scale * sum(action + value_loss_coef * value - entropy_coef * entropy)

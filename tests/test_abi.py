@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     for s in header_symbols():
         assert hasattr(lib, s), f"{s} declared in the header but not exported"
     from embclip_b200 import _lib
-    assert _lib.load().embclip_abi_version() == 3
+    assert _lib.load().embclip_abi_version() == 4
 
 
 def test_sass_is_blackwell_native(built_lib):
@@ -61,9 +61,10 @@ def test_plan_queries_without_gpu(built_lib):
     # workspace scales linearly with batch (up to 1 KiB alignment per tensor)
     w1, w8 = lib.embclip_rn50_workspace_bytes(h, 1), lib.embclip_rn50_workspace_bytes(h, 8)
     assert 0 < w1 and 7.9 * w1 < w8 <= 8 * w1
-    # trunk launches: 3 stem convs (pool fused into conv3), 16 x 3 convs, 3 identity-path pools; + heads
-    assert lib.embclip_rn50_launches_per_forward(h, 0, 0, 0) == 3 + 48 + 3
-    assert lib.embclip_rn50_launches_per_forward(h, 1, 1, 1) == 3 + 48 + 3 + 2 + 6
+    # trunk launches: 3 stem convs (pool fused into conv3), 16 x 3 convs minus the 3 conv1s that layer 1's bneck_tail launches
+    # compute (layer1.1, layer1.2, layer2.0), 3 identity-path pools; + heads
+    assert lib.embclip_rn50_launches_per_forward(h, 0, 0, 0) == 3 + 48 - 3 + 3
+    assert lib.embclip_rn50_launches_per_forward(h, 1, 1, 1) == 3 + 48 - 3 + 3 + 2 + 6
     # error paths: state and argument checks happen before any CUDA call
     assert lib.embclip_rn50_forward(h, None, 1, None, None, None, None, 0, None) == -1
     bad = _lib.RN50Cfg()

@@ -471,3 +471,135 @@ def test_full_size_block_properties(models, lib):
         out.append(grads)
     assert rel(out[1], 1024.0 * out[0]) <= 1e-4
     assert out[0].abs().max().item() > 0
+
+
+# ----------------------------------------------------------------------------------------------- rollout-step fast path
+def test_encode_rows_equals_packed_trunk(lib, rn50_visual):
+    """ClipRN50Encoder.encode_rows (fp16 NHWC rows straight from the trunk) == pack_features(fp32 NCHW trunk), bit for bit."""
+    from conftest import synthetic_frames
+    from embclip_b200.actor_critic import ResnetTensorNavActorCritic
+    from embclip_b200.encoder import ClipRN50Encoder
+    enc = ClipRN50Encoder(rn50_visual.state_dict(), "cuda:0")
+    model = ResnetTensorNavActorCritic(device="cuda:0")
+    frames = synthetic_frames(5, seed=3).cuda()
+    trunk = enc(frames, ("trunk",))["trunk"]
+    packed = model.pack_features(trunk.unsqueeze(0)).data
+    rows = enc.encode_rows(frames)
+    torch.cuda.synchronize()
+    assert rows.shape == packed.shape == (5 * 49, 2048) and rows.dtype == torch.float16
+    assert torch.equal(rows, packed)
+    with pytest.raises(ValueError):
+        enc.encode_rows(frames, out=torch.empty(3, 2048, dtype=torch.float16, device="cuda"))
+
+
+@pytest.mark.parametrize("N", [1, 7, 60])
+def test_act_step_matches_forward_and_samples_by_inverse_cdf(models, N):
+    """embclip_ac_act == forward(T=1) bit for bit (same kernels), its sampled action is the inverse-CDF draw for the supplied
+    uniform, and the returned log-prob is log_softmax(logits)[action]."""
+    ours, _ = models
+    ro = _rollout(1, N, seed=100 + N)
+    pf = ours.pack_features(ro["features"].cuda())
+    g = torch.Generator(device="cuda").manual_seed(N)
+    u = torch.rand(N, device="cuda", generator=g)
+    with torch.no_grad():
+        logits, values, h_last = ours.forward_tensors(pf, ro["goals"].cuda(), ro["memory"].cuda(), ro["masks"].cuda())
+    for _ in range(2):                                     # second call runs on the cached fp16 weight layouts
+        a, lp, v, h, lg = ours.act(pf.data, ro["goals"][0].cuda(), ro["masks"][0].cuda(), ro["memory"][0].cuda(), u)
+        torch.cuda.synchronize()
+        assert torch.equal(lg, logits[0]) and torch.equal(v, values[0]) and torch.equal(h, h_last)
+        p = torch.softmax(lg.double(), -1)
+        cdf = p.cumsum(-1)
+        lo, hi = cdf.gather(-1, a[:, None])[:, 0] - p.gather(-1, a[:, None])[:, 0], cdf.gather(-1, a[:, None])[:, 0]
+        assert ((u.double() >= lo - 1e-6) & (u.double() <= hi + 1e-6)).all()
+        assert a.dtype == torch.int64 and int(a.min()) >= 0 and int(a.max()) < 6
+        assert (lp - torch.log_softmax(lg, -1).gather(-1, a[:, None])[:, 0]).abs().max().item() <= 2e-6
+    # extremes of u: first / last action with mass
+    a0 = ours.act(pf.data, ro["goals"][0].cuda(), ro["masks"][0].cuda(), ro["memory"][0].cuda(), torch.zeros(N, device="cuda"))[0]
+    a1 = ours.act(pf.data, ro["goals"][0].cuda(), ro["masks"][0].cuda(), ro["memory"][0].cuda(), torch.full((N,), 1 - 2 ** -24, device="cuda"))[0]
+    assert (a0 == 0).all() and (a1 == 5).all()
+
+
+def test_act_weight_layout_cache_follows_parameter_changes(models):
+    from embclip_b200.actor_critic import ResnetTensorNavActorCritic
+    ours0, _ = models
+    ours = ResnetTensorNavActorCritic(device="cuda:0")
+    ours.load_state_dict(ours0.state_dict())
+    N = 9
+    ro = _rollout(1, N, seed=5)
+    pf = ours.pack_features(ro["features"].cuda())
+    args = (pf.data, ro["goals"][0].cuda(), ro["masks"][0].cuda(), ro["memory"][0].cuda(), torch.full((N,), 0.5, device="cuda"))
+    lg0 = ours.act(*args)[4].clone()
+    v0 = ours.params_version()
+    assert torch.equal(ours.act(*args)[4], lg0) and ours.params_version() == v0
+    with torch.no_grad():
+        ours.flat_params.mul_(1.25)                        # what an optimizer step looks like to torch's version counter
+    assert ours.params_version() != v0
+    lg1 = ours.act(*args)[4].clone()
+    with torch.no_grad():
+        ref1 = ours.forward_tensors(pf, ro["goals"].cuda(), ro["memory"].cuda(), ro["masks"].cuda())[0][0]
+    assert not torch.equal(lg1, lg0) and torch.equal(lg1, ref1)
+    ours.flat_params.data.mul_(0.8)                        # raw write, invisible to torch: the caller must say so
+    ours.mark_params_changed()
+    lg2 = ours.act(*args)[4]
+    with torch.no_grad():
+        ref2 = ours.forward_tensors(pf, ro["goals"].cuda(), ro["memory"].cuda(), ro["masks"].cuda())[0][0]
+    assert torch.equal(lg2, ref2) and not torch.equal(lg2, lg1)
+    # a training forward/backward in between (different block shape, same workspace) must not leave stale layouts behind
+    ro2 = _rollout(4, N, seed=6)
+    lo, va, _ = ours.forward_tensors(ro2["features"].cuda(), ro2["goals"].cuda(), ro2["memory"].cuda(), ro2["masks"].cuda())
+    (lo.sum() + va.sum()).backward()
+    assert torch.equal(ours.act(*args)[4], ref2)
+
+
+def test_sampler_frequencies(lib):
+    """ac_sample: empirical action frequencies over 100k draws follow softmax(logits) (4.5-sigma per action)."""
+    from embclip_b200.actor_critic import ResnetTensorNavActorCritic
+    model = ResnetTensorNavActorCritic(device="cuda:0")
+    N = 60
+    bias = torch.tensor([0.0, 1.0, -1.0, 0.5, 2.0, -3.0])
+    with torch.no_grad():
+        model.flat_params.zero_()
+        model.named_views()["actor.linear.bias"].copy_(bias)
+    feats = torch.zeros(N * 49, 2048, dtype=torch.float16, device="cuda")
+    goals, masks, mem = torch.zeros(N, dtype=torch.int64, device="cuda"), torch.ones(N, device="cuda"), torch.zeros(N, 512, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    reps = 1700
+    u = torch.rand(reps, N, device="cuda", generator=g)
+    acts = torch.empty(reps, N, dtype=torch.int64, device="cuda")
+    for r in range(reps):
+        lg = model.act(feats, goals, masks, mem, u[r], actions=acts[r])[4]
+    torch.cuda.synchronize()
+    assert (lg[0].cpu() - bias).abs().max().item() <= 1e-5, lg[0]          # all other weights are zero: logits = actor bias
+    counts = torch.bincount(acts.flatten().cpu(), minlength=6).double()
+    p = torch.softmax(bias.double(), -1)
+    n = N * reps
+    sigma = (p * (1 - p) / n).sqrt()
+    assert ((counts / n - p).abs() <= 4.5 * sigma).all(), (counts / n, p, sigma)
+
+
+def test_harness_packed_rollout_equals_allenact_data_flow(lib, rn50_visual):
+    """The packed rollout (encode_rows -> act -> PackedFeatures) and the verbatim AllenAct flow (fp32 NCHW features, forward,
+    torch sampling, pack_features) see the same values / hidden states bit for bit; only the sampled actions use a different
+    random stream.  Then one update runs on the packed storage."""
+    from embclip_b200.actor_critic import PPOTrainer, ResnetTensorNavActorCritic
+    from embclip_b200.encoder import ClipRN50Encoder
+    from embclip_b200.harness import SyntheticPPOStep
+    enc = ClipRN50Encoder(rn50_visual.state_dict(), "cuda:0")
+    T, N = 3, 4
+    g = torch.Generator().manual_seed(0)
+    frames = torch.randint(0, 256, (T, N, 224, 224, 3), generator=g, dtype=torch.uint8).cuda()
+    vals = []
+    for packed in (True, False):
+        torch.manual_seed(3)
+        model = ResnetTensorNavActorCritic(device="cuda:0")
+        st = SyntheticPPOStep(enc, model, PPOTrainer(model), T=T, N=N, seed=1, packed_rollout=packed)
+        st.collect(lambda t: frames[t])
+        torch.cuda.synchronize()
+        vals.append(st.values.clone())
+        assert int(st.actions.min()) >= 0 and int(st.actions.max()) < 6 and torch.isfinite(st.log_probs).all()
+        if packed:
+            losses = st.update()
+            torch.cuda.synchronize()
+            assert all(torch.isfinite(v).all() for v in losses.values())
+            assert st.launches_per_step() > 0
+    assert torch.equal(vals[0], vals[1])
