@@ -383,6 +383,24 @@ static int launch_conv3x3_halo(const Conv3Op& op, cudaStream_t st) {
     const uint32_t stage = op.pool ? uint32_t(ms) * 128u * (bn * 2 + 16) : 0u;
     if (2u * plane + 4u * uint32_t(bn * kc * 2) + stage + 1024u + kC3BarBytes <= 227u * 1024u) break;
   }
+  // Under-filled launches (rollout batches: a few dozen frames): halving the sub-tile count doubles the tiles.  Cost model =
+  // rounds over the SMs x work per tile; ties keep the larger tile (less weight traffic per MAC).  Large launches (> 2 rounds)
+  // keep the default -- there the weight traffic matters more than the last partial round.
+  static const bool small_ok = getenv("EMBCLIP_C3_NO_SMALL") == nullptr;
+  while (small_ok && !env_ms && ms > 1) {
+    const long long nb = op.N / bn, sms = num_sms();
+    const long long tiles = (long long)g.tiles * nb;
+    if (tiles > 2 * sms) break;
+    C3Geom g2;
+    if (!c3_geometry(op.B, op.H, op.W, ms / 2, op.pool != 0, &g2)) break;
+    const uint32_t plane2 = ((g2.rows_alloc * (kc * 2)) + 1023u) & ~1023u;
+    const uint32_t stage2 = op.pool ? uint32_t(ms / 2) * 128u * (bn * 2 + 16) : 0u;
+    if (2u * plane2 + 4u * uint32_t(bn * kc * 2) + stage2 + 1024u + kC3BarBytes > 227u * 1024u) break;
+    const long long rounds = (tiles + sms - 1) / sms, rounds2 = ((long long)g2.tiles * nb + sms - 1) / sms;
+    if (rounds2 * (ms / 2) >= rounds * ms) break;
+    ms /= 2;
+    g = g2;
+  }
 #define EMBCLIP_C3(BN_, MS_, KC_) \
   if (bn == BN_ && ms == MS_ && kc == KC_) \
     return op.pool ? launch_c3_cfg<BN_, MS_, KC_, true>(op, g, st) : launch_c3_cfg<BN_, MS_, KC_, false>(op, g, st);
