@@ -281,6 +281,167 @@ stem_conv1_tc_kernel(const TIn* __restrict__ x, const __half* __restrict__ wtc, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Stem conv1, row-tiled: the same hi/lo-split UMMA as stem_conv1_tc_kernel, but one tile = ONE OUTPUT ROW (Ro <= 128 pixels)
+// and the three input rows it needs are brought into a shared-memory ring by 1-D bulk copies (cp.async.bulk) two tiles
+// ahead.  The ncu capture of the gather version (profiles/r1f: 1.9 TB/s, 24 % warp occupancy, long-scoreboard stalls) shows its
+// per-tile chain  global gather -> convert -> UMMA -> store  exposes the DRAM latency every tile; here DRAM requests are always
+// in flight without holding registers, and the gather reads shared memory.  Needs 16-B aligned rows (R*3*sizeof(TIn) % 16 == 0).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+constexpr int kStemRowsStages = 3;
+template <typename TIn>
+constexpr int stem_rows_stage_bytes(int R) { return ((R * 3 * int(sizeof(TIn)) + 127) / 128 * 128) * 3; }
+template <typename TIn>
+__global__ void __launch_bounds__(128)
+stem_conv1_rows_kernel(const TIn* __restrict__ x, const __half* __restrict__ wtc, const float* __restrict__ bias,
+                       __half* __restrict__ y, int B, int R, const StemNorm norm) {
+  constexpr int COUT = 32, S = kStemRowsStages;
+  constexpr bool kRaw = sizeof(TIn) == 1;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t row_bytes = uint32_t(R) * 3u * uint32_t(sizeof(TIn));
+  const uint32_t row_pitch = (row_bytes + 127u) & ~127u;
+  const uint32_t stage_bytes = row_pitch * 3u;
+  const uint32_t sA = base;                        // 2 k-blocks x [128 rows][128 B]
+  const uint32_t sW = base + 32768;                // 2 k-blocks x [32 rows][128 B]
+  const uint32_t sIn = sW + 8192;                  // S stages x 3 rows
+  const uint32_t sBar = sIn + S * stage_bytes;     // S full barriers, 1 MMA barrier, TMEM slot
+  const uint32_t bar_mma = sBar + 8 * S, tmem_slot = bar_mma + 8;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int Ro = R / 2;
+
+  for (int i = tid; i < 32 * 16; i += 128) {       // weights -> swizzled K-major tiles (as in stem_conv1_tc_kernel)
+    const int n = i >> 4, piece = i & 15;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(wtc + n * 128) + piece);
+    *reinterpret_cast<uint4*>(gen + 32768 + (piece >> 3) * 4096 + swizzle_off<128>(uint32_t(n), uint32_t(piece & 7))) = v;
+  }
+  for (int i = tid; i < 2 * 16384 / 16; i += 128)  // A rows >= Ro are never written again: they must read as zero
+    reinterpret_cast<uint4*>(gen)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    for (int s2 = 0; s2 < S; ++s2) mbar_init(sBar + 8 * s2, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<32>(tmem_slot);
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  griddep_wait();
+
+  const long long num_tiles = (long long)B * Ro;
+  float bv[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) bv[c] = __ldg(bias + c);
+
+  // tile -> (image, output row); input rows 2*oh-1 .. 2*oh+1 (row -1 is the zero pad: not loaded, not read)
+  auto issue = [&](long long tile, int stage) {
+    const int oh = int(tile % Ro);
+    const long long b = tile / Ro;
+    const int first = oh == 0 ? 1 : 0;
+    const uint32_t bar = sBar + 8 * stage;
+    mbar_arrive_expect_tx(bar, row_bytes * uint32_t(3 - first));
+    for (int kh = first; kh < 3; ++kh)
+      bulk_load_1d(sIn + stage * stage_bytes + kh * row_pitch, x + ((size_t)b * R + (2 * oh - 1 + kh)) * R * 3, row_bytes, bar);
+  };
+  if (tid == 0) {
+    long long t = blockIdx.x;
+    for (int s2 = 0; s2 < S && t < num_tiles; ++s2, t += gridDim.x) issue(t, s2);
+  }
+  int stage = 0;
+  uint32_t in_phase = 0, mma_phase = 0;
+  for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int oh = int(tile % Ro);
+    mbar_wait(sBar + 8 * stage, in_phase);
+    if (tid < Ro) {
+      const uint8_t* st = gen + (sIn - base) + stage * stage_bytes;
+      uint32_t hi[16], lo[16];
+      float v[28];
+      v[27] = 0.f;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const bool rok = kh > 0 || oh > 0;
+        const TIn* row = reinterpret_cast<const TIn*>(st + kh * row_pitch) + (2 * tid - 1) * 3;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          float t = 0.f;
+          if (rok && (tid > 0 || j >= 3)) {
+            t = float(row[j]);
+            if (kRaw) t = t * norm.scale[j % 3] + norm.offset[j % 3];
+          }
+          v[kh * 9 + j] = t;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float a = i < 14 ? v[2 * i] : 0.f, b2 = i < 14 ? v[2 * i + 1] : 0.f;
+        const __half ha = __float2half_rn(a), hb = __float2half_rn(b2);
+        const __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b2 - __half2float(hb));
+        hi[i] = uint32_t(__half_as_ushort(ha)) | (uint32_t(__half_as_ushort(hb)) << 16);
+        lo[i] = uint32_t(__half_as_ushort(la)) | (uint32_t(__half_as_ushort(lb)) << 16);
+      }
+#pragma unroll
+      for (int piece = 0; piece < 8; ++piece) {    // k-block 0: [hi | lo]
+        const uint32_t* src = piece < 4 ? hi + 4 * piece : lo + 4 * (piece - 4);
+        const uint32_t a = sA + swizzle_off<128>(uint32_t(tid), uint32_t(piece));
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(src[0]), "r"(src[1]), "r"(src[2]), "r"(src[3]) : "memory");
+      }
+#pragma unroll
+      for (int piece = 0; piece < 4; ++piece) {    // k-block 1: [hi | 0]  (the zero half was written once above)
+        const uint32_t a = sA + 16384 + swizzle_off<128>(uint32_t(tid), uint32_t(piece));
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hi[4 * piece]), "r"(hi[4 * piece + 1]), "r"(hi[4 * piece + 2]), "r"(hi[4 * piece + 3]) : "memory");
+      }
+    }
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();                               // A rows written, input stage fully read, previous accumulator drained
+    if (tid == 0) {
+      tcgen05_fence_after();
+      constexpr uint32_t idesc = make_idesc_f16_f32(128, COUT);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_f16_ss(tmem_base, make_kmajor_desc<128>(sA + uint32_t(k >> 2) * 16384u + 32u * uint32_t(k & 3)),
+                    make_kmajor_desc<128>(sW + uint32_t(k >> 2) * 4096u + 32u * uint32_t(k & 3)), idesc, k != 0);
+      umma_commit(bar_mma);
+      const long long nxt = tile + (long long)S * gridDim.x;      // refill the stage just consumed
+      if (nxt < num_tiles) issue(nxt, stage);
+    }
+    __syncwarp();
+    mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1u;
+    tcgen05_fence_after();
+    uint32_t acc[32];
+    tmem_ld_32x32b<32>(tmem_base + (uint32_t(warp * 32) << 16), acc);
+    tmem_ld_wait();
+    if (tid < Ro) {
+      uint4* out = reinterpret_cast<uint4*>(y + ((size_t)tile * Ro + tid) * COUT);
+#pragma unroll
+      for (int i = 0; i < COUT / 8; ++i) {
+        uint4 o;
+        o.x = pack_half2(fmaxf(__uint_as_float(acc[8 * i + 0]) + bv[8 * i + 0], 0.f), fmaxf(__uint_as_float(acc[8 * i + 1]) + bv[8 * i + 1], 0.f));
+        o.y = pack_half2(fmaxf(__uint_as_float(acc[8 * i + 2]) + bv[8 * i + 2], 0.f), fmaxf(__uint_as_float(acc[8 * i + 3]) + bv[8 * i + 3], 0.f));
+        o.z = pack_half2(fmaxf(__uint_as_float(acc[8 * i + 4]) + bv[8 * i + 4], 0.f), fmaxf(__uint_as_float(acc[8 * i + 5]) + bv[8 * i + 5], 0.f));
+        o.w = pack_half2(fmaxf(__uint_as_float(acc[8 * i + 6]) + bv[8 * i + 6], 0.f), fmaxf(__uint_as_float(acc[8 * i + 7]) + bv[8 * i + 7], 0.f));
+        out[i] = o;
+      }
+    }
+    if (++stage == S) { stage = 0; in_phase ^= 1u; }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc<32>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // nn.AvgPool2d(2) on NHWC fp16; one thread = 8 channels of one output pixel (16-B vectors).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void acc8(float (&a)[8], const uint4 v) {

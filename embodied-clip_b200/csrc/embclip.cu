@@ -547,6 +547,34 @@ static int launch_stem_conv1_tc(const void* x, int x_u8, const float* norm6, con
     CUDA_TRY(cudaFuncSetAttribute(stem_conv1_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemTcSmem));
     attr = true;
   }
+  // row-tiled variant (bulk-copied input rows, see aux_kernels.cuh) when rows are 16-B granular and one output row fits a tile
+  static const bool gather_only = getenv("EMBCLIP_STEM_GATHER") != nullptr;
+  const size_t esz = x_u8 ? 1 : 4;
+  if (!gather_only && R / 2 <= 128 && (size_t(R) * 3 * esz) % 16 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0) {
+    const int stage_bytes = x_u8 ? stem_rows_stage_bytes<uint8_t>(R) : stem_rows_stage_bytes<float>(R);
+    const size_t smem = 1024 + 32768 + 8192 + size_t(kStemRowsStages) * stage_bytes + 64;
+    static size_t attr_f = 0, attr_u = 0;
+    size_t& cur = x_u8 ? attr_u : attr_f;
+    if (smem > cur) {
+      if (x_u8) CUDA_TRY(cudaFuncSetAttribute(stem_conv1_rows_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      else CUDA_TRY(cudaFuncSetAttribute(stem_conv1_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cur = smem;
+    }
+    const long long row_tiles = (long long)B * (R / 2);
+    int per_sm = int((227u * 1024u) / smem);
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    long long g = (long long)num_sms() * per_sm;
+    if (g > row_tiles) g = row_tiles;
+    if (g <= 0) return 0;
+    if (x_u8)
+      CUDA_TRY(launch_pdl(stem_conv1_rows_kernel<uint8_t>, dim3((unsigned)g), dim3(128), smem, st, reinterpret_cast<const uint8_t*>(x),
+                          reinterpret_cast<const __half*>(wtc), b, reinterpret_cast<__half*>(y), B, R, nm));
+    else
+      CUDA_TRY(launch_pdl(stem_conv1_rows_kernel<float>, dim3((unsigned)g), dim3(128), smem, st, reinterpret_cast<const float*>(x),
+                          reinterpret_cast<const __half*>(wtc), b, reinterpret_cast<__half*>(y), B, R, nm));
+    return 0;
+  }
   const long long tiles = ((long long)B * (R / 2) * (R / 2) + 127) / 128;
   long long grid = (long long)num_sms() * 4;
   if (grid > tiles) grid = tiles;
