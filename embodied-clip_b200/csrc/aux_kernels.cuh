@@ -294,11 +294,14 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
 constexpr int kStemRowsStages = 3;
 template <typename TIn>
 constexpr int stem_rows_stage_bytes(int R) { return ((R * 3 * int(sizeof(TIn)) + 127) / 128 * 128) * 3; }
-template <typename TIn>
+// COUT = 32 (width 64) or 64 (width 96: 48 real channels + 16 zero-weight pad channels).  An output row longer than 128
+// pixels (R = 384) is cut into equal segments; every segment's tile loads the three full input rows.
+template <typename TIn, int COUT>
 __global__ void __launch_bounds__(128)
 stem_conv1_rows_kernel(const TIn* __restrict__ x, const __half* __restrict__ wtc, const float* __restrict__ bias,
-                       __half* __restrict__ y, int B, int R, const StemNorm norm) {
-  constexpr int COUT = 32, S = kStemRowsStages;
+                       __half* __restrict__ y, int B, int R, int segs, const StemNorm norm) {
+  constexpr int S = kStemRowsStages;
+  constexpr int kWBytes = 2 * COUT * 128;
   constexpr bool kRaw = sizeof(TIn) == 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -308,25 +311,26 @@ stem_conv1_rows_kernel(const TIn* __restrict__ x, const __half* __restrict__ wtc
   const uint32_t stage_bytes = row_pitch * 3u;
   const uint32_t sA = base;                        // 2 k-blocks x [128 rows][128 B]
   const uint32_t sW = base + 32768;                // 2 k-blocks x [32 rows][128 B]
-  const uint32_t sIn = sW + 8192;                  // S stages x 3 rows
+  const uint32_t sIn = sW + kWBytes;               // S stages x 3 rows
   const uint32_t sBar = sIn + S * stage_bytes;     // S full barriers, 1 MMA barrier, TMEM slot
   const uint32_t bar_mma = sBar + 8 * S, tmem_slot = bar_mma + 8;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int Ro = R / 2;
+  const int seg_len = Ro / segs;                   // <= 128 output pixels per tile
 
-  for (int i = tid; i < 32 * 16; i += 128) {       // weights -> swizzled K-major tiles (as in stem_conv1_tc_kernel)
+  for (int i = tid; i < COUT * 16; i += 128) {     // weights -> swizzled K-major tiles (as in stem_conv1_tc_kernel)
     const int n = i >> 4, piece = i & 15;
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(wtc + n * 128) + piece);
-    *reinterpret_cast<uint4*>(gen + 32768 + (piece >> 3) * 4096 + swizzle_off<128>(uint32_t(n), uint32_t(piece & 7))) = v;
+    *reinterpret_cast<uint4*>(gen + 32768 + (piece >> 3) * (COUT * 128) + swizzle_off<128>(uint32_t(n), uint32_t(piece & 7))) = v;
   }
-  for (int i = tid; i < 2 * 16384 / 16; i += 128)  // A rows >= Ro are never written again: they must read as zero
+  for (int i = tid; i < 2 * 16384 / 16; i += 128)  // A rows >= seg_len are never written again: they must read as zero
     reinterpret_cast<uint4*>(gen)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     for (int s2 = 0; s2 < S; ++s2) mbar_init(sBar + 8 * s2, 1);
     mbar_init(bar_mma, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<32>(tmem_slot);
+  if (warp == 0) tmem_alloc<COUT>(tmem_slot);
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
@@ -335,15 +339,16 @@ stem_conv1_rows_kernel(const TIn* __restrict__ x, const __half* __restrict__ wtc
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   griddep_wait();
 
-  const long long num_tiles = (long long)B * Ro;
+  const long long num_tiles = (long long)B * Ro * segs;
   float bv[COUT];
 #pragma unroll
   for (int c = 0; c < COUT; ++c) bv[c] = __ldg(bias + c);
 
   // tile -> (image, output row); input rows 2*oh-1 .. 2*oh+1 (row -1 is the zero pad: not loaded, not read)
   auto issue = [&](long long tile, int stage) {
-    const int oh = int(tile % Ro);
-    const long long b = tile / Ro;
+    const long long rowi = tile / segs;
+    const int oh = int(rowi % Ro);
+    const long long b = rowi / Ro;
     const int first = oh == 0 ? 1 : 0;
     const uint32_t bar = sBar + 8 * stage;
     mbar_arrive_expect_tx(bar, row_bytes * uint32_t(3 - first));
@@ -357,9 +362,10 @@ stem_conv1_rows_kernel(const TIn* __restrict__ x, const __half* __restrict__ wtc
   int stage = 0;
   uint32_t in_phase = 0, mma_phase = 0;
   for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int oh = int(tile % Ro);
+    const int oh = int((tile / segs) % Ro);
+    const int ow = int(tile % segs) * seg_len + tid;                  // this thread's output column
     mbar_wait(sBar + 8 * stage, in_phase);
-    if (tid < Ro) {
+    if (tid < seg_len) {
       const uint8_t* st = gen + (sIn - base) + stage * stage_bytes;
       uint32_t hi[16], lo[16];
       float v[28];
@@ -367,11 +373,11 @@ stem_conv1_rows_kernel(const TIn* __restrict__ x, const __half* __restrict__ wtc
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
         const bool rok = kh > 0 || oh > 0;
-        const TIn* row = reinterpret_cast<const TIn*>(st + kh * row_pitch) + (2 * tid - 1) * 3;
+        const TIn* row = reinterpret_cast<const TIn*>(st + kh * row_pitch) + (2 * ow - 1) * 3;
 #pragma unroll
         for (int j = 0; j < 9; ++j) {
           float t = 0.f;
-          if (rok && (tid > 0 || j >= 3)) {
+          if (rok && (ow > 0 || j >= 3)) {
             t = float(row[j]);
             if (kRaw) t = t * norm.scale[j % 3] + norm.offset[j % 3];
           }
@@ -407,7 +413,7 @@ stem_conv1_rows_kernel(const TIn* __restrict__ x, const __half* __restrict__ wtc
 #pragma unroll
       for (int k = 0; k < 8; ++k)
         umma_f16_ss(tmem_base, make_kmajor_desc<128>(sA + uint32_t(k >> 2) * 16384u + 32u * uint32_t(k & 3)),
-                    make_kmajor_desc<128>(sW + uint32_t(k >> 2) * 4096u + 32u * uint32_t(k & 3)), idesc, k != 0);
+                    make_kmajor_desc<128>(sW + uint32_t(k >> 2) * uint32_t(COUT * 128) + 32u * uint32_t(k & 3)), idesc, k != 0);
       umma_commit(bar_mma);
       const long long nxt = tile + (long long)S * gridDim.x;      // refill the stage just consumed
       if (nxt < num_tiles) issue(nxt, stage);
@@ -416,19 +422,22 @@ stem_conv1_rows_kernel(const TIn* __restrict__ x, const __half* __restrict__ wtc
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1u;
     tcgen05_fence_after();
-    uint32_t acc[32];
-    tmem_ld_32x32b<32>(tmem_base + (uint32_t(warp * 32) << 16), acc);
-    tmem_ld_wait();
-    if (tid < Ro) {
-      uint4* out = reinterpret_cast<uint4*>(y + ((size_t)tile * Ro + tid) * COUT);
 #pragma unroll
-      for (int i = 0; i < COUT / 8; ++i) {
-        uint4 o;
-        o.x = pack_half2(fmaxf(__uint_as_float(acc[8 * i + 0]) + bv[8 * i + 0], 0.f), fmaxf(__uint_as_float(acc[8 * i + 1]) + bv[8 * i + 1], 0.f));
-        o.y = pack_half2(fmaxf(__uint_as_float(acc[8 * i + 2]) + bv[8 * i + 2], 0.f), fmaxf(__uint_as_float(acc[8 * i + 3]) + bv[8 * i + 3], 0.f));
-        o.z = pack_half2(fmaxf(__uint_as_float(acc[8 * i + 4]) + bv[8 * i + 4], 0.f), fmaxf(__uint_as_float(acc[8 * i + 5]) + bv[8 * i + 5], 0.f));
-        o.w = pack_half2(fmaxf(__uint_as_float(acc[8 * i + 6]) + bv[8 * i + 6], 0.f), fmaxf(__uint_as_float(acc[8 * i + 7]) + bv[8 * i + 7], 0.f));
-        out[i] = o;
+    for (int c0 = 0; c0 < COUT; c0 += 32) {
+      uint32_t acc[32];
+      tmem_ld_32x32b<32>(tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(c0), acc);
+      tmem_ld_wait();
+      if (tid < seg_len) {
+        uint4* out = reinterpret_cast<uint4*>(y + ((size_t)(tile / segs) * Ro + ow) * COUT + c0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 o;
+          o.x = pack_half2(fmaxf(__uint_as_float(acc[8 * i + 0]) + bv[c0 + 8 * i + 0], 0.f), fmaxf(__uint_as_float(acc[8 * i + 1]) + bv[c0 + 8 * i + 1], 0.f));
+          o.y = pack_half2(fmaxf(__uint_as_float(acc[8 * i + 2]) + bv[c0 + 8 * i + 2], 0.f), fmaxf(__uint_as_float(acc[8 * i + 3]) + bv[c0 + 8 * i + 3], 0.f));
+          o.z = pack_half2(fmaxf(__uint_as_float(acc[8 * i + 4]) + bv[c0 + 8 * i + 4], 0.f), fmaxf(__uint_as_float(acc[8 * i + 5]) + bv[c0 + 8 * i + 5], 0.f));
+          o.w = pack_half2(fmaxf(__uint_as_float(acc[8 * i + 6]) + bv[c0 + 8 * i + 6], 0.f), fmaxf(__uint_as_float(acc[8 * i + 7]) + bv[c0 + 8 * i + 7], 0.f));
+          out[i] = o;
+        }
       }
     }
     if (++stage == S) { stage = 0; in_phase ^= 1u; }
@@ -437,7 +446,7 @@ stem_conv1_rows_kernel(const TIn* __restrict__ x, const __half* __restrict__ wtc
   __syncthreads();
   if (warp == 0) {
     tcgen05_fence_after();
-    tmem_dealloc<32>(tmem_base);
+    tmem_dealloc<COUT>(tmem_base);
   }
 }
 

@@ -368,7 +368,7 @@ static int launch_c3_cfg(const Conv3Op& op, const C3Geom& g, cudaStream_t st) {
 static int launch_conv3x3_halo(const Conv3Op& op, cudaStream_t st) {
   if (op.C % 32 || op.N % 32) return fail(EMBCLIP_EINVAL, "conv3x3: channels must be multiples of 32 (cin %d cout %d)", op.C, op.N);
   if (op.pool && ((op.H | op.W) & 1)) return fail(EMBCLIP_EINVAL, "conv3x3: fused 2x2 pool needs even H, W");
-  const int kc = op.C % 64 == 0 ? 64 : 32;
+  int kc = op.C % 64 == 0 ? 64 : 32;
   static const int env_bn = getenv("EMBCLIP_C3_BN") ? atoi(getenv("EMBCLIP_C3_BN")) : 0;
   static const int env_ms = getenv("EMBCLIP_C3_MS") ? atoi(getenv("EMBCLIP_C3_MS")) : 0;
   int bn = op.N % 128 == 0 ? 128 : (op.N % 64 == 0 ? 64 : 32);
@@ -376,8 +376,14 @@ static int launch_conv3x3_halo(const Conv3Op& op, cudaStream_t st) {
   int ms = bn == 256 ? 1 : (bn == 128 ? 2 : 4);
   if (env_ms && env_ms * bn * 2 <= 512) ms = env_ms;
   C3Geom g;
+  const int ms0 = ms;
   for (;; ms >>= 1) {
-    if (ms < 1) return fail(EMBCLIP_EINVAL, "conv3x3: no strip geometry for H %d W %d", op.H, op.W);
+    if (ms < 1) {
+      // wide rows (e.g. 192-pixel rows with the fused pool need a 2-row strip): retry with 32-channel chunks, whose planes
+      // are half the size -- only tile widths that have a 32-chunk instantiation
+      if (kc == 64 && bn <= 64) { kc = 32; ms = ms0 << 1; continue; }
+      return fail(EMBCLIP_EINVAL, "conv3x3: no strip geometry for H %d W %d", op.H, op.W);
+    }
     if (!c3_geometry(op.B, op.H, op.W, ms, op.pool != 0, &g)) continue;
     const uint32_t plane = ((g.rows_alloc * (kc * 2)) + 1023u) & ~1023u;
     const uint32_t stage = op.pool ? uint32_t(ms) * 128u * (bn * 2 + 16) : 0u;
@@ -405,6 +411,7 @@ static int launch_conv3x3_halo(const Conv3Op& op, cudaStream_t st) {
   if (bn == BN_ && ms == MS_ && kc == KC_) \
     return op.pool ? launch_c3_cfg<BN_, MS_, KC_, true>(op, g, st) : launch_c3_cfg<BN_, MS_, KC_, false>(op, g, st);
   EMBCLIP_C3(32, 4, 32) EMBCLIP_C3(32, 2, 32) EMBCLIP_C3(32, 1, 32)
+  EMBCLIP_C3(32, 4, 64) EMBCLIP_C3(32, 2, 64) EMBCLIP_C3(32, 1, 64)
   EMBCLIP_C3(64, 4, 32) EMBCLIP_C3(64, 2, 32) EMBCLIP_C3(64, 1, 32)
   EMBCLIP_C3(64, 4, 64) EMBCLIP_C3(64, 2, 64) EMBCLIP_C3(64, 1, 64)
   EMBCLIP_C3(128, 2, 64) EMBCLIP_C3(128, 1, 64)
@@ -537,43 +544,49 @@ extern "C" int embclip_avgpool2_f16(const void* in, void* out, int B, int H, int
 }
 
 // tensor-core version (hi/lo-split im2col rows); wtc = fp16 [32][128]
-static int launch_stem_conv1_tc(const void* x, int x_u8, const float* norm6, const void* wtc, const float* b, void* y, int B, int R, cudaStream_t st) {
+template <typename TIn, int COUT>
+static int launch_stem_rows(const void* x, const void* wtc, const float* b, void* y, int B, int R, const StemNorm& nm, cudaStream_t st) {
+  const int Ro = R / 2;
+  int segs = (Ro + 127) / 128;
+  while (Ro % segs) ++segs;                                  // equal segments of <= 128 output pixels
+  const size_t smem = 1024 + 32768 + 2 * COUT * 128 + size_t(kStemRowsStages) * stem_rows_stage_bytes<TIn>(R) + 64;
+  if (smem > 227u * 1024u) return fail(EMBCLIP_EINVAL, "stem: resolution %d does not fit the row ring", R);
+  static size_t attr = 0;
+  if (smem > attr) {
+    CUDA_TRY(cudaFuncSetAttribute(stem_conv1_rows_kernel<TIn, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  const long long tiles = (long long)B * Ro * segs;
+  int per_sm = int((227u * 1024u) / smem);
+  if (per_sm > 4) per_sm = 4;
+  long long g = (long long)num_sms() * per_sm;
+  if (g > tiles) g = tiles;
+  if (g <= 0) return 0;
+  CUDA_TRY(launch_pdl(stem_conv1_rows_kernel<TIn, COUT>, dim3((unsigned)g), dim3(128), smem, st, reinterpret_cast<const TIn*>(x),
+                      reinterpret_cast<const __half*>(wtc), b, reinterpret_cast<__half*>(y), B, R, segs, nm));
+  return 0;
+}
+
+static int launch_stem_conv1_tc(const void* x, int x_u8, const float* norm6, const void* wtc, const float* b, void* y, int B, int R, int Cout, cudaStream_t st) {
   if (R % 2) return fail(EMBCLIP_EINVAL, "stem: resolution must be even");
   StemNorm nm;
   for (int c = 0; c < 3; ++c) { nm.scale[c] = norm6 ? norm6[c] : 1.f; nm.offset[c] = norm6 ? norm6[3 + c] : 0.f; }
+  // row-tiled variant (bulk-copied input rows, see aux_kernels.cuh) when rows are 16-B granular
+  static const bool gather_only = getenv("EMBCLIP_STEM_GATHER") != nullptr;
+  const size_t esz = x_u8 ? 1 : 4;
+  const bool rows_ok = (size_t(R) * 3 * esz) % 16 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0;
+  if (Cout == 64) {
+    if (!rows_ok) return fail(EMBCLIP_EINVAL, "stem: the 64-channel stem needs 16-B aligned frame rows (resolution %d)", R);
+    return x_u8 ? launch_stem_rows<uint8_t, 64>(x, wtc, b, y, B, R, nm, st) : launch_stem_rows<float, 64>(x, wtc, b, y, B, R, nm, st);
+  }
+  if (Cout != 32) return fail(EMBCLIP_EINVAL, "stem conv1: Cout %d not built (32 or 64)", Cout);
+  if (!gather_only && rows_ok)
+    return x_u8 ? launch_stem_rows<uint8_t, 32>(x, wtc, b, y, B, R, nm, st) : launch_stem_rows<float, 32>(x, wtc, b, y, B, R, nm, st);
   static bool attr = false;
   if (!attr) {
     CUDA_TRY(cudaFuncSetAttribute(stem_conv1_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemTcSmem));
     CUDA_TRY(cudaFuncSetAttribute(stem_conv1_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemTcSmem));
     attr = true;
-  }
-  // row-tiled variant (bulk-copied input rows, see aux_kernels.cuh) when rows are 16-B granular and one output row fits a tile
-  static const bool gather_only = getenv("EMBCLIP_STEM_GATHER") != nullptr;
-  const size_t esz = x_u8 ? 1 : 4;
-  if (!gather_only && R / 2 <= 128 && (size_t(R) * 3 * esz) % 16 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0) {
-    const int stage_bytes = x_u8 ? stem_rows_stage_bytes<uint8_t>(R) : stem_rows_stage_bytes<float>(R);
-    const size_t smem = 1024 + 32768 + 8192 + size_t(kStemRowsStages) * stage_bytes + 64;
-    static size_t attr_f = 0, attr_u = 0;
-    size_t& cur = x_u8 ? attr_u : attr_f;
-    if (smem > cur) {
-      if (x_u8) CUDA_TRY(cudaFuncSetAttribute(stem_conv1_rows_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      else CUDA_TRY(cudaFuncSetAttribute(stem_conv1_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      cur = smem;
-    }
-    const long long row_tiles = (long long)B * (R / 2);
-    int per_sm = int((227u * 1024u) / smem);
-    if (per_sm > 4) per_sm = 4;
-    if (per_sm < 1) per_sm = 1;
-    long long g = (long long)num_sms() * per_sm;
-    if (g > row_tiles) g = row_tiles;
-    if (g <= 0) return 0;
-    if (x_u8)
-      CUDA_TRY(launch_pdl(stem_conv1_rows_kernel<uint8_t>, dim3((unsigned)g), dim3(128), smem, st, reinterpret_cast<const uint8_t*>(x),
-                          reinterpret_cast<const __half*>(wtc), b, reinterpret_cast<__half*>(y), B, R, nm));
-    else
-      CUDA_TRY(launch_pdl(stem_conv1_rows_kernel<float>, dim3((unsigned)g), dim3(128), smem, st, reinterpret_cast<const float*>(x),
-                          reinterpret_cast<const __half*>(wtc), b, reinterpret_cast<__half*>(y), B, R, nm));
-    return 0;
   }
   const long long tiles = ((long long)B * (R / 2) * (R / 2) + 127) / 128;
   long long grid = (long long)num_sms() * 4;
@@ -657,6 +670,7 @@ struct embclip_rn50 {
   int embed = 0, fres = 0, tokens = 0;
   int act_trunk_f32 = -1;
   int p_stem_wtc = -1;
+  bool attn_ok = true;           // false: more than 64 tokens, the attention-pool head is not in the plan
   // fork / join plumbing for ops marked `side` (identity-branch pools, layout heads): they overlap the tensor-bound
   // kernels that do not depend on them.  Created lazily on the device of the first forward.
   cudaStream_t side_stream = nullptr;
@@ -721,34 +735,36 @@ static int add_pool(embclip_rn50* m, const std::string& name, int in0) {
 extern "C" int embclip_rn50_create(const embclip_rn50_cfg* cfg, embclip_rn50_t* out) {
   if (!cfg || !out) return fail(EMBCLIP_EINVAL, "rn50_create: null argument");
   const int width = cfg->width, R = cfg->input_resolution;
-  if (width != 64) return fail(EMBCLIP_EINVAL, "rn50_create: only width 64 (RN50 / RN101) is built, got %d", width);
+  if (width != 64 && width != 96) return fail(EMBCLIP_EINVAL, "rn50_create: width 64 (RN50 / RN101) and 96 (RN50x16) are built, got %d", width);
   if (R <= 0 || R % 32) return fail(EMBCLIP_EINVAL, "rn50_create: input_resolution must be a positive multiple of 32");
   for (int i = 0; i < 4; ++i)
     if (cfg->layers[i] < 1) return fail(EMBCLIP_EINVAL, "rn50_create: layers[%d] < 1", i);
   const int embed = width * 32, fres = R / 32, L = fres * fres + 1;
   if (cfg->heads <= 0 || embed % cfg->heads || embed / cfg->heads != 64)
     return fail(EMBCLIP_EINVAL, "rn50_create: head dim must be 64 (embed %d heads %d)", embed, cfg->heads);
-  if (L > 64) return fail(EMBCLIP_EINVAL, "rn50_create: attention pool supports at most 64 tokens (got %d)", L);
-  if (cfg->output_dim % 32) return fail(EMBCLIP_EINVAL, "rn50_create: output_dim must be a multiple of 32");
+  const bool attn_ok = L <= 64 && cfg->output_dim > 0;   // output_dim 0 = "no attention-pool head" (positional embedding of another resolution)      // (RN50x16 at its native 384 x 384 has 145 tokens: trunk and avg-pool heads only)
+  if (cfg->output_dim < 0 || cfg->output_dim % 32) return fail(EMBCLIP_EINVAL, "rn50_create: output_dim must be a non-negative multiple of 32");
 
   embclip_rn50* m = new embclip_rn50();
   m->cfg = *cfg;
-  m->embed = embed; m->fres = fres; m->tokens = L;
+  m->embed = embed; m->fres = fres; m->tokens = L; m->attn_ok = attn_ok;
+  // the stem's width/2 channels are carried in a multiple of 32 (width 96: 48 real + 16 zero-weight channels, exact)
+  const int stem_c = (width / 2 + 31) / 32 * 32;
 
   // ---- stem
   {
     Op op;
     op.kind = K_STEM1;
     op.name = "stem.conv1";
-    op.cout = width / 2;
-    op.wp = add_param(m, "stem.conv1.w", EMBCLIP_DTYPE_F32, {27, width / 2});
-    op.bp = add_param(m, "stem.conv1.b", EMBCLIP_DTYPE_F32, {width / 2});
-    m->p_stem_wtc = add_param(m, "stem.conv1.wtc", EMBCLIP_DTYPE_F16, {width / 2, 128});   // hi/lo-split rows for the tensor-core stem
-    op.out = add_act(m, "stem.conv1", EMBCLIP_DTYPE_F16, R / 2, R / 2, width / 2);
+    op.cout = stem_c;
+    op.wp = add_param(m, "stem.conv1.w", EMBCLIP_DTYPE_F32, {27, stem_c});
+    op.bp = add_param(m, "stem.conv1.b", EMBCLIP_DTYPE_F32, {stem_c});
+    m->p_stem_wtc = add_param(m, "stem.conv1.wtc", EMBCLIP_DTYPE_F16, {stem_c, 128});   // hi/lo-split rows for the tensor-core stem
+    op.out = add_act(m, "stem.conv1", EMBCLIP_DTYPE_F16, R / 2, R / 2, stem_c);
     m->ops.push_back(op);
   }
   int t = (int)m->acts.size() - 1;
-  t = add_conv(m, "stem.conv2", t, -1, -1, 9, width / 2, 1);
+  t = add_conv(m, "stem.conv2", t, -1, -1, 9, stem_c, 1);
   t = add_conv(m, "stem.conv3", t, -1, -1, 9, width, 1, 0, /*pool=*/1);   // AvgPool2d(2) fused into the epilogue
 
   // ---- bottleneck stages
@@ -786,7 +802,7 @@ extern "C" int embclip_rn50_create(const embclip_rn50_cfg* cfg, embclip_rn50_t* 
     op2.kind = K_AVGHEAD; op2.name = "head.avgpool"; op2.head = H_AVG; op2.in0 = t; op2.out = -3; op2.side = 1;
     m->ops.push_back(op2);
   }
-  {
+  if (attn_ok) {
     const int heads = cfg->heads, E = embed;
     const int p_pos = add_param(m, "attnpool.pos", EMBCLIP_DTYPE_F32, {L, E});
     Op tk;
@@ -911,9 +927,9 @@ static int run_op(embclip_rn50* m, const Op& op, const std::vector<uint64_t>& of
   switch (op.kind) {
     case K_STEM1: {
       static const bool cuda_core = getenv("EMBCLIP_STEM_CUDA_CORE") != nullptr;       // first version, kept for A/B timing
-      if (!cuda_core && op.cout == 32)
+      if ((!cuda_core && op.cout == 32) || op.cout == 64)
         return launch_stem_conv1_tc(frames.ptr, frames.u8, frames.u8 ? frames.norm : nullptr, param_ptr(m->p_stem_wtc),
-                                    (const float*)param_ptr(op.bp), act_ptr(op.out), B, m->cfg.input_resolution, st);
+                                    (const float*)param_ptr(op.bp), act_ptr(op.out), B, m->cfg.input_resolution, op.cout, st);
       return launch_stem_conv1(frames.ptr, frames.u8, frames.u8 ? frames.norm : nullptr, (const float*)param_ptr(op.wp),
                                (const float*)param_ptr(op.bp), act_ptr(op.out), B, m->cfg.input_resolution, op.cout, st);
     }
@@ -1008,6 +1024,7 @@ static int forward_impl(embclip_rn50* m, const FramesIn& frames, int B, float* o
                         uint64_t ws_bytes, cudaStream_t st, float* op_ms, char* names, int max_ops) {
   if (!m || !frames.ptr || !ws || B <= 0) return fail(EMBCLIP_EINVAL, "forward: null argument or empty batch");
   if (!m->blob) return fail(EMBCLIP_ESTATE, "forward: weights not bound (call embclip_rn50_bind_weights first)");
+  if (o_attn && !m->attn_ok) return fail(EMBCLIP_EINVAL, "forward: the attention-pool head is built for at most 64 tokens (this plan has %d)", m->tokens);
   const uint64_t need = embclip_rn50_workspace_bytes(m, B);
   if (ws_bytes < need) return fail(EMBCLIP_ENOSPC, "forward: workspace %llu B < required %llu B", (unsigned long long)ws_bytes, (unsigned long long)need);
   if (reinterpret_cast<uintptr_t>(ws) % 1024) return fail(EMBCLIP_EINVAL, "forward: workspace must be 1024-B aligned");

@@ -27,16 +27,28 @@ class ClipRN50Encoder:
     CLIP_RGB_MEANS = (0.48145466, 0.4578275, 0.40821073)
     CLIP_RGB_STDS = (0.26862954, 0.26130258, 0.27577711)
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device: torch.device | str = "cuda:0"):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device: torch.device | str = "cuda:0",
+                 input_resolution: Optional[int] = None):
+        """``input_resolution``: run the trunk at another resolution than the checkpoint's attention pool was trained for
+        (AllenAct feeds RN50x16 -- native 384 x 384 -- with 224 x 224 frames and uses the trunk / avg-pool outputs only).
+        The 'attnpool' head exists only when the positional embedding matches the resolution and has at most 64 tokens."""
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("embclip_b200 has no CPU path: ClipRN50Encoder needs a CUDA (sm_100a) device")
         cfg = infer_rn_cfg(state_dict)
+        native = cfg["input_resolution"]
+        if input_resolution is not None:
+            cfg["input_resolution"] = int(input_resolution)
+        tokens = (cfg["input_resolution"] // 32) ** 2 + 1
+        self.has_attnpool = cfg["input_resolution"] == native and tokens <= 64
+        if not self.has_attnpool:
+            cfg["input_resolution_native"] = native
         self.cfg = cfg
         c = _lib.RN50Cfg()
         c.layers[:] = cfg["layers"]
-        c.width, c.heads, c.output_dim, c.input_resolution = cfg["width"], cfg["heads"], cfg["output_dim"], cfg["input_resolution"]
+        c.width, c.heads, c.input_resolution = cfg["width"], cfg["heads"], cfg["input_resolution"]
+        c.output_dim = cfg["output_dim"] if self.has_attnpool else 0          # 0: plan without the attention-pool head
         self._h = C.c_void_p()
         _lib.check(self.lib.embclip_rn50_create(C.byref(c), C.byref(self._h)))
         self.param_infos = self._param_infos()
@@ -93,6 +105,10 @@ class ClipRN50Encoder:
     def _outputs(self, batch: int, want: Iterable[str]) -> Dict[str, torch.Tensor]:
         outs = {}
         for k in want:
+            if k == "attnpool" and not self.has_attnpool:
+                raise ValueError("the 'attnpool' head is not available: the positional embedding is for "
+                                 f"{self.cfg.get('input_resolution_native', self.cfg['input_resolution'])} x "
+                                 f"{self.cfg.get('input_resolution_native', self.cfg['input_resolution'])} frames and the library builds it for at most 64 tokens")
             if k == "trunk":
                 outs[k] = torch.empty(batch, self.embed, self.fres, self.fres, dtype=torch.float32, device=self.device)
             elif k == "avgpool":

@@ -64,7 +64,14 @@ def packed_tensors(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     sd = strip_visual_prefix(sd)
     out: Dict[str, torch.Tensor] = {}
 
+    # The library carries the stem's width/2 channels in a multiple of 32 (RN50x16: 48 -> 64).  The extra channels get zero
+    # weights and zero bias, so they are exactly 0 after ReLU and contribute nothing downstream.
+    c_half = sd["conv1.weight"].shape[0]
+    c_pad = (c_half + 31) // 32 * 32
+    pad_out = lambda w_, b_: (torch.nn.functional.pad(w_, (0, 0, 0, 0, 0, 0, 0, c_pad - w_.shape[0])), torch.nn.functional.pad(b_, (0, c_pad - b_.shape[0])))
+    pad_in = lambda w_: torch.nn.functional.pad(w_, (0, 0, 0, 0, 0, c_pad - w_.shape[1]))
     w, b = fold_bn(sd, "conv1", "bn1")
+    w, b = pad_out(w, b)
     out["stem.conv1.w"] = w.permute(2, 3, 1, 0).reshape(27, -1).contiguous()         # [(kh,kw,ci), co] fp32
     out["stem.conv1.b"] = b
     # tensor-core stem: weight rows [w_hi | w_hi | w_lo | 0] against im2col rows [v_hi | v_lo | v_hi | 0] (32-wide slots, 27 used)
@@ -76,6 +83,9 @@ def packed_tensors(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     out["stem.conv1.wtc"] = wtc
     for i in (2, 3):
         w, b = fold_bn(sd, f"conv{i}", f"bn{i}")
+        w = pad_in(w)
+        if i == 2:
+            w, b = pad_out(w, b)
         out[f"stem.conv{i}.w"] = _kmajor(w).half()
         out[f"stem.conv{i}.b"] = b
 

@@ -91,6 +91,8 @@ def load_clip_visual_state_dict(clip_model_type: str, state_dict: Optional[Dict[
         pass
     if os.environ.get("EMBCLIP_SYNTHETIC_WEIGHTS") == "1":
         from .synthetic import synthetic_rn50_state_dict
+        if clip_model_type == "RN50x16":
+            return synthetic_rn50_state_dict(seed=1234, layers=(6, 8, 18, 8), width=96, output_dim=768, input_resolution=384)
         return synthetic_rn50_state_dict(seed=1234)
     raise RuntimeError(
         f"ClipResNetPreprocessor: no weights for '{clip_model_type}': pass clip_state_dict=..., set "
@@ -103,10 +105,13 @@ class ClipResNetEmbedder:
     [B,3,224,224] -> [B,2048,7,7] (pool=False) or [B,2048] (pool=True, adaptive average pool).
     Always frozen / eval (BatchNorm statistics are folded into the conv weights at construction)."""
 
-    def __init__(self, clip_visual_state_dict: Dict[str, torch.Tensor], pool: bool = True, device: Any = "cuda:0"):
+    def __init__(self, clip_visual_state_dict: Dict[str, torch.Tensor], pool: bool = True, device: Any = "cuda:0",
+                 input_resolution: int = 224):
         from .encoder import ClipRN50Encoder
         self.pool = pool
-        self.encoder = ClipRN50Encoder(clip_visual_state_dict, device)
+        # AllenAct's RGB sensor renders 224 x 224 for every CLIP ResNet (RN50x16's native 384 only matters to its attention
+        # pool, which this embedder never calls): the trunk plan is built for the frames it will actually see
+        self.encoder = ClipRN50Encoder(clip_visual_state_dict, device, input_resolution=input_resolution)
 
     def eval(self) -> "ClipResNetEmbedder":
         return self
@@ -129,7 +134,7 @@ class ClipResNetPreprocessor(_Base):
 
     CLIP_RGB_MEANS = (0.48145466, 0.4578275, 0.40821073)
     CLIP_RGB_STDS = (0.26862954, 0.26130258, 0.27577711)
-    SUPPORTED = {"RN50": (2048, 7, 7)}
+    SUPPORTED = {"RN50": (2048, 7, 7), "RN50x16": (3072, 7, 7)}     # output shapes AllenAct declares at 224 x 224 input
 
     def __init__(self, rgb_input_uuid: str, clip_model_type: str, pool: bool,
                  device: Optional[torch.device] = None, device_ids: Optional[Sequence[Any]] = None,

@@ -48,7 +48,7 @@ typedef struct {
   int32_t layers[4];         /* (3,4,6,3) for RN50                         */
   int32_t width;             /* 64                                         */
   int32_t heads;             /* 32 attention-pool heads                    */
-  int32_t output_dim;        /* 1024                                       */
+  int32_t output_dim;        /* 1024 (RN50x16: 768); 0 = plan without the attention-pool head (trunk / avg-pool only) */
   int32_t input_resolution;  /* 224                                        */
 } embclip_rn50_cfg;
 
@@ -63,7 +63,8 @@ typedef struct {
   uint64_t nbytes;
 } embclip_param_info;
 
-/* Build the layer table.  Needs no GPU. */
+/* Build the layer table.  Needs no GPU.  width 64 (RN50, RN101) or 96 (RN50x16: the stem's 48 channels are carried as 64,
+ * 16 of them zero); the attention-pool head is planned only for (input_resolution / 32)^2 + 1 <= 64 tokens. */
 int embclip_rn50_create(const embclip_rn50_cfg* cfg, embclip_rn50_t* out);
 int embclip_rn50_destroy(embclip_rn50_t h);
 int embclip_rn50_num_params(embclip_rn50_t h);

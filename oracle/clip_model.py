@@ -298,6 +298,16 @@ def build_rn50(embed_dim=1024) -> CLIP:
                 transformer_width=512, transformer_heads=8, transformer_layers=12)
 
 
+def build_rn50x16(embed_dim=768, image_resolution=384) -> CLIP:
+    """CLIP-RN50x16 (`clip.load('RN50x16')`): layers (6,8,18,8), width 96, 48 heads, 384 x 384, embed 768 -- the second encoder
+    AllenAct's ClipResNetPreprocessor accepts.  `image_resolution=224` builds the attention pool
+    for the 7 x 7 grid AllenAct's 224 x 224 frames produce (a synthetic-weights convenience: the real checkpoint's positional
+    embedding is 12 x 12 + 1, and AllenAct never calls its attention pool)."""
+    return CLIP(embed_dim=embed_dim, image_resolution=image_resolution, vision_layers=(6, 8, 18, 8), vision_width=96,
+                vision_patch_size=None, context_length=77, vocab_size=49408,
+                transformer_width=768, transformer_heads=12, transformer_layers=12)
+
+
 def build_vit_b32(embed_dim=512) -> CLIP:
     return CLIP(embed_dim=embed_dim, image_resolution=224, vision_layers=12, vision_width=768,
                 vision_patch_size=32, context_length=77, vocab_size=49408,
@@ -324,7 +334,9 @@ def init_synthetic_rn50_visual(visual: ModifiedResNet, seed: int = 1234) -> Modi
     arithmetic of the path is).  strict=True doubles as a check that the restated module has exactly the
     official state-dict keys."""
     from embclip_b200.synthetic import synthetic_rn50_state_dict
-    visual.load_state_dict(synthetic_rn50_state_dict(seed, output_dim=visual.output_dim,
+    layers = tuple(len(getattr(visual, f"layer{i}")) for i in (1, 2, 3, 4))
+    visual.load_state_dict(synthetic_rn50_state_dict(seed, layers=layers, width=visual.conv3.out_channels,
+                                                     output_dim=visual.output_dim,
                                                      input_resolution=visual.input_resolution), strict=True)
     return visual
 

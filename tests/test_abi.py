@@ -69,10 +69,30 @@ def test_plan_queries_without_gpu(built_lib):
     assert lib.embclip_rn50_forward(h, None, 1, None, None, None, None, 0, None) == -1
     bad = _lib.RN50Cfg()
     bad.layers[:] = (3, 4, 6, 3)
-    bad.width, bad.heads, bad.output_dim, bad.input_resolution = 96, 48, 768, 384
+    bad.width, bad.heads, bad.output_dim, bad.input_resolution = 80, 40, 640, 224
     h2 = C.c_void_p()
     assert lib.embclip_rn50_create(C.byref(bad), C.byref(h2)) == -1
     assert b"width" in lib.embclip_last_error()
+    # RN50x16 (width 96) at its native 384 x 384: 145 tokens -> planned without the attention-pool head; at AllenAct's 224 x 224
+    # with output_dim 0 (checkpoint positional embedding does not fit) likewise; stem channels are carried as 64
+    x16 = _lib.RN50Cfg()
+    x16.layers[:] = (6, 8, 18, 8)
+    x16.width, x16.heads, x16.output_dim, x16.input_resolution = 96, 48, 768, 384
+    h3 = C.c_void_p()
+    assert lib.embclip_rn50_create(C.byref(x16), C.byref(h3)) == 0
+    names = {}
+    for i in range(lib.embclip_rn50_num_params(h3)):
+        pi = _lib.ParamInfo()
+        assert lib.embclip_rn50_param_info(h3, i, C.byref(pi)) == 0
+        names[pi.name.decode()] = tuple(pi.shape[:pi.ndim])
+    assert names["stem.conv1.w"] == (27, 64) and names["stem.conv2.w"] == (64, 9 * 64) and names["stem.conv3.w"] == (96, 9 * 64)
+    assert names["layer4.7.conv3.w"] == (3072, 768) and not any(n.startswith("attnpool") for n in names)
+    assert lib.embclip_rn50_launches_per_forward(h3, 1, 1, 0) == 3 + 3 * 40 + 3 + 2
+    assert lib.embclip_rn50_destroy(h3) == 0
+    x16.input_resolution = 224
+    assert lib.embclip_rn50_create(C.byref(x16), C.byref(h3)) == 0
+    assert any(lib.embclip_rn50_param_info(h3, i, C.byref(pi)) == 0 and pi.name.startswith(b"attnpool") for i in range(lib.embclip_rn50_num_params(h3)))
+    assert lib.embclip_rn50_destroy(h3) == 0
     assert lib.embclip_rn50_destroy(h) == 0
 
 
