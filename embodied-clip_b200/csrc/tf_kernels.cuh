@@ -18,12 +18,26 @@ vit_patchify_kernel(const float* __restrict__ x, __half* __restrict__ y, int B, 
   const int g = R / PS;
   const int row_elems = PS * 3, patch_elems = PS * row_elems;
   const long long total = (long long)B * g * g;
+  const bool vec8 = row_elems % 8 == 0 && (R * 3) % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0;
   for (long long i = blockIdx.x; i < total; i += gridDim.x) {
     const int px = int(i % g);
     const int py = int((i / g) % g);
     const int b = int(i / ((long long)g * g));
     const float* src = x + (((size_t)b * R + (size_t)py * PS) * R + (size_t)px * PS) * 3;
     __half* dst = y + (size_t)i * patch_elems;
+    if (vec8) {
+      // a patch row is PS*3 contiguous floats: 8 per thread (two 16-B loads, one 16-B store)
+      const int vpr = row_elems / 8;
+      for (int j = threadIdx.x; j < PS * vpr; j += blockDim.x) {
+        const int kh = j / vpr, v = j - kh * vpr;
+        const float4* s4 = reinterpret_cast<const float4*>(src + (size_t)kh * R * 3 + v * 8);
+        const float4 a = __ldg(s4), c = __ldg(s4 + 1);
+        uint4 o;
+        o.x = pack_half2(a.x, a.y); o.y = pack_half2(a.z, a.w); o.z = pack_half2(c.x, c.y); o.w = pack_half2(c.z, c.w);
+        *reinterpret_cast<uint4*>(dst + kh * row_elems + v * 8) = o;
+      }
+      continue;
+    }
     for (int j = threadIdx.x; j < patch_elems; j += blockDim.x) {
       const int kh = j / row_elems, r = j - kh * row_elems;
       dst[j] = __float2half_rn(__ldg(src + (size_t)kh * R * 3 + r));
