@@ -297,7 +297,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           for (int i = 0; i < CH; ++i) f[i] = fmaxf(f[i], 0.f);
         } else if (p.relu == 2) {
 #pragma unroll
-          for (int i = 0; i < CH; ++i) f[i] = f[i] / (1.f + __expf(-1.702f * f[i]));
+          for (int i = 0; i < CH; ++i) f[i] = __fdividef(f[i], 1.f + __expf(-1.702f * f[i]));
         }
         if (p.out_f32) {
           if (row_ok) {

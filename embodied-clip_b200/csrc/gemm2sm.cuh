@@ -314,22 +314,51 @@ gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int i = 0; i < CH; ++i) f[i] = fmaxf(f[i], 0.f);
           } else if (p.relu == 2) {
 #pragma unroll
-            for (int i = 0; i < CH; ++i) f[i] = f[i] / (1.f + __expf(-1.702f * f[i]));
+            for (int i = 0; i < CH; ++i) f[i] = __fdividef(f[i], 1.f + __expf(-1.702f * f[i]));
           }
           if (p.out_f32) {
-            if (row_ok) {
-              float4* op = reinterpret_cast<float4*>(p.out_f32_ptr + size_t(grow) * p.N + n0 + col);
-              if (p.res_f32_ptr) {
-                const float4* rp = reinterpret_cast<const float4*>(p.res_f32_ptr + size_t(grow) * p.N + n0 + col);
+            // fp32 rows (+ fp32 residual): a thread owns one ROW of the 32 x 32 block, so direct global access would touch 32
+            // cache lines per instruction (the first version: the ViT out / c_proj GEMMs ran at 300 / 950 TFLOP/s, LSU-bound).
+            // Go through a per-warp scratch block in the (otherwise unused) staging buffers instead: global <-> scratch is
+            // coalesced (lane = (row % 4, 16-B piece): 4 full lines per instruction), scratch <-> registers is row-wise.
+            static_assert(CH == 32, "fp32 epilogue block is 32 x 32");
+            constexpr uint32_t kPitch = 144;                           // 128 B + 16 B pad: conflict-free for 8-lane phases
+            const uint32_t scr = sC + uint32_t(warp - 2) * (32u * kPitch);
+            const int sub_r = lane >> 3, piece = lane & 7;
+            const size_t gbase = size_t(m0 + q * 32) * p.N + n0 + col;
+            if (p.res_f32_ptr) {
 #pragma unroll
-                for (int i = 0; i < CH / 4; ++i) {
-                  const float4 r = rp[i];
-                  f[4 * i] += r.x; f[4 * i + 1] += r.y; f[4 * i + 2] += r.z; f[4 * i + 3] += r.w;
-                }
+              for (int k = 0; k < 8; ++k) {
+                const int r = 4 * k + sub_r;
+                float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m0 + q * 32 + r < p.M) v4 = *(reinterpret_cast<const float4*>(p.res_f32_ptr + gbase + size_t(r) * p.N) + piece);
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(scr + uint32_t(r) * kPitch + uint32_t(piece) * 16u),
+                             "f"(v4.x), "f"(v4.y), "f"(v4.z), "f"(v4.w) : "memory");
               }
+              __syncwarp();
 #pragma unroll
-              for (int i = 0; i < CH / 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+              for (int i = 0; i < 8; ++i) {
+                float4 r4;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r4.x), "=f"(r4.y), "=f"(r4.z), "=f"(r4.w)
+                             : "r"(scr + uint32_t(lane) * kPitch + uint32_t(i) * 16u));
+                f[4 * i] += r4.x; f[4 * i + 1] += r4.y; f[4 * i + 2] += r4.z; f[4 * i + 3] += r4.w;
+              }
+              __syncwarp();
             }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(scr + uint32_t(lane) * kPitch + uint32_t(i) * 16u),
+                           "f"(f[4 * i]), "f"(f[4 * i + 1]), "f"(f[4 * i + 2]), "f"(f[4 * i + 3]) : "memory");
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int r = 4 * k + sub_r;
+              float4 o4;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o4.x), "=f"(o4.y), "=f"(o4.z), "=f"(o4.w)
+                           : "r"(scr + uint32_t(r) * kPitch + uint32_t(piece) * 16u));
+              if (m0 + q * 32 + r < p.M) *(reinterpret_cast<float4*>(p.out_f32_ptr + gbase + size_t(r) * p.N) + piece) = o4;
+            }
+            __syncwarp();
           } else {
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
