@@ -229,7 +229,7 @@ attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int L
 //   O = P V              tcgen05.mma 128 x 64 x 128; V is the MN-major operand (keys are its K dimension)  -> TMEM
 //   out = O / rowsum     fp16, 128 B per row
 // The cross-sequence quarter of S is computed and discarded: the tensor pipe is ~30x faster than the CUDA-core loop above,
-// so the waste is free.  ~82 KB smem and 256 TMEM columns per CTA: two CTAs per SM hide the load -> MMA -> softmax -> MMA chain.
+// so the waste is free.  49 KB smem and 128 TMEM columns per CTA: four CTAs per SM hide the load -> MMA -> softmax -> MMA chain.
 // ------------------------------------------------------------------------------------------------
 struct AttnTcParams {
   int rows;        // S * L rows of qkv
@@ -238,14 +238,16 @@ struct AttnTcParams {
   int causal;
   __half* out;     // [rows][D]
 };
-constexpr int kAttnTcSmem = 1024 + 3 * 16384 + 32768 + 64;
+constexpr int kAttnTcSmem = 1024 + 3 * 16384 + 64;
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, 4)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = base, sK = base + 16384, sV = base + 32768, sP = base + 49152;
-  const uint32_t bar_load = sP + 32768, bar_s = bar_load + 8, bar_o = bar_load + 16, tmem_slot = bar_load + 24;
+  // P (128 x 128 fp16, 32 KB) overwrites Q and K, which are dead once S = Q K^T has been accumulated; O likewise reuses the
+  // first 64 TMEM columns of S after every thread has read its S row: 49 KB smem + 128 TMEM columns -> four CTAs per SM
+  const uint32_t sQ = base, sK = base + 16384, sV = base + 32768, sP = base;
+  const uint32_t bar_load = base + 49152, bar_s = bar_load + 8, bar_o = bar_load + 16, tmem_slot = bar_load + 24;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, h = blockIdx.y;
   const int r0 = tile * p.nseq * p.L;
@@ -258,13 +260,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParam
     mbar_init(bar_o, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  if (warp == 0) tmem_alloc<128>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  const uint32_t tS = tmem_base, tO = tmem_base;
 
   if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(bar_load, 3 * 16384);
@@ -370,7 +372,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParam
   __syncthreads();
   if (warp == 0) {
     tcgen05_fence_after();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<128>(tmem_base);
   }
 }
 
