@@ -74,6 +74,40 @@ def time_cpu_oracle(model, batch, iters, warmup):
     return batch * len(ts) / sum(ts), sum(ts) / len(ts)
 
 
+def time_gpu_eager_oracle(model, dev, batch, iters=10, warmup=3):
+    """The library bar on the same GPU: the restated PyTorch module run by torch eager (cuDNN / cuBLAS) on
+    `dev`, (a) fp32 NCHW -- what AllenAct's ClipResNetPreprocessor executes -- and (b) fp16 channels-last, the strongest library
+    configuration (the reference's in-tree CUDA call also runs CLIP in fp16).  Reported baselines like cpu_baseline; not shipped."""
+    import copy
+    import torch
+    out = {}
+    x32 = synthetic_frames(batch, seed=1).permute(0, 3, 1, 2).contiguous().to(dev)
+    for name, dtype, fmt in (("fp32_nchw", torch.float32, torch.contiguous_format), ("fp16_channels_last", torch.float16, torch.channels_last)):
+        try:
+            m = copy.deepcopy(model).to(dev, dtype).to(memory_format=fmt)
+            x = x32.to(dtype).contiguous(memory_format=fmt)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.no_grad():
+                for i in range(warmup + iters):
+                    if i == warmup:
+                        e0.record()
+                    t = m.trunk(x)
+                    a = m.attnpool(t)
+                    p = t.float().mean(dim=(2, 3))
+                    del t, a, p
+                e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / iters
+            out[name] = {"value": batch / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms}
+            del m, x
+            torch.cuda.empty_cache()
+        except Exception as e:                                   # a baseline must never take the bench down
+            out[name] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    out["what"] = (f"oracle/clip_model.py ModifiedResNet (trunk + attnpool + avgpool) under torch {torch.__version__} eager on the same GPU, "
+                   f"batch {batch}, cudnn.allow_tf32={torch.backends.cudnn.allow_tf32}, matmul.allow_tf32={torch.backends.cuda.matmul.allow_tf32}")
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 100 ms from before the warm-up; stop(t0, t1) keeps the
     samples whose timestamp falls inside the timed region [t0, t1] (wall clock), or -- if the region was shorter
@@ -476,7 +510,9 @@ def run_ours(args, rank, local_rank, world):
     top = sorted(prof, key=lambda x: -x[1])[:8]
     traffic, traffic_src = committed_traffic()
 
-    cpu_fps, cpu_sec = (None, None) if args.no_cpu else time_cpu_oracle(oracle_model(), 32, 4, 1)
+    ref_model = None if args.no_cpu else oracle_model()
+    cpu_fps, cpu_sec = (None, None) if args.no_cpu else time_cpu_oracle(ref_model, 32, 4, 1)
+    gpu_eager = None if args.no_cpu else time_gpu_eager_oracle(ref_model, dev, BATCH)
     line_ppo = ppo
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -501,6 +537,7 @@ def run_ours(args, rank, local_rank, world):
                      "whole_step_tflops": step_tflops, "whole_step_frac": step_tflops / sustained},
         "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": "fp32 PyTorch oracle, 32 frames x 4 iterations (1 warm-up)"},
+        "gpu_eager_baseline": gpu_eager,
         "top_ops_ms": top,
         "ppo_step": line_ppo,
         "vit_zero_shot": vit,
