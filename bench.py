@@ -334,6 +334,27 @@ def measured_peaks():
     return 1400.0, 1590.0, 6650.0, "fallback"
 
 
+def time_linear_probe_cpu(iters=200, warmup=20):
+    """BASELINE.json configs[0] (the reference's own CPU-runnable case): primitive_probing/train.py's LinearEncoder, one
+    training step (forward, BCE loss, backward, Adam) on cached 2048-d CLIP features, at the batch BASELINE names (32) and the
+    batch the code uses (128, train.py:136) -- microseconds per step on the host cores.  A reported figure, not a GPU target."""
+    import torch
+    from oracle.probe import LinearEncoder, probe_train_step
+    out = {}
+    for bs in (32, 128):
+        torch.manual_seed(1)                                       # train.py:117
+        m = LinearEncoder("clip_avgpool", "object_presence")
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+        x, y = torch.randn(bs, 2048), (torch.rand(bs, 52) < 0.1).float()
+        for i in range(warmup + iters):
+            if i == warmup:
+                t0 = time.perf_counter()
+            probe_train_step(m, opt, (x, y))
+        out[f"batch_{bs}_us_per_step"] = (time.perf_counter() - t0) / iters * 1e6
+    out["what"] = "oracle/probe.py LinearEncoder('clip_avgpool', 'object_presence'): forward + BCE + backward + Adam, host cores"
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -352,6 +373,7 @@ def run_reference(args, rank, world):
                          "sample": f"fp32 PyTorch oracle (oracle/clip_model.py), {sample} frames/step x {args.steps} steps, {cores} threads"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "linear_probe_cpu": time_linear_probe_cpu(),
     }
     print(json.dumps(line), flush=True)
 
@@ -538,6 +560,7 @@ def run_ours(args, rank, local_rank, world):
         "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": "fp32 PyTorch oracle, 32 frames x 4 iterations (1 warm-up)"},
         "gpu_eager_baseline": gpu_eager,
+        "linear_probe_cpu": None if args.no_cpu else time_linear_probe_cpu(),
         "top_ops_ms": top,
         "ppo_step": line_ppo,
         "vit_zero_shot": vit,
