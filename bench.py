@@ -168,11 +168,16 @@ class ClockSampler:
         return out
 
 
-def run_ppo_block(enc, dev, rank, world, rollouts, max_over_ranks, barrier, T=128, N=60):
+def run_ppo_block(enc, dev, rank, world, rollouts, max_over_ranks, barrier, T=128, N=60, global_samplers=None):
     """BASELINE configs 3 / 4: end-to-end PPO step on synthetic rollouts -- T x N frames encoded in T rollout steps of N
     (the faithful AllenAct schedule: the preprocessor sees one step of all samplers at a time), T act() calls, GAE, and
-    4 update passes with the flat-bucket gradient all-reduce.  Weak scaling: N samplers per GPU."""
+    4 update passes with the flat-bucket gradient all-reduce.  Weak scaling: N samplers per GPU.
+    global_samplers: BASELINE config 4 verbatim instead -- that many samplers in TOTAL, split across the ranks as evenly as
+    AllenAct distributes them (60 over 8 GPUs = 8,8,8,8,7,7,7,7): strong scaling, a few frames per rollout step per GPU."""
     import torch
+    strong = global_samplers is not None
+    if strong:
+        N = global_samplers // world + (1 if rank < global_samplers % world else 0)
     from embclip_b200.actor_critic import PPOTrainer, ResnetTensorNavActorCritic
     from embclip_b200.harness import SyntheticPPOStep
     model = ResnetTensorNavActorCritic(device=dev, seed=1)
@@ -180,7 +185,7 @@ def run_ppo_block(enc, dev, rank, world, rollouts, max_over_ranks, barrier, T=12
     stepper = SyntheticPPOStep(enc, model, trainer, T=T, N=N, seed=10 + rank)
     host = synthetic_frames_u8(N, seed=200 + rank).pin_memory()     # e2e leg: raw uint8 frames, normalised in the stem kernel
     frames = synthetic_frames(N, seed=200 + rank).to(dev)           # device-resident leg: fp32 normalised (the AllenAct boundary dtype)
-    grows = T * N * world
+    grows = T * global_samplers if strong else T * N * world
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     # device-resident
@@ -241,12 +246,12 @@ def run_ppo_block(enc, dev, rank, world, rollouts, max_over_ranks, barrier, T=12
     s1.record(main)
     barrier()
     e2e_ms = max_over_ranks(s0.elapsed_time(s1)) / rollouts
-    frames_per_step = T * N * world
+    frames_per_step = grows
     return {
         "metric": "frames/sec end-to-end PPO step (encode T x N frames in T rollout steps + act + GAE + 4 update passes)",
         "value": frames_per_step / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms, "rollouts_timed": rollouts,
-        "collect_ms": collect_ms, "update_ms": update_ms, "scaling": "weak",
-        "config": {"workload": "objectnav_ppo_step", "steps": T, "samplers_per_gpu": N, "update_repeats": 4, "num_mini_batch": 1,
+        "collect_ms": collect_ms, "update_ms": update_ms, "scaling": "strong" if strong else "weak",
+        "config": {"workload": "objectnav_ppo_step", "steps": T, "samplers_per_gpu": N, "samplers_total": grows // T, "update_repeats": 4, "num_mini_batch": 1,
                    "global_rows": grows,
                    "rollout_storage": "fp16 pixel rows on device (encode_rows -> act -> PackedFeatures); the AllenAct fp32 NCHW flow is SyntheticPPOStep(packed_rollout=False)",
                    "collective": "1 flat fp32 gradient all-reduce (13.9 MB) per update pass" if world > 1 else "none (1 GPU)"},
@@ -513,6 +518,9 @@ def run_ours(args, rank, local_rank, world):
 
     # ---------------- BASELINE configs 3 / 4: end-to-end PPO step (all ranks: the update all-reduces gradients)
     ppo = None if args.no_ppo else run_ppo_block(enc, dev, rank, world, args.ppo_rollouts, max_over_ranks, barrier)
+    # BASELINE config 4 as written (60 samplers in total over the ranks); identical to `ppo` on one GPU, so only timed for N > 1
+    ppo_strong = None if (args.no_ppo or world == 1) else run_ppo_block(enc, dev, rank, world, args.ppo_rollouts, max_over_ranks,
+                                                                       barrier, global_samplers=60)
     vit = None if args.no_vit else run_vit_block(dev, rank, world, max(10, K // 4), 5, max_over_ranks, barrier)
 
     if rank != 0:
@@ -563,6 +571,7 @@ def run_ours(args, rank, local_rank, world):
         "linear_probe_cpu": None if args.no_cpu else time_linear_probe_cpu(),
         "top_ops_ms": top,
         "ppo_step": line_ppo,
+        "ppo_step_60_samplers_total": ppo_strong,
         "vit_zero_shot": vit,
     }
     print(json.dumps(line), flush=True)
