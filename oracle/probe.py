@@ -83,4 +83,4 @@ def probe_train_step(model: LinearEncoder, optimizer: torch.optim.Optimizer, bat
     loss = model.compute_loss(batch)
     loss.backward()
     optimizer.step()
-    return float(loss)
+    return float(loss.detach())
