@@ -263,6 +263,58 @@ def run_ppo_block(enc, dev, rank, world, rollouts, max_over_ranks, barrier, T=12
     }
 
 
+def run_multi_rank_parity(dev, rank, world, T=8, samplers_total=None):
+    """Product-path check of SURVEY.md section 8(e): an N-rank PPOTrainer.update (samplers sharded the
+    AllenAct way, flat-bucket NCCL all-reduce) against a 1-rank update on the concatenated batch.  Every rank must end with
+    bit-identical parameters; rank 0's first-pass gradient and 4-pass parameter change are compared with the single-rank run
+    (differences = fp32 summation order of the sharded reduction)."""
+    import torch
+    import torch.distributed as dist
+    from embclip_b200.actor_critic import PPOTrainer, ResnetTensorNavActorCritic
+    from embclip_b200.distributed import shard_samplers
+    Ntot = samplers_total or (3 * world + 1)
+    g = torch.Generator().manual_seed(77)
+    full = dict(features=torch.randn(T, Ntot, 2048, 7, 7, generator=g).relu_(), goals=torch.randint(0, 12, (T, Ntot), generator=g),
+                masks=(torch.rand(T, Ntot, 1, generator=g) > 0.1).float(), memory=0.3 * torch.randn(1, Ntot, 512, generator=g),
+                actions=torch.randint(0, 6, (T, Ntot), generator=g), old_action_log_probs=-1.79 + 0.1 * torch.randn(T, Ntot, generator=g),
+                values=0.2 * torch.randn(T, Ntot, 1, generator=g), returns=0.5 * torch.randn(T, Ntot, 1, generator=g),
+                norm_adv_targ=torch.randn(T, Ntot, 1, generator=g))
+    s0, cnt = shard_samplers(Ntot, world, rank)
+    local = {k: (v[:, s0:s0 + cnt] if k != "memory" else v[:, s0:s0 + cnt]).contiguous().to(dev) for k, v in full.items()}
+    m = ResnetTensorNavActorCritic(device=dev, seed=5)
+    p0 = m.flat_params.data.clone()
+    tr = PPOTrainer(m, update_repeats=1)
+    tr.update(local, global_rows=T * Ntot)
+    g1 = tr.grads.clone()
+    for _ in range(3):
+        tr.update(local, global_rows=T * Ntot)
+    torch.cuda.synchronize()
+    bits = m.flat_params.data.view(torch.int32).to(torch.int64)
+    chk = torch.stack([bits.sum(), (bits * torch.arange(1, bits.numel() + 1, device=dev)).sum()])
+    allc = [torch.empty_like(chk) for _ in range(world)]
+    dist.all_gather(allc, chk)
+    identical = all(torch.equal(c, allc[0]) for c in allc)
+    out = None
+    if rank == 0:
+        m1 = ResnetTensorNavActorCritic(device=dev, seed=5)
+        tr1 = PPOTrainer(m1, update_repeats=1, distributed=False)
+        fd = {k: v.to(dev) for k, v in full.items()}
+        tr1.update(fd, global_rows=T * Ntot)
+        g1_ref = tr1.grads.clone()
+        for _ in range(3):
+            tr1.update(fd, global_rows=T * Ntot)
+        torch.cuda.synchronize()
+        rl = lambda a, b: float((a - b).norm() / b.norm())
+        out = {"world": world, "steps": T, "samplers_total": Ntot, "samplers_per_rank": [shard_samplers(Ntot, world, r)[1] for r in range(world)],
+               "params_bit_identical_across_ranks": bool(identical),
+               "grad_rel_l2_pass1_vs_1rank": rl(g1, g1_ref),
+               "param_change_rel_l2_4pass_vs_1rank": rl(m.flat_params.data - p0, m1.flat_params.data - p0),
+               "what": "N-rank PPOTrainer.update (NCCL flat all-reduce) vs 1-rank update on the concatenated batch, same init"}
+        assert identical, "multi-rank update left different parameters on different ranks"
+        assert out["grad_rel_l2_pass1_vs_1rank"] <= 1e-4, out
+    return out
+
+
 def run_vit_block(dev, rank, world, steps, warmup, max_over_ranks, barrier, total_batch=512, prompts=12):
     """BASELINE config 5: zero-shot ObjectNav path -- CLIP ViT-B/32 image tower + cached text tower + cosine-sim logits,
     512 frames per step split across the ranks (strong scaling; no collective: per-image logits are independent)."""
@@ -419,6 +471,14 @@ def run_ours(args, rank, local_rank, world):
         build.build()                       # no-op when the in-tree .so is up to date
     if world > 1:
         dist.barrier()
+    if args.parity_only:
+        if world < 2:
+            raise SystemExit("--parity-only needs WORLD_SIZE >= 2 (launch under torchrun)")
+        res = run_multi_rank_parity(dev, rank, world)
+        if rank == 0:
+            print(json.dumps({"multi_rank_parity": res}), flush=True)
+        dist.destroy_process_group()
+        return
     from embclip_b200.encoder import ClipRN50Encoder
     from embclip_b200.synthetic import synthetic_rn50_state_dict
     enc = ClipRN50Encoder(synthetic_rn50_state_dict(seed=1234), dev)
@@ -522,6 +582,7 @@ def run_ours(args, rank, local_rank, world):
     ppo_strong = None if (args.no_ppo or world == 1) else run_ppo_block(enc, dev, rank, world, args.ppo_rollouts, max_over_ranks,
                                                                        barrier, global_samplers=60)
     vit = None if args.no_vit else run_vit_block(dev, rank, world, max(10, K // 4), 5, max_over_ranks, barrier)
+    parity_n = None if (args.no_ppo or world == 1) else run_multi_rank_parity(dev, rank, world)
 
     if rank != 0:
         if world > 1:
@@ -573,6 +634,7 @@ def run_ours(args, rank, local_rank, world):
         "ppo_step": line_ppo,
         "ppo_step_60_samplers_total": ppo_strong,
         "vit_zero_shot": vit,
+        "multi_rank_parity": parity_n,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -589,6 +651,7 @@ def main():
     ap.add_argument("--no-ppo", action="store_true", help="skip the PPO-step block (BASELINE configs 3 / 4)")
     ap.add_argument("--no-vit", action="store_true", help="skip the ViT-B/32 zero-shot block (BASELINE config 5)")
     ap.add_argument("--ppo-rollouts", type=int, default=3, help="timed rollouts of the PPO-step block")
+    ap.add_argument("--parity-only", action="store_true", help="N > 1: run only the multi-rank update parity check and print its JSON")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

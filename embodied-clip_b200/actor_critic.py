@@ -126,6 +126,7 @@ class _ACFunction(torch.autograd.Function):
                                                    masks.data_ptr(), h0.data_ptr(), T, N, logits.data_ptr(), values.data_ptr(),
                                                    h_last.data_ptr(), ws.data_ptr(), ws.numel(), int(need_grad), _stream(dev)))
         ctx.model, ctx.T, ctx.N = model, T, N
+        ctx.ws_gen = model._touch_workspace()          # the forward's intermediates live in the model's shared workspace
         ctx.save_for_backward(flat_params, feats16, goals, masks, h0)
         return logits, values, h_last
 
@@ -141,6 +142,18 @@ class _ACFunction(torch.autograd.Function):
         grads = torch.zeros_like(flat_params)
         ws = model._workspace(T, N)
         with torch.cuda.device(dev):
+            if model._ws_gen != ctx.ws_gen:
+                # another forward()/act()/update() ran on this module since (a second minibatch, a bootstrap-value forward, a
+                # larger block that re-allocated the workspace): the saved intermediates are gone -- recompute them from the
+                # saved inputs instead of differentiating someone else's activations
+                H = plan.cfg["hidden"]
+                scratch = torch.empty(T * N * (A + 1) + N * H, dtype=torch.float32, device=dev)
+                _lib.check(plan.lib.embclip_ac_forward(plan._h, flat_params.data_ptr(), feats16.data_ptr(), goals.data_ptr(),
+                                                       masks.data_ptr(), h0.data_ptr(), T, N, scratch.data_ptr(),
+                                                       scratch[T * N * A:].data_ptr(), scratch[T * N * (A + 1):].data_ptr(),
+                                                       ws.data_ptr(), ws.numel(), 1, _stream(dev)))
+                model.recomputed_backwards += 1
+            model._touch_workspace()
             _lib.check(plan.lib.embclip_ac_backward(plan._h, flat_params.data_ptr(), feats16.data_ptr(), goals.data_ptr(),
                                                     masks.data_ptr(), h0.data_ptr(), T, N, dl.data_ptr(), dv.data_ptr(),
                                                     dh.data_ptr() if dh is not None else None, grads.data_ptr(), ws.data_ptr(),
@@ -186,11 +199,22 @@ class ResnetTensorNavActorCritic(nn.Module):
             raise RuntimeError("embclip_b200 ResnetTensorNavActorCritic has no CPU path: construct it on a CUDA device")
         self.flat_params = nn.Parameter(torch.zeros(self._plan.n_floats, dtype=torch.float32, device=dev))
         self._ws: Optional[torch.Tensor] = None
+        self._ws_gen = 0
+        self.recomputed_backwards = 0          # backward passes that had to re-run their forward (workspace overwritten in between)
         self._init_parameters(seed)
 
     # ------------------------------------------------------------------ parameters under upstream names
     def named_views(self) -> Dict[str, torch.Tensor]:
-        return {name: self.flat_params.data[off:off + n].view(shape) for name, shape, off, n in self._plan.params}
+        """Upstream-named views of the flat parameter tensor.  They are views of the Parameter itself (taken under
+        ``no_grad``), so an in-place write through one bumps ``flat_params._version`` and ``params_version()`` sees it
+        (views of ``.data`` would not share the counter)."""
+        with torch.no_grad():
+            return {name: self.flat_params[off:off + n].view(shape) for name, shape, off, n in self._plan.params}
+
+    def _touch_workspace(self) -> int:
+        """Every call that overwrites the shared workspace takes a new generation number (see ``_ACFunction.backward``)."""
+        self._ws_gen += 1
+        return self._ws_gen
 
     def _init_parameters(self, seed: Optional[int]) -> None:
         """Upstream initialisers: conv / embedding = torch defaults; GRU weights orthogonal, biases 0
@@ -218,23 +242,36 @@ class ResnetTensorNavActorCritic(nn.Module):
                     bound = (1.0 / w[0].numel()) ** 0.5
                     cpu.uniform_(-bound, bound, generator=g)
                 t.copy_(cpu)
+        self.mark_params_changed()
 
-    def state_dict(self, *args, **kwargs):                          # upstream key names, detached copies
-        return {k: t.clone() for k, t in self.named_views().items()}
+    # nn.Module checkpoint protocol under the upstream key names.  Implemented at the _save_to / _load_from level so the
+    # module also round-trips as a SUBMODULE (a parent's state_dict() passes destination / prefix and ignores the return value).
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        for k, t in self.named_views().items():
+            destination[prefix + k] = t if keep_vars else t.detach().clone()
 
-    def load_state_dict(self, state_dict, strict: bool = True):
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
         v = self.named_views()
-        missing = [k for k in v if k not in state_dict]
-        unexpected = [k for k in state_dict if k not in v]
-        if strict and (missing or unexpected):
-            raise RuntimeError(f"load_state_dict: missing {missing}, unexpected {unexpected}")
         with torch.no_grad():
             for k, t in v.items():
-                if k in state_dict:
-                    if tuple(state_dict[k].shape) != tuple(t.shape):
-                        raise RuntimeError(f"load_state_dict: '{k}' is {tuple(state_dict[k].shape)}, expected {tuple(t.shape)}")
-                    t.copy_(state_dict[k].to(t.device, torch.float32))
-        return missing, unexpected
+                key = prefix + k
+                if key not in state_dict:
+                    missing_keys.append(key)
+                    continue
+                src = state_dict[key]
+                if tuple(src.shape) != tuple(t.shape):
+                    error_msgs.append(f"size mismatch for {key}: copying a param with shape {tuple(src.shape)} from checkpoint, "
+                                      f"the shape in current model is {tuple(t.shape)}.")
+                    continue
+                t.copy_(src.to(t.device, torch.float32))
+        if strict:                           # this module has no children: every key under its prefix is its own
+            unexpected_keys.extend(key for key in state_dict if key.startswith(prefix) and key[len(prefix):] not in v)
+        self.mark_params_changed()           # the fp16 weight layouts cached by act() are stale now
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        if assign:
+            raise RuntimeError("load_state_dict(assign=True): parameters are views of one flat buffer and cannot be re-assigned")
+        return super().load_state_dict(state_dict, strict=strict)
 
     # ------------------------------------------------------------------ AllenAct ActorCriticModel surface
     @property
@@ -327,6 +364,7 @@ class ResnetTensorNavActorCritic(nn.Module):
                 raise ValueError(f"{name} must be a contiguous {dt} tensor of {n} elements on {dev}")
         logits = torch.empty(N, A, dtype=torch.float32, device=dev)
         ws = self._workspace(1, N)
+        self._touch_workspace()
         with torch.cuda.device(dev):
             _lib.check(self._plan.lib.embclip_ac_act(self._plan._h, self.flat_params.data_ptr(), self.params_version(), feats_rows.data_ptr(),
                                                      g.data_ptr(), m.data_ptr(), h0.data_ptr(), N, u.data_ptr(), actions.data_ptr(),
@@ -384,6 +422,18 @@ def compute_returns_gae(rewards: torch.Tensor, value_preds: torch.Tensor, masks:
 # ---------------------------------------------------------------------------------------------------
 # OnPolicyTrainer.update / backprop_step
 # ---------------------------------------------------------------------------------------------------
+class LinearDecay:
+    """allenact.utils.experiment_utils.LinearDecay [UPSTREAM]: multiplier going linearly from `startp` to `endp` over
+    `steps` environment steps, constant afterwards.  ``PPOTrainer(lr_schedule=LinearDecay(steps=ppo_steps))``."""
+
+    def __init__(self, steps: int, startp: float = 1.0, endp: float = 0.0):
+        self.steps, self.startp, self.endp = int(steps), float(startp), float(endp)
+
+    def __call__(self, epoch: int) -> float:
+        epoch = max(min(int(epoch), self.steps), 0)
+        return self.startp + (self.endp - self.startp) * (epoch / float(self.steps))
+
+
 class PPOTrainer:
     """update_repeats x (forward, PPO.loss, backward, gradient all-reduce, clip_grad_norm_(0.5), Adam(lr)).
 
@@ -392,11 +442,25 @@ class PPOTrainer:
 
     def __init__(self, model: ResnetTensorNavActorCritic, lr: float = 3e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  max_grad_norm: float = 0.5, update_repeats: int = 4, clip_param: float = 0.1, value_loss_coef: float = 0.5,
-                 entropy_coef: float = 0.01, process_group: Any = None):
-        self.model, self.lr, self.betas, self.eps = model, lr, betas, eps
+                 entropy_coef: float = 0.01, process_group: Any = None, lr_schedule: Optional[Any] = None,
+                 num_mini_batch: int = 1, distributed: bool = True, seed: int = 0):
+        """lr_schedule: a multiplier ``f(total_steps) -> float`` on the base lr (``LinearDecay``), applied the way AllenAct's
+        ``LambdaLR(optimizer, lr_lambda=LinearDecay(steps))`` + ``lr_scheduler.step(epoch=total_steps)`` does: the lr of an
+        update is ``lr * f(environment steps collected before it)``.  num_mini_batch: samplers are split into that many
+        contiguous chunks per update repeat, visited in shuffled order (RolloutStorage.recurrent_generator [UPSTREAM]).
+        distributed=False keeps the gradient local even inside an initialised process group (single-rank reference runs)."""
+        self.model, self.base_lr, self.betas, self.eps = model, lr, betas, eps
+        self.lr_schedule = lr_schedule
+        self.total_steps = 0                   # environment steps (global rows) consumed by update() so far
         self.max_grad_norm, self.update_repeats = max_grad_norm, update_repeats
         self.clip_param, self.value_loss_coef, self.entropy_coef = clip_param, value_loss_coef, entropy_coef
         self.process_group = process_group
+        self.distributed = bool(distributed)
+        self.num_mini_batch = int(num_mini_batch)
+        if self.num_mini_batch < 1:
+            raise ValueError("num_mini_batch must be >= 1")
+        import random
+        self._rng = random.Random(seed)         # mini-batch order (upstream: python's global `random.shuffle`)
         p = model.flat_params
         self.grads = torch.zeros_like(p.data)
         self.exp_avg = torch.zeros_like(p.data)
@@ -406,8 +470,19 @@ class PPOTrainer:
         self.step_count = 0
         self.kernel_launch_estimate = 0
 
+    @property
+    def lr(self) -> float:
+        """Learning rate the NEXT update will use."""
+        return self.base_lr * (float(self.lr_schedule(self.total_steps)) if self.lr_schedule is not None else 1.0)
+
+    @lr.setter
+    def lr(self, value: float) -> None:
+        self.base_lr = float(value)
+
     def _world(self) -> int:
         import torch.distributed as dist
+        if not self.distributed:
+            return 1
         return dist.get_world_size(self.process_group) if dist.is_available() and dist.is_initialized() else 1
 
     def update(self, rollout: Dict[str, Any], global_rows: Optional[int] = None) -> Dict[str, torch.Tensor]:
@@ -431,31 +506,63 @@ class PPOTrainer:
         world = self._world()
         rows = T * N
         grows = global_rows if global_rows is not None else rows * world
-        logits = torch.empty(T, N, A, dtype=torch.float32, device=dev)
-        values = torch.empty(T, N, dtype=torch.float32, device=dev)
-        ws = mdl._workspace(T, N)
         P = mdl.flat_params.data
         st = _stream(dev)
+        # mini-batches = contiguous chunks of samplers (RolloutStorage.recurrent_generator [UPSTREAM]: chunk bounds
+        # round(linspace(0, N, num_mini_batch + 1)), chunk ORDER shuffled per repeat); one chunk = the whole [T, N] block
+        nmb = self.num_mini_batch
+        if nmb > N:
+            raise ValueError(f"num_mini_batch {nmb} exceeds the {N} samplers of this rank")
+        bounds = [int(round(i * N / nmb)) for i in range(nmb + 1)]
+        chunks = [(a, b) for a, b in zip(bounds[:-1], bounds[1:])]
+        C_ = pf.data.shape[-1]
+
+        def block(a: int, b: int):
+            if (a, b) == (0, N):
+                return dict(n=N, feats=pf.data, goals=goals, masks=masks, h0=h0, actions=actions, old_lp=old_lp, old_v=old_v,
+                            rets=rets, nadv=nadv)
+            cut = lambda t: t[:, a:b].contiguous()
+            return dict(n=b - a, feats=pf.data.view(T, N, -1)[:, a:b].reshape(-1, C_).contiguous(), goals=cut(goals), masks=cut(masks),
+                        h0=h0[a:b].contiguous(), actions=cut(actions), old_lp=cut(old_lp), old_v=cut(old_v), rets=cut(rets), nadv=cut(nadv))
+
+        blocks = {c: block(*c) for c in chunks}            # sliced once, reused by every repeat
+        lr = self.lr
         with torch.cuda.device(dev):
             for _ in range(self.update_repeats):
-                _lib.check(lib.embclip_ac_forward(plan._h, P.data_ptr(), pf.data.data_ptr(), goals.data_ptr(), masks.data_ptr(),
-                                                  h0.data_ptr(), T, N, logits.data_ptr(), values.data_ptr(), None, ws.data_ptr(),
-                                                  ws.numel(), 1, st))
-                _lib.check(lib.embclip_ac_ppo_loss(plan._h, P.data_ptr(), T, N, actions.data_ptr(), old_lp.data_ptr(), nadv.data_ptr(),
-                                                   old_v.data_ptr(), rets.data_ptr(), self.clip_param, self.value_loss_coef,
-                                                   self.entropy_coef, 1.0 / grows, logits.data_ptr(), values.data_ptr(),
-                                                   self.loss_sums.data_ptr(), ws.data_ptr(), ws.numel(), st))
-                self.grads.zero_()
-                _lib.check(lib.embclip_ac_backward(plan._h, P.data_ptr(), pf.data.data_ptr(), goals.data_ptr(), masks.data_ptr(),
-                                                   h0.data_ptr(), T, N, None, None, None, self.grads.data_ptr(), ws.data_ptr(),
-                                                   ws.numel(), st))
-                allreduce_flat_(self.grads, self.process_group)       # the path's one collective (no-op when world == 1)
-                self.step_count += 1
-                _lib.check(lib.embclip_sumsq_f32(self.grads.data_ptr(), self.grads.numel(), self.sumsq.data_ptr(), st))
-                _lib.check(lib.embclip_adam_clip_step(P.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(),
-                                                      self.exp_avg_sq.data_ptr(), P.numel(), self.sumsq.data_ptr(), self.max_grad_norm,
-                                                      self.lr, self.betas[0], self.betas[1], self.eps, self.step_count, st))
-                mdl.mark_params_changed()                              # raw-pointer update: torch's version counter does not see it
+                order = list(chunks)
+                if nmb > 1:
+                    self._rng.shuffle(order)
+                for c in order:
+                    bk = blocks[c]
+                    n = bk["n"]
+                    mb_grows = grows * n / N               # rows of this mini-batch over all ranks (equal splits on every rank)
+                    logits = torch.empty(T, n, A, dtype=torch.float32, device=dev)
+                    values = torch.empty(T, n, dtype=torch.float32, device=dev)
+                    ws = mdl._workspace(T, n)
+                    mdl._touch_workspace()
+                    _lib.check(lib.embclip_ac_forward(plan._h, P.data_ptr(), bk["feats"].data_ptr(), bk["goals"].data_ptr(),
+                                                      bk["masks"].data_ptr(), bk["h0"].data_ptr(), T, n, logits.data_ptr(),
+                                                      values.data_ptr(), None, ws.data_ptr(), ws.numel(), 1, st))
+                    _lib.check(lib.embclip_ac_ppo_loss(plan._h, P.data_ptr(), T, n, bk["actions"].data_ptr(), bk["old_lp"].data_ptr(),
+                                                       bk["nadv"].data_ptr(), bk["old_v"].data_ptr(), bk["rets"].data_ptr(),
+                                                       self.clip_param, self.value_loss_coef, self.entropy_coef, 1.0 / mb_grows,
+                                                       logits.data_ptr(), values.data_ptr(), self.loss_sums.data_ptr(), ws.data_ptr(),
+                                                       ws.numel(), st))
+                    self.grads.zero_()
+                    _lib.check(lib.embclip_ac_backward(plan._h, P.data_ptr(), bk["feats"].data_ptr(), bk["goals"].data_ptr(),
+                                                       bk["masks"].data_ptr(), bk["h0"].data_ptr(), T, n, None, None, None,
+                                                       self.grads.data_ptr(), ws.data_ptr(), ws.numel(), st))
+                    if self.distributed:
+                        allreduce_flat_(self.grads, self.process_group)   # the path's one collective (no-op when world == 1)
+                    self.step_count += 1
+                    _lib.check(lib.embclip_sumsq_f32(self.grads.data_ptr(), self.grads.numel(), self.sumsq.data_ptr(), st))
+                    _lib.check(lib.embclip_adam_clip_step(P.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(),
+                                                          self.exp_avg_sq.data_ptr(), P.numel(), self.sumsq.data_ptr(),
+                                                          self.max_grad_norm, lr, self.betas[0], self.betas[1], self.eps,
+                                                          self.step_count, st))
+                    mdl.mark_params_changed()                          # raw-pointer update: torch's version counter does not see it
+                    rows = T * n
+        self.total_steps += int(grows)                                  # lr_scheduler.step(epoch=total_steps) [UPSTREAM]
         s = self.loss_sums / rows
         return {"action": s[0], "value": s[1], "entropy": -s[2],
                 "total": s[0] + self.value_loss_coef * s[1] - self.entropy_coef * s[2], "grad_norm": self.sumsq.sqrt()[0]}

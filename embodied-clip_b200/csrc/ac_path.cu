@@ -34,11 +34,7 @@ struct WgradOp {
 template <int BN>
 int launch_wgrad_cfg(const WgradOp& op, cudaStream_t st) {
   using Cfg = WgradCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(wgrad_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  { const int rc_ = ensure_smem((const void*)wgrad_gemm_kernel<BN>, (size_t)(Cfg::kSmemBytes)); if (rc_) return rc_; }
   CUtensorMap tmA, tmB;
   int rc;
   if ((rc = make_map_2d(&tmA, op.a, (int)op.Kdim, op.M1, op.lda, 64, 64))) return rc;
@@ -102,12 +98,17 @@ extern "C" int embclip_wgrad_f16(const void* a, int lda, int M1, const void* b, 
 // =============================================================================================
 namespace {
 
+// scratch32 layout (ABI: 256 B): [0, kGruMaxGroups) barrier counters (one per sampler group), [kGruAmaxSlot] max |dgi| bits
+constexpr int kGruMaxGroups = 32;
+constexpr int kGruAmaxSlot = 32;
+constexpr size_t kGruScratchBytes = 256;
 struct GruGeom { int groups, ns, grid; };
 int gru_geometry(int N, int H, GruGeom* g) {
   if (H % 64 || H <= 0) return fail(EMBCLIP_EINVAL, "gru: hidden size must be a multiple of 64");
   if (N <= 0) return fail(EMBCLIP_EINVAL, "gru: no samplers");
   const int ub = H / kGruUB;
-  const int max_groups = num_sms() / ub;
+  int max_groups = num_sms() / ub;
+  if (max_groups > kGruMaxGroups) max_groups = kGruMaxGroups;      // one barrier counter per group in scratch32
   if (max_groups < 1) return fail(EMBCLIP_EINVAL, "gru: hidden size %d needs more CTAs than the device has SMs", H);
   int groups = (N + kGruNS - 1) / kGruNS;
   if (groups > max_groups) return fail(EMBCLIP_EINVAL, "gru: %d samplers exceed one launch (max %d); split the batch", N, max_groups * kGruNS);
@@ -116,6 +117,7 @@ int gru_geometry(int N, int H, GruGeom* g) {
   g->ns = (N + groups - 1) / groups;
   g->groups = (N + g->ns - 1) / g->ns;
   g->grid = ub * g->groups;
+  if (g->groups > kGruMaxGroups) return fail(EMBCLIP_EINVAL, "gru: %d sampler groups exceed the %d barrier slots", g->groups, kGruMaxGroups);
   return 0;
 }
 size_t gru_fwd_smem(int H) { return sizeof(float) * (size_t(3 * kGruUB + kGruNS) * (H + 4) + 8 * kGruNS * 24); }
@@ -127,12 +129,8 @@ int launch_gru_forward(GruFwdParams p, cudaStream_t st) {
   if ((rc = gru_geometry(p.N, p.H, &g))) return rc;
   p.groups = g.groups; p.ns = g.ns;
   const size_t smem = gru_fwd_smem(p.H);
-  static size_t attr = 0;
-  if (smem > attr) {
-    CUDA_TRY(cudaFuncSetAttribute(gru_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
-  CUDA_TRY(cudaMemsetAsync(p.bar, 0, sizeof(unsigned int) * 8, st));
+  { const int rc_ = ensure_smem((const void*)gru_forward_kernel, (size_t)(smem)); if (rc_) return rc_; }
+  CUDA_TRY(cudaMemsetAsync(p.bar, 0, sizeof(unsigned int) * kGruMaxGroups, st));
   void* args[] = {&p};
   CUDA_TRY(cudaLaunchCooperativeKernel((const void*)gru_forward_kernel, dim3(g.grid), dim3(kGruThreads), args, smem, st));
   return 0;
@@ -143,12 +141,8 @@ int launch_gru_backward(GruBwdParams p, cudaStream_t st) {
   if ((rc = gru_geometry(p.N, p.H, &g))) return rc;
   p.groups = g.groups; p.ns = g.ns;
   const size_t smem = gru_bwd_smem(p.H);
-  static size_t attr = 0;
-  if (smem > attr) {
-    CUDA_TRY(cudaFuncSetAttribute(gru_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
-  CUDA_TRY(cudaMemsetAsync(p.bar, 0, sizeof(unsigned int) * 8, st));
+  { const int rc_ = ensure_smem((const void*)gru_backward_kernel, (size_t)(smem)); if (rc_) return rc_; }
+  CUDA_TRY(cudaMemsetAsync(p.bar, 0, sizeof(unsigned int) * kGruMaxGroups, st));
   void* args[] = {&p};
   CUDA_TRY(cudaLaunchCooperativeKernel((const void*)gru_backward_kernel, dim3(g.grid), dim3(kGruThreads), args, smem, st));
   return 0;
@@ -182,7 +176,7 @@ extern "C" int embclip_gru_backward(const float* w_hh, const float* h0, const fl
   p.r = save_r; p.z = save_z; p.n = save_n; p.hn = save_hn; p.dout = dout; p.dhT = dh_last;
   p.dgi = dgi; p.dgh = dgh; p.hm_h = reinterpret_cast<__half*>(hm_f16); p.dh0 = dh0;
   p.bar = reinterpret_cast<unsigned int*>(scratch32);
-  p.amax = p.bar + 8;                                   // scratch32: [0,8) barrier counters, [8] amax bits
+  p.amax = p.bar + kGruAmaxSlot;
   CUDA_TRY(cudaMemsetAsync(p.amax, 0, sizeof(unsigned int), (cudaStream_t)stream));
   return launch_gru_backward(p, (cudaStream_t)stream);
 }
@@ -281,7 +275,7 @@ struct AcWs {
   // fp32
   float *GI, *Hout, *R, *Z, *Nn, *HN, *dH, *dGI, *dGH, *dlogits, *dvalues;
   float* scale;                            // [2]
-  unsigned int* scratch32;                 // [0,8) barriers, [8] amax
+  unsigned int* scratch32;                 // [0,32) group barriers, [32] amax (kGruScratchBytes)
   uint64_t total;
 };
 
@@ -311,7 +305,7 @@ void ac_workspace(const embclip_ac* m, int T, int N, uint8_t* base, AcWs* w) {
   w->dH = f32(F * H); w->dGI = f32(F * 3 * H); w->dGH = f32(F * 3 * H);
   w->dlogits = f32(F * c.num_actions); w->dvalues = f32(F);
   w->scale = f32(2);
-  w->scratch32 = reinterpret_cast<unsigned int*>(base + carve(off, 64));
+  w->scratch32 = reinterpret_cast<unsigned int*>(base + carve(off, kGruScratchBytes));
   w->total = off;
 }
 
@@ -373,11 +367,7 @@ extern "C" int embclip_ac_pack_features(embclip_ac_t h, const float* feats_nchw,
   const int C = h->cfg.feat_channels, Pp = h->cfg.feat_pixels;
   const size_t smem = (size_t)128 * (Pp + 1) * 4;
   if (frames > 65535LL * 1024) return fail(EMBCLIP_EINVAL, "ac_pack_features: too many frames");
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    CUDA_TRY(cudaFuncSetAttribute(ac_pack_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  { const int rc_ = ensure_smem((const void*)ac_pack_features_kernel, (size_t)(smem)); if (rc_) return rc_; }
   for (long long f0 = 0; f0 < frames; f0 += 65535) {       // gridDim.y limit
     const int nf = (int)(frames - f0 < 65535 ? frames - f0 : 65535);
     dim3 grid((C + 127) / 128, nf);
@@ -455,11 +445,7 @@ static int ac_forward_impl(embclip_ac_t h, const float* params, uint64_t params_
   hp.h = w.Hout; hp.w_actor = P(h, params, P_AW); hp.b_actor = P(h, params, P_AB); hp.w_critic = P(h, params, P_CW);
   hp.b_critic = P(h, params, P_CB); hp.logits = logits; hp.values = values; hp.F = F; hp.H = H; hp.A = c.num_actions;
   const size_t hsmem = sizeof(float) * (size_t)(c.num_actions + 1) * H;
-  static size_t hattr = 48 * 1024;
-  if (hsmem > hattr) {
-    CUDA_TRY(cudaFuncSetAttribute(ac_heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
-    hattr = hsmem;
-  }
+  { const int rc_ = ensure_smem((const void*)ac_heads_fwd_kernel, (size_t)(hsmem)); if (rc_) return rc_; }
   ac_heads_fwd_kernel<<<blocks_for(F, 8, 4), 256, hsmem, st>>>(hp);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -544,7 +530,7 @@ extern "C" int embclip_ac_backward(embclip_ac_t h, const float* params, const vo
   gp.T = T; gp.N = N; gp.H = H; gp.w_hh = P(h, params, P_WHH); gp.h0 = h0; gp.masks = masks; gp.out = w.Hout;
   gp.r = w.R; gp.z = w.Z; gp.n = w.Nn; gp.hn = w.HN; gp.dout = w.dH; gp.dhT = dh_last;
   gp.dgi = w.dGI; gp.dgh = w.dGH; gp.hm_h = w.hm_h; gp.dh0 = nullptr;
-  gp.bar = w.scratch32; gp.amax = w.scratch32 + 8;
+  gp.bar = w.scratch32; gp.amax = w.scratch32 + kGruAmaxSlot;
   CUDA_TRY(cudaMemsetAsync(gp.amax, 0, sizeof(unsigned int), st));
   if ((rc = launch_gru_backward(gp, st))) return rc;
 

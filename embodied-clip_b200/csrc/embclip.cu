@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -93,19 +95,37 @@ int embclip::make_map_2d(CUtensorMap* m, const void* base, int rows, int cols, i
 // =============================================================================================
 // conv_gemm launcher
 // =============================================================================================
-static int g_num_sms = 0;
+// Per-device caches: the dynamic-smem opt-in is a per-device function attribute and the SM count differs by device, so both
+// are keyed on the current device ordinal (one process may drive several GPUs: Preprocessor.to(other_device)).
+static std::mutex g_dev_mu;
+static std::map<std::pair<const void*, int>, size_t> g_smem_attr;
+static int g_num_sms[64] = {0};
+int embclip::ensure_smem(const void* func, size_t bytes) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  size_t& have = g_smem_attr[std::make_pair(func, dev)];
+  if (bytes > have) {
+    if (bytes > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+  }
+  return 0;
+}
 bool embclip::pdl_enabled() {
   static const bool on = getenv("EMBCLIP_NO_PDL") == nullptr;
   return on;
 }
 int embclip::num_sms() {
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int slot = dev >= 0 && dev < 64 ? dev : 0;
+  int n = g_num_sms[slot];
+  if (!n) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    g_num_sms[slot] = n;
   }
-  return g_num_sms;
+  return n;
 }
 
 static void choose_box(int H, int W, int B, int* bw, int* bh, int* bn) {
@@ -126,11 +146,7 @@ static void choose_box(int H, int W, int B, int* bw, int* bh, int* bn) {
 template <int BN, int BK, bool kRes>
 static int launch_cfg(const GemmOp& op, cudaStream_t st) {
   using Cfg = ConvGemmCfg<BN, BK, kRes>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<BN, BK, kRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  { const int rc_ = ensure_smem((const void*)conv_gemm_kernel<BN, BK, kRes>, Cfg::kSmemBytes); if (rc_) return rc_; }
   ConvGemmParams p;
   memset(&p, 0, sizeof p);
   CUtensorMap tmA0, tmA1, tmB, tmC, tmR;
@@ -195,11 +211,7 @@ static int launch_cfg(const GemmOp& op, cudaStream_t st) {
 template <int BN, bool kRes>
 static int launch_gemm2sm(const GemmOp& op, cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(gemm2sm_kernel<BN, kRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  { const int rc_ = ensure_smem((const void*)gemm2sm_kernel<BN, kRes>, Cfg::kSmemBytes); if (rc_) return rc_; }
   const long long M = (long long)op.n * op.h * op.w;
   if (M > 0x7fffffffLL) return fail(EMBCLIP_EINVAL, "M too large");
   CUtensorMap tmA0, tmA1, tmB, tmC, tmR;
@@ -339,11 +351,7 @@ static int launch_c3_cfg(const Conv3Op& op, const C3Geom& g, cudaStream_t st) {
   }
   if (n_b > 12) n_b = 12;
   const size_t smem = 1024 + size_t(n_a) * plane_bytes + size_t(n_b) * kBBytes + kC3BarBytes + stage_bytes;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    CUDA_TRY(cudaFuncSetAttribute(conv3x3_halo_kernel<BN, MS, KC, kPool>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
+  { const int rc_ = ensure_smem((const void*)conv3x3_halo_kernel<BN, MS, KC, kPool>, (size_t)(smem)); if (rc_) return rc_; }
   CUtensorMap tmA, tmB;
   int rc;
   if ((rc = make_map_nhwc(&tmA, op.in, op.B, op.H, op.W, op.C, op.C, KC, g.Wp, g.BH, g.G))) return rc;
@@ -440,11 +448,7 @@ struct TailOp {
 template <int K3C, int N1, bool kRes>
 static int launch_tail_cfg(const TailOp& op, cudaStream_t st) {
   using Cfg = TailCfg<K3C, N1>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(bneck_tail_kernel<K3C, N1, kRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  { const int rc_ = ensure_smem((const void*)bneck_tail_kernel<K3C, N1, kRes>, Cfg::kSmemBytes); if (rc_) return rc_; }
   const int M = (int)op.M;
   CUtensorMap tmA0, tmA1, tmW3, tmW1, tmR, tmC;
   int rc;
@@ -551,11 +555,7 @@ static int launch_stem_rows(const void* x, const void* wtc, const float* b, void
   while (Ro % segs) ++segs;                                  // equal segments of <= 128 output pixels
   const size_t smem = 1024 + 32768 + 2 * COUT * 128 + size_t(kStemRowsStages) * stem_rows_stage_bytes<TIn>(R) + 64;
   if (smem > 227u * 1024u) return fail(EMBCLIP_EINVAL, "stem: resolution %d does not fit the row ring", R);
-  static size_t attr = 0;
-  if (smem > attr) {
-    CUDA_TRY(cudaFuncSetAttribute(stem_conv1_rows_kernel<TIn, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  { const int rc_ = ensure_smem((const void*)stem_conv1_rows_kernel<TIn, COUT>, (size_t)(smem)); if (rc_) return rc_; }
   const long long tiles = (long long)B * Ro * segs;
   int per_sm = int((227u * 1024u) / smem);
   if (per_sm > 4) per_sm = 4;
@@ -582,12 +582,8 @@ static int launch_stem_conv1_tc(const void* x, int x_u8, const float* norm6, con
   if (Cout != 32) return fail(EMBCLIP_EINVAL, "stem conv1: Cout %d not built (32 or 64)", Cout);
   if (!gather_only && rows_ok)
     return x_u8 ? launch_stem_rows<uint8_t, 32>(x, wtc, b, y, B, R, nm, st) : launch_stem_rows<float, 32>(x, wtc, b, y, B, R, nm, st);
-  static bool attr = false;
-  if (!attr) {
-    CUDA_TRY(cudaFuncSetAttribute(stem_conv1_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemTcSmem));
-    CUDA_TRY(cudaFuncSetAttribute(stem_conv1_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemTcSmem));
-    attr = true;
-  }
+  { const int rc_ = ensure_smem((const void*)stem_conv1_tc_kernel<float>, (size_t)(kStemTcSmem)); if (rc_) return rc_; }
+  { const int rc_ = ensure_smem((const void*)stem_conv1_tc_kernel<uint8_t>, (size_t)(kStemTcSmem)); if (rc_) return rc_; }
   const long long tiles = ((long long)B * (R / 2) * (R / 2) + 127) / 128;
   long long grid = (long long)num_sms() * 4;
   if (grid > tiles) grid = tiles;
@@ -978,11 +974,7 @@ static int run_op(embclip_rn50* m, const Op& op, const std::vector<uint64_t>& of
     case K_ATTN_CORE: {
       static const bool cuda_core = getenv("EMBCLIP_ATTNPOOL_CUDA_CORE") != nullptr;   // first version, kept for A/B timing
       if (!cuda_core && m->cfg.heads == 32 && 4 * m->tokens <= 256 && m->embed % 128 == 0) {
-        static bool attr_tc = false;
-        if (!attr_tc) {
-          CUDA_TRY(cudaFuncSetAttribute(attnpool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kApSmem));
-          attr_tc = true;
-        }
+        { const int rc_ = ensure_smem((const void*)attnpool_tc_kernel, (size_t)(kApSmem)); if (rc_) return rc_; }
         CUtensorMap tq, tk, tmn;
         int rc;
         if ((rc = make_map_2d(&tq, act_ptr(op.in0), B * m->cfg.heads, m->embed, m->embed, 64, 128))) return rc;
@@ -996,11 +988,7 @@ static int run_op(embclip_rn50* m, const Op& op, const std::vector<uint64_t>& of
       constexpr int HG = 8;
       if (m->cfg.heads % HG) return fail(EMBCLIP_EINVAL, "attention pool: heads must be a multiple of %d", HG);
       const size_t smem = (size_t)HG * m->embed * 2 + HG * 64 * 4;
-      static bool attr = false;
-      if (!attr) {
-        CUDA_TRY(cudaFuncSetAttribute(attnpool_core_kernel<HG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-      }
+      { const int rc_ = ensure_smem((const void*)attnpool_core_kernel<HG>, (size_t)(smem)); if (rc_) return rc_; }
       dim3 grid(B, m->cfg.heads / HG);
       CUDA_TRY(launch_pdl(attnpool_core_kernel<HG>, grid, dim3(256), smem, st, (const __half*)act_ptr(op.in0), (const __half*)act_ptr(op.in1),
                           (__half*)act_ptr(op.out), m->cfg.heads, m->tokens, m->embed));

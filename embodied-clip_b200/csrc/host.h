@@ -18,8 +18,11 @@ int fail(int code, const char* fmt, ...);
     if (e_ != cudaSuccess) return ::embclip::fail(EMBCLIP_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
   } while (0)
 
-int num_sms();
+int num_sms();         // SM count of the CURRENT device (cached per device ordinal)
 bool pdl_enabled();   // false when $EMBCLIP_NO_PDL is set
+// Raises the kernel's MaxDynamicSharedMemorySize to `bytes` on the CURRENT device if it is not there yet.  The attribute is
+// per (function, device): state is keyed on both, so a second GPU in the same process gets its own opt-in.  Thread-safe.
+int ensure_smem(const void* func, size_t bytes);
 
 // Launch with programmatic stream serialization: the kernel MUST execute griddepcontrol.wait before touching global
 // memory written by earlier kernels in the stream (see ptx.cuh).

@@ -187,11 +187,7 @@ int tf_attention(embclip_tf* m, const TfWs& w, int S, int causal, cudaStream_t s
     CUDA_TRY(cudaGetLastError());
     return 0;
   }
-  static bool attr = false;
-  if (!attr) {
-    CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnTcSmem));
-    attr = true;
-  }
+  { const int rc_ = ensure_smem((const void*)attention_tc_kernel, (size_t)(kAttnTcSmem)); if (rc_) return rc_; }
   CUtensorMap tm;
   int rc;
   if ((rc = make_map_2d(&tm, w.qkv, rows, 3 * D, 3 * D, 64, 128))) return rc;

@@ -273,7 +273,8 @@ int embclip_adam_clip_step(float* params, float* grads, float* exp_avg, float* e
 int embclip_wgrad_f16(const void* a, int lda, int M1, const void* b, int ldb, int N1, long long Kdim, float* out,
                       long long ldo_m, long long ldo_n, const float* alpha, void* stream);
 /* nn.GRU (1 layer) with RNNStateEncoder's episode masking: gi = x W_ih^T + b_ih precomputed [T,N,3H];
- * out [T,N,H]; save_* [T,N,H] (all NULL for inference); scratch32 = 64 B of device scratch. */
+ * out [T,N,H]; save_* [T,N,H] (all NULL for inference); scratch32 = 256 B of device scratch
+ * (uint32 [0,32): one barrier counter per sampler group, zeroed by the call; [32]: max |dgi| bits written by the backward). */
 int embclip_gru_forward(const float* gi, const float* w_hh, const float* b_hh, const float* h0, const float* masks,
                         int T, int N, int H, float* out, float* save_r, float* save_z, float* save_n, float* save_hn,
                         void* scratch32, void* stream);

@@ -5,13 +5,13 @@ Tolerances (DESIGN.md "Numerics"):
   * forward outputs (logits, values, final hidden state): rel-L2 <= 1e-3 -- the north-star bar; argmax actions
     bit-exact on every row whose top-2 logit gap exceeds the forward error bound;
   * kernels whose arithmetic is fp32 end to end (GRU recurrence / BPTT, heads, loss, GAE, Adam): rel-L2 <= 2e-5;
-  * gradients that pass through fp16-operand tensor-core GEMMs: rel-L2 <= 3e-3 per parameter tensor against the
+  * gradients that pass through fp16-operand tensor-core GEMMs: rel-L2 <= 1e-3 per parameter tensor against the
     oracle evaluated WITH THE SAME ReLU MASKS (two roundings to fp16 per layer over a 5-layer backward chain;
     measured values are printed with -s).  The ReLU derivative is discontinuous: a forward error of 4e-4 flips
     ~1e-4 of the masks (pre-activations within rounding distance of zero), and each flipped element contributes
     its whole gradient, so the UNALIGNED gradient differs by ~sqrt(2 * 1e-4) = 1.5-2.5 % -- the same noise the
     reference itself has between its fp32 and TF32 (cuDNN default on Ampere+) executions.  Both numbers are
-    checked: aligned <= 3e-3, unaligned <= 5e-2 with the flip fraction <= 1e-3.  PPO's clipped objective has the
+    checked: aligned <= 1e-3, unaligned <= 5e-2 with the flip fraction <= 1e-3.  PPO's clipped objective has the
     same property at ratio = 1 +- clip and |v - v_old| = clip, so the synthetic batches keep a 2e-3 margin from
     those boundaries (one straddling row out of 960 is a 2 % gradient difference).
 """
@@ -98,7 +98,7 @@ def _gru_case(lib, T, N, H, seed, mask_p=0.15):
     h0d, md = h0[0].to(dev).contiguous(), masks[..., 0].to(dev).contiguous()
     out = torch.empty(T, N, H, device=dev)
     sv = [torch.empty(T, N, H, device=dev) for _ in range(4)]
-    scratch = torch.zeros(16, dtype=torch.int32, device=dev)
+    scratch = torch.zeros(64, dtype=torch.int32, device=dev)
     _check(lib, lib.embclip_gru_forward(gi.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(), h0d.data_ptr(), md.data_ptr(), T, N, H,
                                         out.data_ptr(), *[s.data_ptr() for s in sv], scratch.data_ptr(), _st()))
     torch.cuda.synchronize()
@@ -123,11 +123,11 @@ def _gru_case(lib, T, N, H, seed, mask_p=0.15):
     assert rel(hm, hprev) <= 1e-3
     assert rel(dgh_c.t() @ hprev.reshape(T * N, H), enc.rnn.weight_hh_l0.grad) <= 5e-5
     assert rel(dgh_c.sum(0), enc.rnn.bias_hh_l0.grad) <= 5e-5
-    amax = scratch[8:9].view(torch.float32).item()
+    amax = scratch[32:33].view(torch.float32).item()
     assert abs(amax - dgi_c.abs().max().item()) <= 1e-6 * max(1.0, amax)
 
 
-@pytest.mark.parametrize("T,N,H", [(1, 1, 64), (5, 7, 128), (16, 60, 512), (3, 33, 512)])
+@pytest.mark.parametrize("T,N,H", [(1, 1, 64), (5, 7, 128), (16, 60, 512), (3, 33, 512), (6, 40, 64), (4, 70, 128), (128, 60, 512)])
 def test_gru_forward_backward_vs_torch(lib, T, N, H):
     _gru_case(lib, T, N, H, seed=T * 100 + N)
 
@@ -213,7 +213,7 @@ def _ref_forward(ref, ro):
     return ref({ref.rgb_uuid: ro["features"], ref.goal_uuid: ro["goals"]}, ro["memory"], None, ro["masks"])
 
 
-@pytest.mark.parametrize("T,N", [(1, 3), (6, 5), (16, 60)])
+@pytest.mark.parametrize("T,N", [(1, 3), (6, 5), (16, 60), (128, 60)])      # (128, 60) = BASELINE config 3 at full size
 def test_actor_critic_forward_vs_oracle(models, T, N):
     ours, ref = models
     ro = _rollout(T, N, seed=T + N)
@@ -231,6 +231,9 @@ def test_actor_critic_forward_vs_oracle(models, T, N):
     margin = top2[..., 0] - top2[..., 1]
     bound = 2 * (torch.log_softmax(logits, -1).cpu() - lr_).abs().max().item()
     decided = margin > bound
+    agree = (logits.cpu().argmax(-1) == lr_.argmax(-1))
+    print(f"argmax: {int(decided.sum())}/{decided.numel()} rows decided (top-2 gap > {bound:.2e}), {int((~decided).sum())} undecided, "
+          f"{int((~agree).sum())} disagreements overall")
     assert decided.float().mean().item() > 0.9
     assert torch.equal(logits.cpu().argmax(-1)[decided], lr_.argmax(-1)[decided])
 
@@ -276,10 +279,10 @@ def _ref_forward_with_masks(ref, ro, acts):
     return ref.actor(x), ref.critic(x), h
 
 
-GRAD_TOL = 3e-3
+GRAD_TOL = 1e-3                       # the north-star bar, on the branch the kernels took (see the module docstring)
 
 
-@pytest.mark.parametrize("T,N", [(6, 5), (16, 60)])
+@pytest.mark.parametrize("T,N", [(6, 5), (16, 60), (128, 60)])             # (128, 60) = BASELINE config 3 at full size
 def test_ppo_loss_and_gradients_vs_oracle(models, lib, T, N):
     """Fused path: embclip_ac_forward -> embclip_ac_ppo_loss -> embclip_ac_backward vs autograd of the oracle."""
     from oracle.allenact_models import ppo_loss
@@ -400,11 +403,23 @@ def test_autograd_surface_matches_fused_path(models):
     assert torch.equal(out2.distributions.mode(), out.distributions.logits.argmax(-1))
 
 
+UPDATE_GRAD_TOL = 1e-3
+UPDATE_STEP_TOL = 0.08
+
+
 def test_ppo_update_vs_oracle(models):
-    """4 update passes (forward, loss, backward, clip 0.5, Adam 3e-4) track the oracle's parameters."""
+    """update_repeats = 4 x (forward, loss, backward, clip 0.5, Adam 3e-4) against the oracle run ON THE SAME ReLU BRANCH:
+    after each of our passes the oracle repeats it with our activation masks (the kernels' forward is still in the
+    workspace), so the two trajectories differ by arithmetic only.  Checked per pass: loss terms and the pre-clip gradient
+    (rel-L2 <= 1e-3 per tensor, the north-star bar; the parameters the gradient is taken at have drifted apart by the
+    previous passes' difference, which is part of what is measured).  Checked at the end: every parameter tensor's
+    deviation relative to the distance it travelled.  That last ratio is bounded by UPDATE_STEP_TOL, not 1e-3: in its first steps
+    Adam moves each element by ~lr * sign(g), so the elements whose gradient is within the 1e-3 error of zero (a fraction
+    ~1e-3 of them) move the opposite way by the full step -- a 1e-3 gradient error is a sqrt(4 * 1e-3) ~ 6 % difference of
+    the step by construction, in the reference's own fp32-vs-TF32 executions as much as here."""
     import copy
     from embclip_b200.actor_critic import PPOTrainer, ResnetTensorNavActorCritic
-    from oracle.allenact_models import ppo_update
+    from oracle.allenact_models import ppo_loss
     _, ref0 = models
     ref = copy.deepcopy(ref0)
     ours = ResnetTensorNavActorCritic(device="cuda:0")
@@ -413,18 +428,40 @@ def test_ppo_update_vs_oracle(models):
     ro = _rollout(T, N, seed=300)
     batch = _loss_batch(ref, ro, seed=9)
     before = {k: v.clone() for k, v in ref.state_dict().items()}
-    info_ref = ppo_update(ref, torch.optim.Adam(ref.parameters(), lr=3e-4), {**ro, **batch}, update_repeats=4, max_grad_norm=0.5)
-    tr = PPOTrainer(ours, lr=3e-4, max_grad_norm=0.5, update_repeats=4)
-    info = tr.update({k: v.cuda() for k, v in {**ro, **batch}.items()})
-    torch.cuda.synchronize()
-    assert abs(info["total"].item() - info_ref["total"]) <= 2e-3 * max(1.0, abs(info_ref["total"]))
+    opt = torch.optim.Adam(ref.parameters(), lr=3e-4)
+    tr = PPOTrainer(ours, lr=3e-4, max_grad_norm=0.5, update_repeats=1)
+    dev_batch = {k: v.cuda() for k, v in {**ro, **batch}.items()}
+    ref_params = dict(ref.named_parameters())
+    worst_grad = 0.0
+    for it in range(4):
+        info = tr.update(dev_batch)
+        torch.cuda.synchronize()
+        acts = ours.activations(T, N)
+        distr_m, v_m, _ = _ref_forward_with_masks(ref, ro, acts)
+        total_ref, parts_ref = ppo_loss(distr_m, v_m, batch)
+        opt.zero_grad()
+        total_ref.backward()
+        gn_ref = torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.5)        # scales .grad in place, as our Adam kernel does to tr.grads
+        g = tr.grads
+        errs = {name: rel(g[off:off + n].view(shape), ref_params[name].grad) for name, shape, off, n in ours._plan.params}
+        worst_grad = max(worst_grad, max(errs.values()))
+        print(f"pass {it}: total {info['total'].item():.6f} vs {float(total_ref):.6f}; worst gradient rel-L2 {max(errs.values()):.2e} "
+              f"({max(errs, key=errs.get)})")
+        assert abs(info["total"].item() - float(total_ref)) <= 1e-3 * max(1.0, abs(float(total_ref)))
+        bad = {k: e for k, e in errs.items() if not e <= UPDATE_GRAD_TOL}
+        assert not bad, f"pass {it}: {bad}"
+        assert abs(info["grad_norm"].item() - float(gn_ref)) <= 1e-3 * float(gn_ref)
+        opt.step()
     after = ours.state_dict()
+    ratios = {}
     for k, v in ref.state_dict().items():
         step = (v - before[k]).norm().item()
         err = (after[k].cpu() - v).norm().item()
-        # Adam normalises each element's step to ~lr (sign-like in the first steps), which amplifies the ReLU-flip
-        # gradient noise on elements whose gradient is near zero: compare the parameter CHANGE, within 20 %
-        assert err <= 0.20 * step + 1e-7, f"{k}: change {step:.3g}, deviation {err:.3g}"
+        ratios[k] = err / max(step, 1e-12)
+        # and against the parameter itself the deviation is at the level of lr: ~1e-6 .. 1e-4
+        assert err <= 2e-4 * v.norm().item() + 1e-7, k
+    print("parameter deviation / distance travelled:", {k.split("encoder.")[-1]: f"{r:.3f}" for k, r in ratios.items()})
+    assert max(ratios.values()) <= UPDATE_STEP_TOL, ratios
 
 
 def test_full_size_block_properties(models, lib):
@@ -549,6 +586,96 @@ def test_act_weight_layout_cache_follows_parameter_changes(models):
     lo, va, _ = ours.forward_tensors(ro2["features"].cuda(), ro2["goals"].cuda(), ro2["memory"].cuda(), ro2["masks"].cuda())
     (lo.sum() + va.sum()).backward()
     assert torch.equal(ours.act(*args)[4], ref2)
+
+
+def test_act_after_load_state_dict_and_named_view_writes(models):
+    """a checkpoint reloaded into a live model (or a write through named_views()) after a first act() must not
+    leave the cached fp16 weight layouts behind: act == forward_tensors afterwards, bit for bit."""
+    from embclip_b200.actor_critic import ResnetTensorNavActorCritic
+    ours0, _ = models
+    ours = ResnetTensorNavActorCritic(device="cuda:0", seed=3)
+    N = 5
+    ro = _rollout(1, N, seed=15)
+    pf = ours.pack_features(ro["features"].cuda())
+    args = (pf.data, ro["goals"][0].cuda(), ro["masks"][0].cuda(), ro["memory"][0].cuda(), torch.full((N,), 0.5, device="cuda"))
+    fwd = lambda: ours.forward_tensors(pf, ro["goals"].cuda(), ro["memory"].cuda(), ro["masks"].cuda())[0][0]
+    lg0 = ours.act(*args)[4].clone()
+    res = ours.load_state_dict(ours0.state_dict())
+    assert not res.missing_keys and not res.unexpected_keys
+    lg1 = ours.act(*args)[4].clone()
+    with torch.no_grad():
+        assert torch.equal(lg1, fwd()) and not torch.equal(lg1, lg0)
+    v = ours.params_version()
+    with torch.no_grad():
+        ours.named_views()["goal_visual_encoder.resnet_compressor.0.weight"].mul_(0.5)     # view write: version counter is shared
+    assert ours.params_version() != v
+    lg2 = ours.act(*args)[4].clone()
+    with torch.no_grad():
+        assert torch.equal(lg2, fwd()) and not torch.equal(lg2, lg1)
+
+
+def test_state_dict_as_submodule_round_trips(models):
+    """nn.Module checkpoint protocol (destination / prefix / keep_vars, _IncompatibleKeys, strict errors)."""
+    from embclip_b200.actor_critic import ResnetTensorNavActorCritic
+    ours0, ref = models
+
+    class Wrapper(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.actor_critic = m
+            self.extra = torch.nn.Linear(2, 2)
+
+    w = Wrapper(ours0)
+    sd = w.state_dict()
+    names = {k for k in sd if k.startswith("actor_critic.")}
+    assert names == {"actor_critic." + k for k in ref.state_dict()}, names ^ {"actor_critic." + k for k in ref.state_dict()}
+    assert "actor_critic.flat_params" not in sd
+    w2 = Wrapper(ResnetTensorNavActorCritic(device="cuda:0", seed=1))
+    res = w2.load_state_dict(sd)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(w2.actor_critic.flat_params.data, ours0.flat_params.data)
+    bad = dict(sd)
+    del bad["actor_critic.actor.linear.weight"]
+    bad["actor_critic.bogus"] = torch.zeros(1)
+    with pytest.raises(RuntimeError):
+        w2.load_state_dict(bad)
+    res = w2.load_state_dict(bad, strict=False)
+    assert res.missing_keys == ["actor_critic.actor.linear.weight"]
+    bad = dict(sd)
+    bad["actor_critic.critic.fc.bias"] = torch.zeros(3)
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        w2.load_state_dict(bad)
+    kv = ours0.state_dict(keep_vars=True)
+    assert kv["actor.linear.bias"].data_ptr() == ours0.named_views()["actor.linear.bias"].data_ptr()
+
+
+def test_backward_after_interleaved_forward_recomputes(models):
+    """the forward's intermediates live in a workspace shared by every call on the module; a backward whose
+    workspace was overwritten in between (second minibatch, bootstrap-value forward, act) re-runs its forward."""
+    ours, _ = models
+    roA, roB = _rollout(5, 4, seed=41), _rollout(7, 6, seed=42)
+    f = lambda ro: ours.forward_tensors(ro["features"].cuda(), ro["goals"].cuda(), ro["memory"].cuda(), ro["masks"].cuda())
+    ours.zero_grad()
+    lo, va, _ = f(roA)
+    (lo.square().sum() + va.sum()).backward()
+    g_ref = ours.flat_params.grad.clone()
+    n0 = ours.recomputed_backwards
+    ours.zero_grad()
+    lo, va, _ = f(roA)
+    loB, vaB, _ = f(roB)                                   # overwrites (and here re-allocates) the workspace
+    with torch.no_grad():
+        f(roA)
+    (lo.square().sum() + va.sum()).backward()
+    assert ours.recomputed_backwards == n0 + 1
+    assert rel(ours.flat_params.grad, g_ref) <= 1e-5       # (split-K weight gradients accumulate with fp32 atomics: order varies)
+    ours.zero_grad()
+    (loB.sum() + vaB.square().sum()).backward()            # the other graph still differentiates its own activations
+    gB = ours.flat_params.grad.clone()
+    ours.zero_grad()
+    loB2, vaB2, _ = f(roB)
+    (loB2.sum() + vaB2.square().sum()).backward()
+    assert rel(gB, ours.flat_params.grad) <= 1e-5
+    ours.zero_grad()
 
 
 def test_sampler_frequencies(lib):

@@ -149,3 +149,86 @@ def test_fp16_path_budget(rn50_visual):
     assert rel(exact["trunk_nchw"], t) < 1e-5 and rel(exact["attnpool"], a) < 1e-5
     q = rn50_fp16_path(rn50_visual, frames, quantize=True)
     assert rel(q["trunk_nchw"], t) < 1e-3 and rel(q["attnpool"], a) < 1e-3 and rel(q["avgpool"], t.mean((2, 3))) < 1e-3
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# ModifiedResNet / Bottleneck: independent pins (the ResNet half of the restatement had none).
+#  * stride-1 bottlenecks == torchvision's own Bottleneck (the library class the reference imports for its ImageNet
+#    baseline, thor_image_features.py:46-47) with weights mapped one to one -- with and without a projection shortcut;
+#  * the anti-aliased stride-2 bottleneck and the whole trunk == a functional expansion written from SURVEY.md 8a
+#    A1-A3 only (F.conv2d / F.avg_pool2d and the eval-BatchNorm formula gamma (x - mu) / sqrt(var + 1e-5) + beta
+#    on raw state-dict tensors): no nn.Module, no shared code with oracle/clip_model.py.
+# --------------------------------------------------------------------------------------------------------------------
+def _randomize_bn(m, g):
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.weight.uniform_(0.5, 1.5, generator=g)
+                mod.bias.normal_(0, 0.1, generator=g)
+                mod.running_mean.normal_(0, 0.1, generator=g)
+                mod.running_var.uniform_(0.5, 1.5, generator=g)
+    return m.eval()
+
+
+@pytest.mark.parametrize("inplanes,planes", [(256, 64), (64, 64), (1024, 256)])
+def test_stride1_bottleneck_equals_torchvision(inplanes, planes):
+    from torchvision.models.resnet import Bottleneck as TVBottleneck
+    g = torch.Generator().manual_seed(inplanes + planes)
+    ours = _randomize_bn(cm.Bottleneck(inplanes, planes, stride=1), g)
+    down = None
+    if inplanes != planes * 4:
+        down = torch.nn.Sequential(torch.nn.Conv2d(inplanes, planes * 4, 1, bias=False), torch.nn.BatchNorm2d(planes * 4))
+    tv = TVBottleneck(inplanes, planes, stride=1, downsample=down).eval()
+    missing, unexpected = tv.load_state_dict(ours.state_dict(), strict=True)     # same key names: conv1..3, bn1..3, downsample.{0,1}
+    assert not missing and not unexpected
+    x = torch.randn(2, inplanes, 14, 14, generator=g)
+    with torch.no_grad():
+        assert torch.allclose(ours(x), tv(x), atol=1e-5, rtol=1e-5)
+
+
+def _bn(sd, p, x, eps=1e-5):
+    shp = (1, -1, 1, 1)
+    return (x - sd[p + ".running_mean"].view(shp)) / torch.sqrt(sd[p + ".running_var"].view(shp) + eps) * sd[p + ".weight"].view(shp) + sd[p + ".bias"].view(shp)
+
+
+def _functional_bottleneck(sd, p, x, stride):
+    import torch.nn.functional as F
+    out = F.relu(_bn(sd, p + "bn1", F.conv2d(x, sd[p + "conv1.weight"])))
+    out = F.relu(_bn(sd, p + "bn2", F.conv2d(out, sd[p + "conv2.weight"], padding=1)))       # the 3x3 is ALWAYS stride 1
+    if stride > 1:
+        out = F.avg_pool2d(out, stride)
+    out = _bn(sd, p + "bn3", F.conv2d(out, sd[p + "conv3.weight"]))
+    idn = x
+    if p + "downsample.0.weight" in sd:
+        idn = F.avg_pool2d(x, stride) if stride > 1 else x
+        idn = _bn(sd, p + "downsample.1", F.conv2d(idn, sd[p + "downsample.0.weight"]))
+    return F.relu(out + idn)
+
+
+def test_antialiased_bottleneck_equals_functional_expansion():
+    g = torch.Generator().manual_seed(5)
+    blk = _randomize_bn(cm.Bottleneck(256, 128, stride=2), g)
+    x = torch.randn(2, 256, 28, 28, generator=g)
+    with torch.no_grad():
+        got = blk(x)
+        ref = _functional_bottleneck(blk.state_dict(), "", x, 2)
+    assert got.shape == (2, 512, 14, 14)
+    assert torch.allclose(got, ref, atol=1e-5, rtol=1e-5)
+
+
+def test_rn50_trunk_equals_functional_expansion(rn50_visual):
+    import torch.nn.functional as F
+    sd = rn50_visual.state_dict()
+    x = synthetic_frames(1, seed=3).permute(0, 3, 1, 2).contiguous()        # NHWC sensor layout -> NCHW
+    with torch.no_grad():
+        got = rn50_visual.trunk(x)
+        t = F.relu(_bn(sd, "bn1", F.conv2d(x, sd["conv1.weight"], stride=2, padding=1)))
+        t = F.relu(_bn(sd, "bn2", F.conv2d(t, sd["conv2.weight"], padding=1)))
+        t = F.relu(_bn(sd, "bn3", F.conv2d(t, sd["conv3.weight"], padding=1)))
+        t = F.avg_pool2d(t, 2)
+        for li, nblocks in enumerate((3, 4, 6, 3), start=1):
+            for bi in range(nblocks):
+                t = _functional_bottleneck(sd, f"layer{li}.{bi}.", t, 2 if (bi == 0 and li > 1) else 1)
+    assert got.shape == (1, 2048, 7, 7)
+    err = ((got - t).norm() / t.norm()).item()
+    assert err <= 2e-6, err
