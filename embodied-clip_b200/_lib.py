@@ -14,7 +14,7 @@ DTYPE_F16, DTYPE_F32 = 0, 1
 
 class RN50Cfg(C.Structure):
     _fields_ = [("layers", C.c_int32 * 4), ("width", C.c_int32), ("heads", C.c_int32),
-                ("output_dim", C.c_int32), ("input_resolution", C.c_int32)]
+                ("output_dim", C.c_int32), ("input_resolution", C.c_int32), ("arch", C.c_int32)]
 
 
 class ParamInfo(C.Structure):
@@ -62,6 +62,7 @@ SIGNATURES = {
     "embclip_gemm_grouped_f16": (_I, [_VP, _I, _VP, _I, _I, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "embclip_conv3x3_f16": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "embclip_avgpool2_f16": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
+    "embclip_pool2_f16": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP]),
     "embclip_bneck_tail_f16": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int64, _I, _VP]),
     "embclip_stem_conv1": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     # CLIP transformer towers

@@ -43,7 +43,8 @@ struct Conv3Params {
   int relu;
   int N;                       // Cout
   int reverse;                 // 1: walk the tiles last-to-first (snake order across layers)
-  int pool;                    // 1: write avgpool2(relu(conv)) [B, H/2, W/2, N] instead of the full-resolution map
+  int pool;                    // 1: write avgpool2(relu(conv)) [B, H/2, W/2, N] instead of the full-resolution map;
+                               // 2: write relu(conv)[:, ::2, ::2] -- a STRIDE-2 3x3 conv (torchvision Bottleneck.conv2), same epilogue
   const float* bias;
   __half* out;
 };
@@ -302,6 +303,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (ho >= Ho || img0 + g >= p.B) continue;
           const int pos = (g * p.BHo + 2 * ro) * p.Wp + 2 * wo;
           const uint32_t a = sStage + uint32_t(pos) * kStagePitch + uint32_t(v) * 16;
+          if (p.pool == 2) {                                    // stride-2 conv: the quad's top-left position IS the output
+            uint4 x;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(a));
+            *reinterpret_cast<uint4*>(p.out + ((size_t(img0 + g) * Ho + ho) * Wo + wo) * p.N + n0 + v * 8) = x;
+            continue;
+          }
           float s8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {

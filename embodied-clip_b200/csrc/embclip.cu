@@ -19,6 +19,7 @@
 #include "conv3x3_halo.cuh"
 #include "gemm2sm.cuh"
 #include "bneck_tail.cuh"
+#include "tv_kernels.cuh"
 
 using namespace embclip;
 
@@ -36,7 +37,7 @@ int embclip::fail(int code, const char* fmt, ...) {
   return code;
 }
 extern "C" const char* embclip_last_error(void) { return g_err.c_str(); }
-extern "C" int embclip_abi_version(void) { return 4; }
+extern "C" int embclip_abi_version(void) { return 5; }
 
 // =============================================================================================
 // TMA descriptors (driver entry point resolved at run time: the library links only against cudart)
@@ -532,15 +533,36 @@ extern "C" int embclip_bneck_tail_f16(const void* y2, const void* x0, const void
   return launch_bneck_tail(op, (cudaStream_t)stream);
 }
 
-static int launch_avgpool2(const void* in, void* out, int B, int H, int W, int C, cudaStream_t st) {
-  if (H % 2 || W % 2 || C % 8) return fail(EMBCLIP_EINVAL, "avgpool2: H, W must be even and C a multiple of 8");
+// mode 1: nn.AvgPool2d(2); 2: x[:, ::2, ::2] (input of a stride-2 1x1 conv); 3: nn.MaxPool2d(3, 2, 1)
+static int launch_avgpool2(const void* in, void* out, int B, int H, int W, int C, cudaStream_t st, int mode = 1) {
+  if (H % 2 || W % 2 || C % 8) return fail(EMBCLIP_EINVAL, "pool: H, W must be even and C a multiple of 8");
   const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   if (blocks <= 0) return 0;
-  CUDA_TRY(launch_pdl(avgpool2_kernel, dim3((int)blocks), dim3(256), 0, st, reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), B, H, W, C));
+  auto k = mode == 3 ? maxpool3x3s2_kernel : (mode == 2 ? subsample2_kernel : avgpool2_kernel);
+  CUDA_TRY(launch_pdl(k, dim3((int)blocks), dim3(256), 0, st, reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), B, H, W, C));
   return 0;
+}
+static int launch_im2col7(const void* x, int x_u8, const float* norm6, void* y, int B, int R, cudaStream_t st) {
+  if (R % 2) return fail(EMBCLIP_EINVAL, "stem: resolution must be even");
+  StemNorm nm;
+  for (int c = 0; c < 3; ++c) { nm.scale[c] = norm6 ? norm6[c] : 1.f; nm.offset[c] = norm6 ? norm6[3 + c] : 0.f; }
+  const long long tiles = ((long long)B * (R / 2) * (R / 2) + 31) / 32;
+  long long blocks = (long long)num_sms() * 8;
+  if (blocks > tiles) blocks = tiles;
+  if (blocks <= 0) return 0;
+  if (x_u8)
+    CUDA_TRY(launch_pdl(im2col7x7s2_kernel<uint8_t>, dim3((unsigned)blocks), dim3(256), 0, st, reinterpret_cast<const uint8_t*>(x), reinterpret_cast<__half*>(y), B, R, nm));
+  else
+    CUDA_TRY(launch_pdl(im2col7x7s2_kernel<float>, dim3((unsigned)blocks), dim3(256), 0, st, reinterpret_cast<const float*>(x), reinterpret_cast<__half*>(y), B, R, nm));
+  return 0;
+}
+extern "C" int embclip_pool2_f16(const void* in, void* out, int B, int H, int W, int C, int mode, void* stream) {
+  if (!in || !out) return fail(EMBCLIP_EINVAL, "pool2: null pointer");
+  if (mode < 1 || mode > 3) return fail(EMBCLIP_EINVAL, "pool2: mode must be 1 (avg 2x2), 2 (subsample ::2) or 3 (max 3x3 stride 2 pad 1)");
+  return launch_avgpool2(in, out, B, H, W, C, (cudaStream_t)stream, mode);
 }
 extern "C" int embclip_avgpool2_f16(const void* in, void* out, int B, int H, int W, int C, void* stream) {
   if (!in || !out) return fail(EMBCLIP_EINVAL, "avgpool2: null pointer");
@@ -634,7 +656,7 @@ struct Act {            // workspace tensor, NHWC; batch dim scales with B
 struct Param {
   embclip_param_info info;
 };
-enum OpKind { K_STEM1, K_GEMM, K_POOL, K_TOKENS, K_ATTN_CORE, K_AVGHEAD, K_NCHW };
+enum OpKind { K_STEM1, K_GEMM, K_POOL, K_TOKENS, K_ATTN_CORE, K_AVGHEAD, K_NCHW, K_IM2COL };
 enum Head { H_TRUNK_ALWAYS = 0, H_NCHW = 1, H_AVG = 2, H_ATTN = 4 };
 struct Op {
   OpKind kind;
@@ -716,13 +738,14 @@ static int add_conv(embclip_rn50* m, const std::string& name, int in0, int in1, 
   m->ops.push_back(op);
   return op.out;
 }
-static int add_pool(embclip_rn50* m, const std::string& name, int in0) {
+static int add_pool(embclip_rn50* m, const std::string& name, int in0, int mode = 1, int side = 1) {
   const Act a = m->acts[in0];
   Op op;
   op.kind = K_POOL;
   op.name = name;
   op.in0 = in0;
-  op.side = 1;
+  op.pool = mode;
+  op.side = side;
   op.out = add_act(m, name, EMBCLIP_DTYPE_F16, a.h / 2, a.w / 2, a.c);
   m->ops.push_back(op);
   return op.out;
@@ -731,12 +754,15 @@ static int add_pool(embclip_rn50* m, const std::string& name, int in0) {
 extern "C" int embclip_rn50_create(const embclip_rn50_cfg* cfg, embclip_rn50_t* out) {
   if (!cfg || !out) return fail(EMBCLIP_EINVAL, "rn50_create: null argument");
   const int width = cfg->width, R = cfg->input_resolution;
+  const bool tv = cfg->arch == 1;        // torchvision ResNet (v1.5 Bottleneck): 7x7/2 stem + max-pool, stride on the 3x3, strided 1x1 downsample
+  if (cfg->arch != 0 && cfg->arch != 1) return fail(EMBCLIP_EINVAL, "rn50_create: arch must be 0 (CLIP ModifiedResNet) or 1 (torchvision ResNet)");
+  if (tv && (width != 64 || cfg->output_dim != 0)) return fail(EMBCLIP_EINVAL, "rn50_create: the torchvision plan is width 64 without an attention-pool head (output_dim 0)");
   if (width != 64 && width != 96) return fail(EMBCLIP_EINVAL, "rn50_create: width 64 (RN50 / RN101) and 96 (RN50x16) are built, got %d", width);
   if (R <= 0 || R % 32) return fail(EMBCLIP_EINVAL, "rn50_create: input_resolution must be a positive multiple of 32");
   for (int i = 0; i < 4; ++i)
     if (cfg->layers[i] < 1) return fail(EMBCLIP_EINVAL, "rn50_create: layers[%d] < 1", i);
   const int embed = width * 32, fres = R / 32, L = fres * fres + 1;
-  if (cfg->heads <= 0 || embed % cfg->heads || embed / cfg->heads != 64)
+  if (!tv && (cfg->heads <= 0 || embed % cfg->heads || embed / cfg->heads != 64))
     return fail(EMBCLIP_EINVAL, "rn50_create: head dim must be 64 (embed %d heads %d)", embed, cfg->heads);
   const bool attn_ok = L <= 64 && cfg->output_dim > 0;   // output_dim 0 = "no attention-pool head" (positional embedding of another resolution)      // (RN50x16 at its native 384 x 384 has 145 tokens: trunk and avg-pool heads only)
   if (cfg->output_dim < 0 || cfg->output_dim % 32) return fail(EMBCLIP_EINVAL, "rn50_create: output_dim must be a non-negative multiple of 32");
@@ -748,7 +774,17 @@ extern "C" int embclip_rn50_create(const embclip_rn50_cfg* cfg, embclip_rn50_t* 
   const int stem_c = (width / 2 + 31) / 32 * 32;
 
   // ---- stem
-  {
+  int t;
+  if (tv) {
+    // conv 7x7 / 2 / pad 3 (3 -> 64) + BN + ReLU as im2col rows x [64, 160] GEMM, then MaxPool2d(3, 2, 1)
+    Op ic;
+    ic.kind = K_IM2COL;
+    ic.name = "stem.im2col";
+    ic.out = add_act(m, "stem.im2col", EMBCLIP_DTYPE_F16, R / 2, R / 2, kStem7K);
+    m->ops.push_back(ic);
+    t = add_conv(m, "stem.conv1", ic.out, -1, -1, 1, 64, 1);
+    t = add_pool(m, "stem.maxpool", t, /*mode=*/3, /*side=*/0);
+  } else {
     Op op;
     op.kind = K_STEM1;
     op.name = "stem.conv1";
@@ -758,10 +794,10 @@ extern "C" int embclip_rn50_create(const embclip_rn50_cfg* cfg, embclip_rn50_t* 
     m->p_stem_wtc = add_param(m, "stem.conv1.wtc", EMBCLIP_DTYPE_F16, {stem_c, 128});   // hi/lo-split rows for the tensor-core stem
     op.out = add_act(m, "stem.conv1", EMBCLIP_DTYPE_F16, R / 2, R / 2, stem_c);
     m->ops.push_back(op);
+    t = (int)m->acts.size() - 1;
+    t = add_conv(m, "stem.conv2", t, -1, -1, 9, stem_c, 1);
+    t = add_conv(m, "stem.conv3", t, -1, -1, 9, width, 1, 0, /*pool=*/1);   // AvgPool2d(2) fused into the epilogue
   }
-  int t = (int)m->acts.size() - 1;
-  t = add_conv(m, "stem.conv2", t, -1, -1, 9, stem_c, 1);
-  t = add_conv(m, "stem.conv3", t, -1, -1, 9, width, 1, 0, /*pool=*/1);   // AvgPool2d(2) fused into the epilogue
 
   // ---- bottleneck stages
   int inplanes = width;
@@ -777,9 +813,11 @@ extern "C" int embclip_rn50_create(const embclip_rn50_cfg* cfg, embclip_rn50_t* 
       const std::string P(pfx);
       const int x = t;
       int xp = x;
-      if (stride == 2) xp = add_pool(m, P + ".xpool", x);   // identity-branch AvgPool2d: needs only x, so it is issued first (side stream)
+      // identity-branch AvgPool2d (CLIP) / stride-2 subsample (torchvision): needs only x, so it is issued first (side stream)
+      if (stride == 2) xp = add_pool(m, P + ".xpool", x, tv ? 2 : 1);
       int a = add_conv(m, P + ".conv1", x, -1, -1, 1, planes, 1);
-      int b = add_conv(m, P + ".conv2", a, -1, -1, 9, planes, 1, 0, /*pool=*/stride == 2);   // avgpool(stride) fused
+      // CLIP: avgpool(stride) after the stride-1 3x3, fused; torchvision: the 3x3 itself has the stride (epilogue keeps ::2)
+      int b = add_conv(m, P + ".conv2", a, -1, -1, 9, planes, 1, 0, /*pool=*/stride == 2 ? (tv ? 2 : 1) : 0);
       // conv3 (+ downsample conv fused along K when the block has one, else identity residual)
       if (down) t = add_conv(m, P + ".conv3", b, xp, -1, 1, planes * 4, 1, last ? 1 : 0);
       else      t = add_conv(m, P + ".conv3", b, -1, x, 1, planes * 4, 1, last ? 1 : 0);
@@ -931,8 +969,10 @@ static int run_op(embclip_rn50* m, const Op& op, const std::vector<uint64_t>& of
     }
     case K_POOL: {
       const Act& a = m->acts[op.in0];
-      return launch_avgpool2(act_ptr(op.in0), act_ptr(op.out), B, a.h, a.w, a.c, st);
+      return launch_avgpool2(act_ptr(op.in0), act_ptr(op.out), B, a.h, a.w, a.c, st, op.pool ? op.pool : 1);
     }
+    case K_IM2COL:
+      return launch_im2col7(frames.ptr, frames.u8, frames.u8 ? frames.norm : nullptr, act_ptr(op.out), B, m->cfg.input_resolution, st);
     case K_GEMM: {
       const Act& a = m->acts[op.in0];
       if (op.taps == 9) {

@@ -12,7 +12,7 @@ from typing import Dict, Iterable, List, Optional, Tuple
 import torch
 
 from . import _lib
-from .packing import infer_rn_cfg, pack_blob
+from .packing import infer_rn_cfg, infer_torchvision_cfg, pack_blob
 
 
 class ClipRN50Encoder:
@@ -27,6 +27,11 @@ class ClipRN50Encoder:
     CLIP_RGB_MEANS = (0.48145466, 0.4578275, 0.40821073)
     CLIP_RGB_STDS = (0.26862954, 0.26130258, 0.27577711)
 
+    ARCH = 0                     # embclip_rn50_cfg.arch
+
+    def _infer_cfg(self, state_dict):
+        return infer_rn_cfg(state_dict)
+
     def __init__(self, state_dict: Dict[str, torch.Tensor], device: torch.device | str = "cuda:0",
                  input_resolution: Optional[int] = None):
         """``input_resolution``: run the trunk at another resolution than the checkpoint's attention pool was trained for
@@ -36,12 +41,12 @@ class ClipRN50Encoder:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("embclip_b200 has no CPU path: ClipRN50Encoder needs a CUDA (sm_100a) device")
-        cfg = infer_rn_cfg(state_dict)
+        cfg = self._infer_cfg(state_dict)
         native = cfg["input_resolution"]
         if input_resolution is not None:
             cfg["input_resolution"] = int(input_resolution)
         tokens = (cfg["input_resolution"] // 32) ** 2 + 1
-        self.has_attnpool = cfg["input_resolution"] == native and tokens <= 64
+        self.has_attnpool = cfg["input_resolution"] == native and tokens <= 64 and cfg["output_dim"] > 0
         if not self.has_attnpool:
             cfg["input_resolution_native"] = native
         self.cfg = cfg
@@ -49,10 +54,11 @@ class ClipRN50Encoder:
         c.layers[:] = cfg["layers"]
         c.width, c.heads, c.input_resolution = cfg["width"], cfg["heads"], cfg["input_resolution"]
         c.output_dim = cfg["output_dim"] if self.has_attnpool else 0          # 0: plan without the attention-pool head
+        c.arch = self.ARCH
         self._h = C.c_void_p()
         _lib.check(self.lib.embclip_rn50_create(C.byref(c), C.byref(self._h)))
         self.param_infos = self._param_infos()
-        blob = pack_blob(state_dict, self.param_infos)
+        blob = pack_blob(state_dict, self.param_infos, arch=self.ARCH)
         with torch.cuda.device(self.device):
             self._blob = blob.to(self.device)
             _lib.check(self.lib.embclip_rn50_bind_weights(self._h, self._blob.data_ptr(), self._blob.numel()))
@@ -195,3 +201,23 @@ class ClipRN50Encoder:
                 self._h = None
         except Exception:
             pass
+
+
+class TorchvisionResNet50Encoder(ClipRN50Encoder):
+    """The reference's ImageNet baseline encoder: ``models.resnet50(pretrained=True)`` cut after layer4
+    (``nn.Sequential(*list(resnet.children())[:-2])``, primitive_probing/generate_data/thor_image_features.py:46-49; forward at
+    :101-105, reachable_image_features.py:49-52,81-85), frozen with ``freeze_model`` (:26-33).
+
+    frames fp32 NHWC [B,224,224,3] (normalised with the ImageNet mean / std of ``resnet_preprocess``, :36-44) or uint8 NHWC
+    (raw RGB, normalised in the im2col kernel) -> 'trunk' fp32 [B,2048,7,7] ('imagenet_conv') | 'avgpool' fp32 [B,2048]
+    ('imagenet_avgpool').  Same kernels as the CLIP plan: the 7x7/2 stem is an im2col + GEMM, the stride-2 3x3 conv is the
+    halo kernel keeping every second position, the stride-2 1x1 downsample is K-concatenated to conv3 after a ::2 subsample.
+    The state dict is torchvision's (``resnet50().state_dict()``) or the cut ``nn.Sequential``'s."""
+
+    ARCH = 1
+    HEADS = ("trunk", "avgpool")
+    CLIP_RGB_MEANS = (0.485, 0.456, 0.406)        # name kept from the base class: the mean / std applied to uint8 frames
+    CLIP_RGB_STDS = (0.229, 0.224, 0.225)
+
+    def _infer_cfg(self, state_dict):
+        return infer_torchvision_cfg(state_dict)

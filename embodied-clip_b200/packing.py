@@ -121,10 +121,72 @@ def packed_tensors(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     return out
 
 
-def pack_blob(sd: Dict[str, torch.Tensor], param_infos) -> torch.Tensor:
+# ---------------------------------------------------------------------------------------------------
+# torchvision ResNet-50 (the reference's ImageNet baseline encoder, thor_image_features.py:46-49)
+# ---------------------------------------------------------------------------------------------------
+_TV_SEQ = {"0": "conv1", "1": "bn1", "4": "layer1", "5": "layer2", "6": "layer3", "7": "layer4"}
+STEM7_K = 160          # 7 * 7 * 3 = 147 taps, zero-padded to a multiple of the 32-element k-block (csrc/tv_kernels.cuh)
+
+
+def torchvision_keys(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Accepts `models.resnet50().state_dict()` (conv1.weight, layer1.0.conv1.weight, ..., fc.* ignored) or the state dict of
+    the reference's `nn.Sequential(*list(resnet.children())[:-2])` (0.weight, 1.running_mean, 4.0.conv1.weight, ...)."""
+    if "conv1.weight" in sd:
+        return {k: v for k, v in sd.items() if not k.startswith("fc.")}
+    out = {}
+    for k, v in sd.items():
+        head, _, rest = k.partition(".")
+        if head in _TV_SEQ:
+            out[_TV_SEQ[head] + "." + rest] = v
+    if "conv1.weight" not in out:
+        raise KeyError("not a torchvision ResNet state dict (no conv1.weight / 0.weight)")
+    return out
+
+
+def infer_torchvision_cfg(sd: Dict[str, torch.Tensor]) -> dict:
+    sd = torchvision_keys(sd)
+    layers = []
+    for b in (1, 2, 3, 4):
+        idx = {int(m.group(1)) for k in sd for m in [re.match(rf"layer{b}\.(\d+)\.", k)] if m}
+        layers.append(len(idx))
+    width = int(sd["layer1.0.conv1.weight"].shape[0])
+    if tuple(sd["conv1.weight"].shape) != (64, 3, 7, 7) or "layer1.0.conv3.weight" not in sd:
+        raise ValueError("torchvision plan: expected a Bottleneck ResNet with a 7x7 stem of 64 channels")
+    return dict(layers=tuple(layers), width=width, heads=0, output_dim=0, input_resolution=224, arch=1)
+
+
+def packed_tensors_torchvision(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Same layouts as `packed_tensors` for the bottlenecks; the 7x7 stem becomes a [64, 160] fp16 GEMM weight whose K order
+    (kh, kw, c) is the one im2col7x7s2_kernel writes."""
+    sd = torchvision_keys(sd)
+    out: Dict[str, torch.Tensor] = {}
+    w, b = fold_bn(sd, "conv1", "bn1")
+    w = _kmajor(w)                                                      # [64, 147]
+    out["stem.conv1.w"] = torch.nn.functional.pad(w, (0, STEM7_K - w.shape[1])).half()
+    out["stem.conv1.b"] = b
+    blocks = sorted({(int(m.group(1)), int(m.group(2))) for k in sd
+                     for m in [re.match(r"layer(\d)\.(\d+)\.conv1\.weight", k)] if m})
+    for (li, bi) in blocks:
+        p = f"layer{li}.{bi}"
+        for i in (1, 2):
+            w, b = fold_bn(sd, f"{p}.conv{i}", f"{p}.bn{i}")
+            out[f"{p}.conv{i}.w"] = _kmajor(w).half()
+            out[f"{p}.conv{i}.b"] = b
+        w3, b3 = fold_bn(sd, p + ".conv3", p + ".bn3")
+        w3 = _kmajor(w3)
+        if p + ".downsample.0.weight" in sd:
+            wd, bd = fold_bn(sd, p + ".downsample.0", p + ".downsample.1")
+            w3 = torch.cat([w3, _kmajor(wd)], dim=1)
+            b3 = b3 + bd
+        out[p + ".conv3.w"] = w3.half()
+        out[p + ".conv3.b"] = b3
+    return out
+
+
+def pack_blob(sd: Dict[str, torch.Tensor], param_infos, arch: int = 0) -> torch.Tensor:
     """param_infos: iterable of (name, dtype('f16'|'f32'), shape tuple, offset, nbytes) as reported by the
     library.  Returns a uint8 CPU tensor holding every packed tensor at its offset."""
-    tensors = packed_tensors(sd)
+    tensors = packed_tensors_torchvision(sd) if arch == 1 else packed_tensors(sd)
     infos = list(param_infos)
     total = max(off + ((nb + 255) // 256) * 256 for _, _, _, off, nb in infos)
     blob = torch.zeros(total, dtype=torch.uint8)

@@ -101,3 +101,40 @@ def synthetic_clip_vit_b32_state_dict(seed: int = 1234, width: int = 768, layers
     sd["text_projection"] = rn(text_width, embed_dim) * text_width ** -0.5
     sd["logit_scale"] = torch.tensor(4.605170185988092)
     return sd
+
+
+def synthetic_torchvision_rn50_state_dict(seed: int = 4321, layers=(3, 4, 6, 3)) -> "OrderedDict[str, torch.Tensor]":
+    """Seeded synthetic weights with torchvision's ``resnet50().state_dict()`` key names (conv1 / bn1 / layer{1-4}.{i}.{conv,bn}{1-3} /
+    downsample.{0,1}; no fc) for the reference's ImageNet baseline encoder (thor_image_features.py:46-49).  Same
+    conditioning as the CLIP generator above: conv ~ N(0, 2/fan_in), BN gamma in U(.5,1.5) (x0.25 on bn3 / downsample BN: this
+    architecture adds the un-pooled identity, so the same residual gain as the CLIP set would grow the stream 12x over the 16
+    blocks), beta, running_mean ~ N(0,.1), running_var in U(.5,1.5)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    rn = lambda *s: torch.randn(*s, generator=g)
+    ru = lambda *s: torch.rand(*s, generator=g)
+
+    def conv(name, cout, cin, k):
+        sd[name + ".weight"] = rn(cout, cin, k, k) * (2.0 / (cin * k * k)) ** 0.5
+
+    def bn(name, c, gain=1.0):
+        sd[name + ".weight"] = (0.5 + ru(c)) * gain
+        sd[name + ".bias"] = 0.1 * rn(c)
+        sd[name + ".running_mean"] = 0.1 * rn(c)
+        sd[name + ".running_var"] = 0.5 + ru(c)
+        sd[name + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+
+    conv("conv1", 64, 3, 7); bn("bn1", 64)
+    inplanes = 64
+    for li, nblocks in enumerate(layers):
+        planes = 64 << li
+        for bi in range(nblocks):
+            p = f"layer{li + 1}.{bi}"
+            stride = 2 if (bi == 0 and li > 0) else 1
+            conv(p + ".conv1", planes, inplanes, 1); bn(p + ".bn1", planes)
+            conv(p + ".conv2", planes, planes, 3); bn(p + ".bn2", planes)
+            conv(p + ".conv3", planes * 4, planes, 1); bn(p + ".bn3", planes * 4, gain=0.25)
+            if stride > 1 or inplanes != planes * 4:
+                conv(p + ".downsample.0", planes * 4, inplanes, 1); bn(p + ".downsample.1", planes * 4, gain=0.25)
+            inplanes = planes * 4
+    return sd

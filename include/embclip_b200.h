@@ -50,6 +50,10 @@ typedef struct {
   int32_t heads;             /* 32 attention-pool heads                    */
   int32_t output_dim;        /* 1024 (RN50x16: 768); 0 = plan without the attention-pool head (trunk / avg-pool only) */
   int32_t input_resolution;  /* 224                                        */
+  int32_t arch;              /* 0: CLIP ModifiedResNet (clip/model.py).  1: torchvision ResNet with v1.5 Bottlenecks
+                              * (models.resnet50: the reference's ImageNet baseline encoder, thor_image_features.py:46-49) --
+                              * conv 7x7/2 + BN + ReLU + MaxPool(3,2,1) stem, stride on the 3x3 conv, strided 1x1 downsample;
+                              * width 64, output_dim 0; heads unused */
 } embclip_rn50_cfg;
 
 /* One packed parameter of the device weight blob.  Python (embclip_b200/packing.py) folds BatchNorm into
@@ -126,11 +130,16 @@ int embclip_gemm_grouped_f16(const void* a, int lda, const void* w, int ldw, int
                              void* out, int M, int N, int K, int grp_n, int grp_a_koff, int grp_b_koff,
                              int grp_b_nmod, int relu, int out_f32, void* stream);
 /* 3x3 / pad 1 / stride 1 conv, NHWC: in [B,H,W,Cin], w [Cout, 9*Cin] (tap-major: kh, kw, cin), out [B,H,W,Cout];
- * pool != 0 fuses the nn.AvgPool2d(2) that follows it in the anti-aliased strided Bottleneck / the stem:
- * out [B,H/2,W/2,Cout] = avgpool2(act(conv)) (H, W even).  Replaces nn.Conv2d(k=3, padding=1) + folded
+ * pool == 1 fuses the nn.AvgPool2d(2) that follows it in the anti-aliased strided Bottleneck / the stem:
+ * out [B,H/2,W/2,Cout] = avgpool2(act(conv)) (H, W even); pool == 2 keeps act(conv)[:, ::2, ::2] instead, i.e. the conv
+ * runs with STRIDE 2 (torchvision Bottleneck.conv2).  Replaces nn.Conv2d(k=3, padding=1) + folded
  * BatchNorm + ReLU (+ AvgPool2d) of clip/model.py Bottleneck / ModifiedResNet stem. */
 int embclip_conv3x3_f16(const void* in, const void* w, const float* bias, void* out, int B, int H, int W,
                         int Cin, int Cout, int relu, int pool, void* stream);
+/* 2x2-window pools on NHWC fp16 [B,H,W,C] -> [B,H/2,W/2,C] (H, W even, C % 8 == 0).  mode 1: nn.AvgPool2d(2) (CLIP's
+ * anti-aliasing pool); 2: x[:, ::2, ::2] (what a stride-2 1x1 conv reads); 3: nn.MaxPool2d(3, stride 2, padding 1)
+ * (torchvision ResNet stem). */
+int embclip_pool2_f16(const void* in, void* out, int B, int H, int W, int C, int mode, void* stream);
 /* Bottleneck tail + next head in one pass (clip/model.py Bottleneck.forward [UPSTREAM]: out = relu(bn3(conv3(y2)) + identity),
  * then the next block's relu(bn1(conv1(out)))):
  *   out[M,256] = relu([y2 | x0] . w3^T + b3 (+ residual));   y1[M,n1] = relu(out . w1^T + b1)

@@ -116,3 +116,44 @@ def rn50_fp16_path(m: ModifiedResNet, frames_nchw: torch.Tensor, quantize: bool 
     o = put2("attnpool.v", q(torch.einsum("bhc,hdc->bhd", xbar, wv).reshape(B, E) + ap.v_proj.bias), (B, 1, 1, E))
     acts["attnpool"] = o @ q(ap.c_proj.weight).t() + ap.c_proj.bias
     return acts
+
+
+@torch.no_grad()
+def torchvision_fp16_path(trunk: torch.nn.Sequential, frames_nchw: torch.Tensor, quantize: bool = True) -> Dict[str, torch.Tensor]:
+    """The same "ideal fp16 path" for the torchvision ResNet-50 trunk (oracle/imagenet_resnet.py): BatchNorm folded in fp32,
+    weights and the im2col'd frames rounded to fp16 once, one rounding per fused op (7x7 stem conv, conv1, strided conv2,
+    conv3 + K-concatenated strided downsample + add), max-pool exact, fp32 sums.  NCHW in, dict of NHWC activations out."""
+    q = _h if quantize else (lambda t: t)
+    acts: Dict[str, torch.Tensor] = {}
+
+    def put(name, t):
+        acts[name] = t.permute(0, 2, 3, 1).contiguous()
+        return t
+
+    def cbr(x, conv, bn, relu=True, extra=None, round_out=True):
+        w, b = _fold(conv, bn)
+        y = F.conv2d(x, q(w), None, conv.stride, conv.padding) + b[None, :, None, None]
+        if extra is not None:
+            y = y + extra
+        if relu:
+            y = F.relu(y)
+        return q(y) if round_out else y
+
+    x = put("stem.conv1", cbr(q(frames_nchw), trunk[0], trunk[1]))
+    x = put("stem.maxpool", trunk[3](x))
+    for li in range(4):
+        layer = trunk[4 + li]
+        for bi, blk in enumerate(layer):
+            p = f"layer{li + 1}.{bi}"
+            last = li == 3 and bi == len(layer) - 1
+            a = put(p + ".conv1", cbr(x, blk.conv1, blk.bn1))
+            b = put(p + ".conv2", cbr(a, blk.conv2, blk.bn2))
+            if blk.downsample is not None:
+                wd, bd = _fold(blk.downsample[0], blk.downsample[1])
+                idn = F.conv2d(x, q(wd), None, blk.downsample[0].stride) + bd[None, :, None, None]
+            else:
+                idn = x
+            x = put(p + ".conv3", cbr(b, blk.conv3, blk.bn3, extra=idn, round_out=not last))
+    acts["trunk_nchw"] = x
+    acts["avgpool"] = x.mean(dim=(2, 3))
+    return acts

@@ -59,12 +59,18 @@ def test_rn50x16_vs_fp32_oracle(x16_encoder, x16_visual):
     out = x16_encoder(frames.cuda(), want=("trunk", "avgpool", "attnpool"))
     torch.cuda.synchronize()
     e = dict(trunk=rel_l2(out["trunk"].cpu(), t), avgpool=rel_l2(out["avgpool"].cpu(), t.mean((2, 3))), attnpool=rel_l2(out["attnpool"].cpu(), ap))
-    print("RN50x16 rel-L2 vs fp32 oracle:", e)
-    # The heads AllenAct uses (trunk, avg-pool) hold the 1e-3 north-star bar (measured 9.3e-4 / 4.5e-4).  The attention pool
-    # at 224 x 224 exists only for synthetic weights (a real RN50x16 checkpoint has a 12 x 12 positional embedding and AllenAct
-    # never calls it); after 40 sequential fp16-stored bottlenecks it measures 1.02e-3, so it is bounded at 1.5e-3.
+    from oracle.fp16_path import rn50_fp16_path
+    ideal = rn50_fp16_path(x16_visual, frames.permute(0, 3, 1, 2).contiguous())
+    i = dict(trunk=rel_l2(ideal["trunk_nchw"], t), avgpool=rel_l2(ideal["avgpool"], t.mean((2, 3))), attnpool=rel_l2(ideal["attnpool"], ap))
+    print("RN50x16 rel-L2 vs fp32 oracle:", e, "| ideal one-rounding-per-op fp16 path (CPU):", i)
+    # The heads AllenAct uses (trunk, avg-pool) hold the 1e-3 north-star bar.  The attention pool at 224 x 224 exists only for
+    # synthetic weights (a real RN50x16 checkpoint has a 12 x 12 positional embedding and AllenAct never calls it); after 40
+    # sequential fp16-stored bottlenecks the IDEAL fp16 path itself (same rounding points, torch fp32 sums on the CPU) is at
+    # ~1e-3 there, which no fp16-operand kernel can beat: that head is held to the ideal path (<= 1.1 x), not to 1e-3.
+    # (r2 measured that keeping the residual stream in fp32 buys only 9 %: the error is the two in-branch activation
+    # roundings and three weight roundings per block, not the stream.)
     assert e["trunk"] <= 1e-3 and e["avgpool"] <= 1e-3, e
-    assert e["attnpool"] <= 1.5e-3, e
+    assert e["attnpool"] <= max(1e-3, 1.1 * i["attnpool"]), (e, i)
 
 
 def test_rn50x16_native_resolution_and_plugin(built_lib):
@@ -86,7 +92,12 @@ def test_rn50x16_native_resolution_and_plugin(built_lib):
     with torch.no_grad():
         t = ref.trunk(frames.permute(0, 3, 1, 2).contiguous())
     assert out["trunk"].shape == (1, 3072, 12, 12)
-    assert rel_l2(out["trunk"].cpu(), t) <= 1.5e-3 and rel_l2(out["avgpool"].cpu(), t.mean((2, 3))) <= 1e-3
+    from oracle.fp16_path import rn50_fp16_path
+    ideal = rel_l2(rn50_fp16_path(ref, frames.permute(0, 3, 1, 2).contiguous())["trunk_nchw"], t)
+    e384 = rel_l2(out["trunk"].cpu(), t)
+    print(f"RN50x16 @ 384: trunk rel-L2 {e384:.3e}; ideal fp16 path {ideal:.3e}")
+    # 144 positions x 40 blocks: where the ideal fp16 path is above the bar the kernels are held to it, not to a looser constant
+    assert e384 <= max(1e-3, 1.1 * ideal) and rel_l2(out["avgpool"].cpu(), t.mean((2, 3))) <= 1e-3
     with pytest.raises(ValueError):
         enc(frames.cuda(), want=("attnpool",))
     for pool, shape in ((False, (2, 3072, 7, 7)), (True, (2, 3072))):
@@ -98,4 +109,4 @@ def test_rn50x16_native_resolution_and_plugin(built_lib):
         with torch.no_grad():
             t224 = ref.trunk(f224.permute(0, 3, 1, 2).contiguous())
         assert tuple(y.shape) == shape and y.dtype == torch.float32
-        assert rel_l2(y.cpu(), t224.mean((2, 3)) if pool else t224) <= 1.5e-3
+        assert rel_l2(y.cpu(), t224.mean((2, 3)) if pool else t224) <= 1e-3
