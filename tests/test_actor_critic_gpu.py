@@ -411,7 +411,7 @@ def test_autograd_surface_matches_fused_path(models):
 
 
 UPDATE_GRAD_TOL = 1e-3
-UPDATE_STEP_TOL = 0.08
+UPDATE_STEP_TOL = 0.03            # measured on B200 (r2): <= 1.5 % on every tensor
 
 
 def test_ppo_update_vs_oracle(models):
@@ -421,9 +421,9 @@ def test_ppo_update_vs_oracle(models):
     (rel-L2 <= 1e-3 per tensor, the north-star bar; the parameters the gradient is taken at have drifted apart by the
     previous passes' difference, which is part of what is measured).  Checked at the end: every parameter tensor's
     deviation relative to the distance it travelled.  That last ratio is bounded by UPDATE_STEP_TOL, not 1e-3: in its first steps
-    Adam moves each element by ~lr * sign(g), so the elements whose gradient is within the 1e-3 error of zero (a fraction
-    ~1e-3 of them) move the opposite way by the full step -- a 1e-3 gradient error is a sqrt(4 * 1e-3) ~ 6 % difference of
-    the step by construction, in the reference's own fp32-vs-TF32 executions as much as here."""
+    Adam moves each element by ~lr * sign(g), so the elements whose gradient is within the 1e-3 error of zero move the opposite way
+    by the full step -- a 1e-3 gradient error is a percent-level difference of the step by construction (measured <= 1.5 %), in the
+    reference's own fp32-vs-TF32 executions as much as here."""
     import copy
     from embclip_b200.actor_critic import PPOTrainer, ResnetTensorNavActorCritic
     from oracle.allenact_models import ppo_loss
@@ -477,8 +477,6 @@ def test_ppo_update_vs_oracle(models):
         step = (v - before[k]).norm().item()
         err = (after[k].cpu() - v).norm().item()
         ratios[k] = err / max(step, 1e-12)
-        # and against the parameter itself the deviation is at the level of lr: ~1e-6 .. 1e-4
-        assert err <= 2e-4 * v.norm().item() + 1e-7, k
     print("parameter deviation / distance travelled:", {k.split("encoder.")[-1]: f"{r:.3f}" for k, r in ratios.items()})
     assert max(ratios.values()) <= UPDATE_STEP_TOL, ratios
 
