@@ -29,7 +29,8 @@ class ActInfo(C.Structure):
 
 class ACCfg(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("feat_channels", "feat_pixels", "compress_hidden", "compress_out", "goal_dims",
-                                         "combine_hidden", "combine_out", "hidden", "num_actions", "num_goals")]
+                                         "combine_hidden", "combine_out", "hidden", "num_actions", "num_goals",
+                                         "trainable_masked_hidden_state")]
 
 
 class TFCfg(C.Structure):
@@ -95,8 +96,8 @@ SIGNATURES = {
     "embclip_sumsq_f32": (_I, [_FP, _LL, _FP, _VP]),
     "embclip_adam_clip_step": (_I, [_FP, _FP, _FP, _FP, _LL, _FP, _F, _F, _F, _F, _F, _I, _VP]),
     "embclip_wgrad_f16": (_I, [_VP, _I, _I, _VP, _I, _I, _LL, _FP, _LL, _LL, _FP, _VP]),
-    "embclip_gru_forward": (_I, [_FP, _FP, _FP, _FP, _FP, _I, _I, _I, _FP, _FP, _FP, _FP, _FP, _VP, _VP]),
-    "embclip_gru_backward": (_I, [_FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _I, _I, _I, _FP, _FP, _VP, _FP, _VP, _VP]),
+    "embclip_gru_forward": (_I, [_FP, _FP, _FP, _FP, _FP, _FP, _I, _I, _I, _FP, _FP, _FP, _FP, _FP, _VP, _VP]),
+    "embclip_gru_backward": (_I, [_FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _I, _I, _I, _FP, _FP, _VP, _FP, _FP, _VP, _VP]),
 }
 
 _lib = None

@@ -176,7 +176,7 @@ class ResnetTensorNavActorCritic(nn.Module):
                  resnet_compressor_hidden_out_dims: Tuple[int, int] = (128, 32),
                  combiner_hidden_out_dims: Tuple[int, int] = (128, 32), num_actions: Optional[int] = None,
                  num_goals: Optional[int] = None, resnet_tensor_shape: Tuple[int, int, int] = (2048, 7, 7),
-                 device: Any = "cuda:0", seed: Optional[int] = None):
+                 device: Any = "cuda:0", seed: Optional[int] = None, trainable_masked_hidden_state: bool = False):
         super().__init__()
         if num_actions is None:
             num_actions = int(getattr(action_space, "n", 6))
@@ -192,7 +192,8 @@ class ResnetTensorNavActorCritic(nn.Module):
         cfg = dict(feat_channels=resnet_tensor_shape[0], feat_pixels=resnet_tensor_shape[1] * resnet_tensor_shape[2],
                    compress_hidden=resnet_compressor_hidden_out_dims[0], compress_out=resnet_compressor_hidden_out_dims[1],
                    goal_dims=goal_dims, combine_hidden=combiner_hidden_out_dims[0], combine_out=combiner_hidden_out_dims[1],
-                   hidden=hidden_size, num_actions=num_actions, num_goals=num_goals)
+                   hidden=hidden_size, num_actions=num_actions, num_goals=num_goals,
+                   trainable_masked_hidden_state=int(bool(trainable_masked_hidden_state)))
         self._plan = _ACPlan(cfg)
         dev = torch.device(device)
         if dev.type != "cuda":
@@ -226,6 +227,8 @@ class ResnetTensorNavActorCritic(nn.Module):
                 cpu = torch.empty(t.shape, dtype=torch.float32)
                 if name.endswith("embed_class.weight"):
                     cpu.normal_(0, 1, generator=g)
+                elif name.endswith("init_hidden_state"):                # RNNStateEncoder: 0.1 * randn
+                    cpu.normal_(0, 0.1, generator=g)
                 elif "rnn.weight" in name:
                     nn.init.orthogonal_(cpu, generator=g)
                 elif name == "actor.linear.weight":
@@ -485,6 +488,79 @@ class PPOTrainer:
             return 1
         return dist.get_world_size(self.process_group) if dist.is_available() and dist.is_initialized() else 1
 
+    def _step_block(self, bk: Dict[str, Any], T: int, mb_grows: float, lr: float) -> None:
+        """One backprop_step on a contiguous [T, n] block: forward, PPO loss (+ dlogits / dvalues), backward, gradient
+        all-reduce, global-norm clip + Adam.  bk: n, feats (fp16 rows), goals, masks, h0, actions, old_lp, old_v, rets, nadv."""
+        from .distributed import allreduce_flat_
+        mdl, plan = self.model, self.model._plan
+        lib, dev = plan.lib, mdl.flat_params.device
+        A = plan.cfg["num_actions"]
+        n = bk["n"]
+        P = mdl.flat_params.data
+        st = _stream(dev)
+        logits = torch.empty(T, n, A, dtype=torch.float32, device=dev)
+        values = torch.empty(T, n, dtype=torch.float32, device=dev)
+        ws = mdl._workspace(T, n)
+        mdl._touch_workspace()
+        with torch.cuda.device(dev):
+            _lib.check(lib.embclip_ac_forward(plan._h, P.data_ptr(), bk["feats"].data_ptr(), bk["goals"].data_ptr(),
+                                              bk["masks"].data_ptr(), bk["h0"].data_ptr(), T, n, logits.data_ptr(),
+                                              values.data_ptr(), None, ws.data_ptr(), ws.numel(), 1, st))
+            _lib.check(lib.embclip_ac_ppo_loss(plan._h, P.data_ptr(), T, n, bk["actions"].data_ptr(), bk["old_lp"].data_ptr(),
+                                               bk["nadv"].data_ptr(), bk["old_v"].data_ptr(), bk["rets"].data_ptr(),
+                                               self.clip_param, self.value_loss_coef, self.entropy_coef, 1.0 / mb_grows,
+                                               logits.data_ptr(), values.data_ptr(), self.loss_sums.data_ptr(), ws.data_ptr(),
+                                               ws.numel(), st))
+            self.grads.zero_()
+            _lib.check(lib.embclip_ac_backward(plan._h, P.data_ptr(), bk["feats"].data_ptr(), bk["goals"].data_ptr(),
+                                               bk["masks"].data_ptr(), bk["h0"].data_ptr(), T, n, None, None, None,
+                                               self.grads.data_ptr(), ws.data_ptr(), ws.numel(), st))
+            if self.distributed:
+                allreduce_flat_(self.grads, self.process_group)   # the path's one collective (no-op when world == 1)
+            self.step_count += 1
+            _lib.check(lib.embclip_sumsq_f32(self.grads.data_ptr(), self.grads.numel(), self.sumsq.data_ptr(), st))
+            _lib.check(lib.embclip_adam_clip_step(P.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(),
+                                                  self.exp_avg_sq.data_ptr(), P.numel(), self.sumsq.data_ptr(),
+                                                  self.max_grad_norm, lr, self.betas[0], self.betas[1], self.eps,
+                                                  self.step_count, st))
+        mdl.mark_params_changed()                              # raw-pointer update: torch's version counter does not see it
+
+    def _loss_info(self, rows: int) -> Dict[str, torch.Tensor]:
+        return self._loss_info(rows)
+
+    def update_from_storage(self, storage: Any, global_rows: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """OnPolicyTrainer.update(rollouts) [UPSTREAM engine.py]: ``update_repeats`` x ``storage.recurrent_generator(...,
+        num_mini_batch)`` x backprop_step, on an ``embclip_b200.storage.RolloutStorage`` whose ``compute_returns`` has run
+        (advantages normalised over this rank's block, as upstream).  The caller runs ``storage.after_update()`` afterwards."""
+        mdl = self.model
+        dev = mdl.flat_params.device
+        T, N, H = storage.num_steps, storage.num_samplers, mdl.hidden_size
+        world = self._world()
+        grows = global_rows if global_rows is not None else T * N * world
+        lr = self.lr
+        rows = T * N
+        packed_once: Dict[Any, PackedFeatures] = {}        # fp32 storage (the AllenAct flow): pack each chunk once per update, not per repeat
+        for _ in range(self.update_repeats):
+            for batch in storage.recurrent_generator(None, None, None, self.num_mini_batch):
+                a, b = batch["samplers"]
+                n = b - a
+                feats = batch["observations"][mdl.resnet_uuid]
+                if isinstance(feats, PackedFeatures):
+                    pf = feats
+                else:
+                    if (a, b) not in packed_once:
+                        packed_once[(a, b)] = mdl.pack_features(feats)
+                    pf = packed_once[(a, b)]
+                bk = dict(n=n, feats=pf.data, goals=batch["observations"][mdl.goal_uuid].reshape(T, n).to(dev, torch.int64).contiguous(),
+                          masks=_f32c(batch["masks"].reshape(T, n)), h0=_f32c(batch["memory"].tensor("rnn").reshape(n, H)),
+                          actions=batch["actions"].reshape(T, n).to(dev, torch.int64).contiguous(),
+                          old_lp=_f32c(batch["old_action_log_probs"].reshape(T, n)), old_v=_f32c(batch["values"].reshape(T, n)),
+                          rets=_f32c(batch["returns"].reshape(T, n)), nadv=_f32c(batch["norm_adv_targ"].reshape(T, n)))
+                self._step_block(bk, T, grows * n / N, lr)
+                rows = T * n
+        self.total_steps += int(grows)
+        return self._loss_info(rows)
+
     def update(self, rollout: Dict[str, Any], global_rows: Optional[int] = None) -> Dict[str, torch.Tensor]:
         """rollout: features (fp32 [T,N,2048,7,7] or PackedFeatures), goals [T,N], masks [T,N,1], memory [1,N,H],
         actions [T,N], old_action_log_probs [T,N], values [T,N,1], returns [T,N,1], norm_adv_targ [T,N,1].
@@ -527,42 +603,13 @@ class PPOTrainer:
 
         blocks = {c: block(*c) for c in chunks}            # sliced once, reused by every repeat
         lr = self.lr
-        with torch.cuda.device(dev):
-            for _ in range(self.update_repeats):
-                order = list(chunks)
-                if nmb > 1:
-                    self._rng.shuffle(order)
-                for c in order:
-                    bk = blocks[c]
-                    n = bk["n"]
-                    mb_grows = grows * n / N               # rows of this mini-batch over all ranks (equal splits on every rank)
-                    logits = torch.empty(T, n, A, dtype=torch.float32, device=dev)
-                    values = torch.empty(T, n, dtype=torch.float32, device=dev)
-                    ws = mdl._workspace(T, n)
-                    mdl._touch_workspace()
-                    _lib.check(lib.embclip_ac_forward(plan._h, P.data_ptr(), bk["feats"].data_ptr(), bk["goals"].data_ptr(),
-                                                      bk["masks"].data_ptr(), bk["h0"].data_ptr(), T, n, logits.data_ptr(),
-                                                      values.data_ptr(), None, ws.data_ptr(), ws.numel(), 1, st))
-                    _lib.check(lib.embclip_ac_ppo_loss(plan._h, P.data_ptr(), T, n, bk["actions"].data_ptr(), bk["old_lp"].data_ptr(),
-                                                       bk["nadv"].data_ptr(), bk["old_v"].data_ptr(), bk["rets"].data_ptr(),
-                                                       self.clip_param, self.value_loss_coef, self.entropy_coef, 1.0 / mb_grows,
-                                                       logits.data_ptr(), values.data_ptr(), self.loss_sums.data_ptr(), ws.data_ptr(),
-                                                       ws.numel(), st))
-                    self.grads.zero_()
-                    _lib.check(lib.embclip_ac_backward(plan._h, P.data_ptr(), bk["feats"].data_ptr(), bk["goals"].data_ptr(),
-                                                       bk["masks"].data_ptr(), bk["h0"].data_ptr(), T, n, None, None, None,
-                                                       self.grads.data_ptr(), ws.data_ptr(), ws.numel(), st))
-                    if self.distributed:
-                        allreduce_flat_(self.grads, self.process_group)   # the path's one collective (no-op when world == 1)
-                    self.step_count += 1
-                    _lib.check(lib.embclip_sumsq_f32(self.grads.data_ptr(), self.grads.numel(), self.sumsq.data_ptr(), st))
-                    _lib.check(lib.embclip_adam_clip_step(P.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(),
-                                                          self.exp_avg_sq.data_ptr(), P.numel(), self.sumsq.data_ptr(),
-                                                          self.max_grad_norm, lr, self.betas[0], self.betas[1], self.eps,
-                                                          self.step_count, st))
-                    mdl.mark_params_changed()                          # raw-pointer update: torch's version counter does not see it
-                    rows = T * n
+        for _ in range(self.update_repeats):
+            order = list(chunks)
+            if nmb > 1:
+                self._rng.shuffle(order)
+            for c in order:
+                bk = blocks[c]
+                self._step_block(bk, T, grows * bk["n"] / N, lr)      # rows of this mini-batch over all ranks (equal splits on every rank)
+                rows = T * bk["n"]
         self.total_steps += int(grows)                                  # lr_scheduler.step(epoch=total_steps) [UPSTREAM]
-        s = self.loss_sums / rows
-        return {"action": s[0], "value": s[1], "entropy": -s[2],
-                "total": s[0] + self.value_loss_coef * s[1] - self.entropy_coef * s[2], "grad_norm": self.sumsq.sqrt()[0]}
+        return self._loss_info(rows)

@@ -151,13 +151,14 @@ int launch_gru_backward(GruBwdParams p, cudaStream_t st) {
 }  // namespace
 
 extern "C" int embclip_gru_forward(const float* gi, const float* w_hh, const float* b_hh, const float* h0, const float* masks,
-                                   int T, int N, int H, float* out, float* save_r, float* save_z, float* save_n, float* save_hn,
-                                   void* scratch32, void* stream) {
+                                   const float* h_init, int T, int N, int H, float* out, float* save_r, float* save_z, float* save_n,
+                                   float* save_hn, void* scratch32, void* stream) {
   if (!gi || !w_hh || !b_hh || !h0 || !masks || !out || !scratch32) return fail(EMBCLIP_EINVAL, "gru_forward: null pointer");
   if (T <= 0) return fail(EMBCLIP_EINVAL, "gru_forward: T must be positive");
   GruFwdParams p;
   memset(&p, 0, sizeof p);
   p.T = T; p.N = N; p.H = H; p.gi = gi; p.w_hh = w_hh; p.b_hh = b_hh; p.h0 = h0; p.masks = masks; p.out = out;
+  p.h_init = h_init;
   p.r = save_r; p.z = save_z; p.n = save_n; p.hn = save_hn;
   p.bar = reinterpret_cast<unsigned int*>(scratch32);
   return launch_gru_forward(p, (cudaStream_t)stream);
@@ -165,8 +166,8 @@ extern "C" int embclip_gru_forward(const float* gi, const float* w_hh, const flo
 
 extern "C" int embclip_gru_backward(const float* w_hh, const float* h0, const float* masks, const float* out, const float* save_r,
                                     const float* save_z, const float* save_n, const float* save_hn, const float* dout,
-                                    const float* dh_last, int T, int N, int H, float* dgi, float* dgh, void* hm_f16, float* dh0,
-                                    void* scratch32, void* stream) {
+                                    const float* dh_last, const float* h_init, int T, int N, int H, float* dgi, float* dgh,
+                                    void* hm_f16, float* dh0, float* dh_init, void* scratch32, void* stream) {
   if (!w_hh || !h0 || !masks || !out || !save_r || !save_z || !save_n || !save_hn || !dout || !dgi || !dgh || !hm_f16 || !scratch32)
     return fail(EMBCLIP_EINVAL, "gru_backward: null pointer");
   if (T <= 0) return fail(EMBCLIP_EINVAL, "gru_backward: T must be positive");
@@ -174,6 +175,8 @@ extern "C" int embclip_gru_backward(const float* w_hh, const float* h0, const fl
   memset(&p, 0, sizeof p);
   p.T = T; p.N = N; p.H = H; p.w_hh = w_hh; p.h0 = h0; p.masks = masks; p.out = out;
   p.r = save_r; p.z = save_z; p.n = save_n; p.hn = save_hn; p.dout = dout; p.dhT = dh_last;
+  p.h_init = h_init; p.dh_init = dh_init;
+  if ((h_init == nullptr) != (dh_init == nullptr)) return fail(EMBCLIP_EINVAL, "gru_backward: pass both h_init and dh_init, or neither");
   p.dgi = dgi; p.dgh = dgh; p.hm_h = reinterpret_cast<__half*>(hm_f16); p.dh0 = dh0;
   p.bar = reinterpret_cast<unsigned int*>(scratch32);
   p.amax = p.bar + kGruAmaxSlot;
@@ -186,7 +189,7 @@ extern "C" int embclip_gru_backward(const float* w_hh, const float* h0, const fl
 // =============================================================================================
 namespace {
 
-enum PId { P_EMBED, P_C1W, P_C1B, P_C2W, P_C2B, P_M1W, P_M1B, P_M2W, P_M2B, P_WIH, P_WHH, P_BIH, P_BHH, P_AW, P_AB, P_CW, P_CB, P_COUNT };
+enum PId { P_EMBED, P_C1W, P_C1B, P_C2W, P_C2B, P_M1W, P_M1B, P_M2W, P_M2B, P_WIH, P_WHH, P_BIH, P_BHH, P_AW, P_AB, P_CW, P_CB, P_HINIT, P_COUNT };
 
 }  // namespace
 
@@ -194,6 +197,7 @@ struct embclip_ac {
   embclip_ac_cfg cfg;
   embclip_param_info params[P_COUNT];
   uint64_t param_floats = 0;
+  int num_params = 0;            // P_COUNT - 1 unless cfg.trainable_masked_hidden_state (P_HINIT is the last slot)
   // fp16 weight layouts left in a workspace by the last forward: (params version, params, workspace, T, N).  embclip_ac_act
   // skips re-packing when its key equals this one; every other entry point that touches a workspace overwrites the key.
   uint64_t packed_version = 0;
@@ -250,13 +254,18 @@ extern "C" int embclip_ac_create(const embclip_ac_cfg* cfg, embclip_ac_t* out) {
   ac_add_param(m, P_AB, "actor.linear.bias", {c.num_actions});
   ac_add_param(m, P_CW, "critic.fc.weight", {1, H});
   ac_add_param(m, P_CB, "critic.fc.bias", {1});
+  m->num_params = P_COUNT - 1;
+  if (c.trainable_masked_hidden_state) {       // RNNStateEncoder(trainable_masked_hidden_state=True): learned episode-start state
+    ac_add_param(m, P_HINIT, "state_encoder.init_hidden_state", {1, 1, H});
+    m->num_params = P_COUNT;
+  }
   *out = m;
   return 0;
 }
 extern "C" int embclip_ac_destroy(embclip_ac_t h) { delete h; return 0; }
-extern "C" int embclip_ac_num_params(embclip_ac_t h) { return h ? (int)P_COUNT : fail(EMBCLIP_EINVAL, "null handle"); }
+extern "C" int embclip_ac_num_params(embclip_ac_t h) { return h ? h->num_params : fail(EMBCLIP_EINVAL, "null handle"); }
 extern "C" int embclip_ac_param_info(embclip_ac_t h, int index, embclip_param_info* out) {
-  if (!h || !out || index < 0 || index >= P_COUNT) return fail(EMBCLIP_EINVAL, "ac_param_info: bad argument");
+  if (!h || !out || index < 0 || index >= h->num_params) return fail(EMBCLIP_EINVAL, "ac_param_info: bad argument");
   *out = h->params[index];
   return 0;
 }
@@ -435,6 +444,7 @@ static int ac_forward_impl(embclip_ac_t h, const float* params, uint64_t params_
   memset(&gp, 0, sizeof gp);
   gp.T = T; gp.N = N; gp.H = H; gp.gi = w.GI; gp.w_hh = P(h, params, P_WHH); gp.b_hh = P(h, params, P_BHH); gp.h0 = h0;
   gp.masks = masks; gp.out = w.Hout;
+  gp.h_init = c.trainable_masked_hidden_state ? P(h, params, P_HINIT) : nullptr;
   if (save_for_backward) { gp.r = w.R; gp.z = w.Z; gp.n = w.Nn; gp.hn = w.HN; }
   gp.bar = w.scratch32;
   if ((rc = launch_gru_forward(gp, st))) return rc;
@@ -530,6 +540,7 @@ extern "C" int embclip_ac_backward(embclip_ac_t h, const float* params, const vo
   gp.T = T; gp.N = N; gp.H = H; gp.w_hh = P(h, params, P_WHH); gp.h0 = h0; gp.masks = masks; gp.out = w.Hout;
   gp.r = w.R; gp.z = w.Z; gp.n = w.Nn; gp.hn = w.HN; gp.dout = w.dH; gp.dhT = dh_last;
   gp.dgi = w.dGI; gp.dgh = w.dGH; gp.hm_h = w.hm_h; gp.dh0 = nullptr;
+  if (c.trainable_masked_hidden_state) { gp.h_init = P(h, params, P_HINIT); gp.dh_init = PG(h, grads, P_HINIT); }
   gp.bar = w.scratch32; gp.amax = w.scratch32 + kGruAmaxSlot;
   CUDA_TRY(cudaMemsetAsync(gp.amax, 0, sizeof(unsigned int), st));
   if ((rc = launch_gru_backward(gp, st))) return rc;

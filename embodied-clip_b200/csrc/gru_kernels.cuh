@@ -1,8 +1,9 @@
 // RNNStateEncoder (allenact basic_models; 1-layer nn.GRU with episode masking) as two persistent cooperative
 // kernels, forward and BPTT.  fp32 throughout (the recurrence feeds itself 128 times: no fp16 here).
 //
-//   hm_t = h_{t-1} * mask_t                                  (mask 0 = episode start, applied IN the kernel:
-//   gh   = W_hh hm_t + b_hh                                    upstream splits the sequence on the host instead)
+//   hm_t = h_{t-1} * mask_t  (+ (1 - mask_t) * h_init)       (mask 0 = episode start, applied IN the kernel:
+//   gh   = W_hh hm_t + b_hh                                    upstream splits the sequence on the host instead;
+//                                                              h_init = RNNStateEncoder(trainable_masked_hidden_state=True))
 //   r = sigmoid(gi_r + gh_r)   z = sigmoid(gi_z + gh_z)   n = tanh(gi_n + r * gh_n)
 //   h_t = (1 - z) * n + z * hm_t
 //
@@ -29,6 +30,7 @@ struct GruFwdParams {
   const float* b_hh;         // [3H]
   const float* h0;           // [N][H]
   const float* masks;        // [T][N]
+  const float* h_init;       // [H] learned state an episode starts from, or null (zeros)
   float* out;                // [T][N][H]
   float* r; float* z; float* n; float* hn;   // [T][N][H] each, or all null (inference)
   unsigned int* bar;         // [groups], zeroed before launch
@@ -100,6 +102,11 @@ gru_forward_kernel(const GruFwdParams p) {
       const float m = p.masks[(size_t)t * p.N + s0 + s];
       float4 v = __ldcg(reinterpret_cast<const float4*>(hprev + (size_t)(s0 + s) * H) + k4);
       v.x *= m; v.y *= m; v.z *= m; v.w *= m;
+      if (p.h_init) {
+        const float4 hi = __ldg(reinterpret_cast<const float4*>(p.h_init) + k4);
+        const float om = 1.f - m;
+        v.x += om * hi.x; v.y += om * hi.y; v.z += om * hi.z; v.w += om * hi.w;
+      }
       *reinterpret_cast<float4*>(sH + s * HP + 4 * k4) = v;
     }
     __syncthreads();
@@ -161,6 +168,8 @@ struct GruBwdParams {
   const float* r; const float* z; const float* n; const float* hn;
   const float* dout;         // [T][N][H] gradient w.r.t. the GRU outputs
   const float* dhT;          // [N][H] gradient w.r.t. the final hidden state, or null
+  const float* h_init;       // [H] or null (see GruFwdParams)
+  float* dh_init;            // [H] accumulated (atomicAdd) gradient of h_init, or null
   float* dgi;                // [T][N][3H]
   float* dgh;                // [T][N][3H]
   __half* hm_h;              // [T][N][H] masked previous hidden state, fp16 (operand of the dW_hh contraction)
@@ -195,6 +204,8 @@ gru_backward_kernel(const GruBwdParams p) {
   const int es = tid >> 3, eu = tid & 7;
   const bool live = es < ns;
   float carry = (live && p.dhT) ? p.dhT[(size_t)(s0 + es) * H + u0 + eu] : 0.f;
+  const float hinit = (live && p.h_init) ? p.h_init[u0 + eu] : 0.f;
+  float dinit = 0.f;
   float amax = 0.f;
   unsigned int nbar = 0;
 
@@ -207,7 +218,7 @@ gru_backward_kernel(const GruBwdParams p) {
       const float r = p.r[o], z = p.z[o], n = p.n[o], hn = p.hn[o];
       m = p.masks[row];
       const float hprev = t == 0 ? p.h0[(size_t)(s0 + es) * H + u0 + eu] : __ldcg(p.out + o - (size_t)p.N * H);
-      const float hm = hprev * m;
+      const float hm = hprev * m + (1.f - m) * hinit;
       const float dn = dh * (1.f - z);
       const float dz = dh * (hm - n);
       direct = dh * z;
@@ -262,8 +273,10 @@ gru_backward_kernel(const GruBwdParams p) {
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == a * kGruUB + b) mine = v;
       }
+    dinit += (direct + mine) * (1.f - m);
     carry = (direct + mine) * m;
   }
+  if (live && p.dh_init) atomicAdd(p.dh_init + u0 + eu, dinit);
   if (live && p.dh0) p.dh0[(size_t)(s0 + es) * H + u0 + eu] = carry;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));

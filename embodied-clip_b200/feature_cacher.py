@@ -7,10 +7,12 @@ and encoded in batches by `ClipRN50Encoder` (normalisation happens in the stem k
 device->host copy per batch.  The label tensors are computed with vectorised numpy instead of a Python loop per object.
 
 Output layout is the reference's (`thor_{split}.pt` = {scene_name: [ {key: tensor} per point ]}, :129-140) with the keys
-'clip_conv' [2048,7,7], 'clip_attnpool' [1024], 'clip_avgpool' [2048], 'object_presence' int64 [52],
-'object_localization' int64 [9,52], 'free_space'.  The 'imagenet_conv' / 'imagenet_avgpool' keys are NOT produced: the
-torchvision ImageNet ResNet-50 is outside this library's scope (section 8f item 4); `primitive_probing/train.py` only reads
-the key named by its --embedding_type, so the CLIP probes run unchanged.
+'imagenet_conv' [2048,7,7], 'imagenet_avgpool' [2048] (when an ImageNet encoder is given: `TorchvisionResNet50Encoder`, the
+reference's `models.resnet50` cut after layer4, :46-49,101-105), 'clip_conv' [2048,7,7], 'clip_attnpool' [1024],
+'clip_avgpool' [2048], 'object_presence' int64 [52], 'object_localization' int64 [9,52], 'free_space'.
+
+`cache_reachable` is the twin of primitive_probing/generate_data/reachable_image_features.py:24-25,77-100: a directory of
+PNG frames -> `reachable_image_features.pt` = {image_name: {'imagenet_avgpool', 'clip_avgpool', 'clip_attnpool'}}.
 """
 from __future__ import annotations
 
@@ -21,7 +23,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import torch
 
-from .encoder import ClipRN50Encoder
+from .encoder import ClipRN50Encoder, TorchvisionResNet50Encoder
 
 # the 52 iTHOR object types probed by the reference (primitive_probing/constants.py:1) -- label order is part of the file format
 TARGET_OBJECTS = (
@@ -81,18 +83,28 @@ def presence_labels(semantic_frame: np.ndarray, object_id_to_color: Dict[str, Se
 
 
 class FeatureCacher:
-    def __init__(self, encoder: ClipRN50Encoder, batch: int = 256, target_objects: Sequence[str] = TARGET_OBJECTS):
+    def __init__(self, encoder: ClipRN50Encoder, batch: int = 256, target_objects: Sequence[str] = TARGET_OBJECTS,
+                 imagenet_encoder: Optional[TorchvisionResNet50Encoder] = None):
         self.enc, self.batch, self.target_objects = encoder, int(batch), tuple(target_objects)
+        self.imagenet = imagenet_encoder
         if self.batch <= 0:
             raise ValueError("batch must be positive")
+        if self.imagenet is not None and self.imagenet.device != self.enc.device:
+            raise ValueError("the CLIP and ImageNet encoders must live on the same device")
         self._pin: Optional[torch.Tensor] = None
 
     def encode_frames(self, frames: Sequence[np.ndarray]) -> Dict[str, torch.Tensor]:
-        """Raw uint8 frames (any resolution) -> {'clip_conv' [N,2048,7,7], 'clip_attnpool' [N,1024], 'clip_avgpool' [N,2048]} on CPU."""
+        """Raw uint8 frames (any resolution) -> {'clip_conv' [N,2048,7,7], 'clip_attnpool' [N,1024], 'clip_avgpool' [N,2048]
+        (+ 'imagenet_conv' [N,2048,7,7], 'imagenet_avgpool' [N,2048] with an ImageNet encoder)} on CPU.  Both encoders read the
+        SAME resized uint8 batch: `resnet_preprocess` and `clip_preprocess` share the geometry (Resize 224 bicubic, CenterCrop
+        224) and differ only in the mean / std, which each stem applies on the device."""
         n = len(frames)
         R = self.enc.cfg["input_resolution"]
         outs = {"clip_conv": torch.empty(n, self.enc.embed, self.enc.fres, self.enc.fres),
                 "clip_attnpool": torch.empty(n, self.enc.cfg["output_dim"]), "clip_avgpool": torch.empty(n, self.enc.embed)}
+        if self.imagenet is not None:
+            outs["imagenet_conv"] = torch.empty(n, self.imagenet.embed, self.imagenet.fres, self.imagenet.fres)
+            outs["imagenet_avgpool"] = torch.empty(n, self.imagenet.embed)
         if self._pin is None:
             self._pin = torch.empty(self.batch, R, R, 3, dtype=torch.uint8).pin_memory()
         for i0 in range(0, n, self.batch):
@@ -104,6 +116,10 @@ class FeatureCacher:
             outs["clip_conv"][i0:i0 + b] = o["trunk"].cpu()
             outs["clip_attnpool"][i0:i0 + b] = o["attnpool"].cpu()
             outs["clip_avgpool"][i0:i0 + b] = o["avgpool"].cpu()
+            if self.imagenet is not None:
+                o = self.imagenet.forward(dev, ("trunk", "avgpool"))
+                outs["imagenet_conv"][i0:i0 + b] = o["trunk"].cpu()
+                outs["imagenet_avgpool"][i0:i0 + b] = o["avgpool"].cpu()
         return outs
 
     def scene_features(self, points: Sequence[dict]) -> List[Dict[str, torch.Tensor]]:
@@ -112,9 +128,40 @@ class FeatureCacher:
         out = []
         for i, p in enumerate(points):
             pres, loc = presence_labels(p["semantic_frame"], p["object_id_to_color"], self.target_objects)
-            out.append({"clip_conv": feats["clip_conv"][i].clone(), "clip_attnpool": feats["clip_attnpool"][i].clone(),
-                        "clip_avgpool": feats["clip_avgpool"][i].clone(), "object_presence": pres,
-                        "object_localization": loc, "free_space": p["valid_moves_forward"]})
+            d = {}
+            if self.imagenet is not None:                       # key order of thor_image_features.py:129-138
+                d["imagenet_conv"] = feats["imagenet_conv"][i].clone()
+                d["imagenet_avgpool"] = feats["imagenet_avgpool"][i].clone()
+            d.update({"clip_conv": feats["clip_conv"][i].clone(), "clip_attnpool": feats["clip_attnpool"][i].clone(),
+                      "clip_avgpool": feats["clip_avgpool"][i].clone(), "object_presence": pres,
+                      "object_localization": loc, "free_space": p["valid_moves_forward"]})
+            out.append(d)
+        return out
+
+    def reachable_features(self, images: Dict[str, np.ndarray]) -> Dict[str, Dict[str, torch.Tensor]]:
+        """{image_name: uint8 HWC frame} -> {image_name: {'imagenet_avgpool', 'clip_avgpool', 'clip_attnpool'}}
+        (reachable_image_features.py:77-98), batched."""
+        names = list(images)
+        feats = self.encode_frames([images[k] for k in names])
+        out = {}
+        for i, k in enumerate(names):
+            d = {}
+            if self.imagenet is not None:
+                d["imagenet_avgpool"] = feats["imagenet_avgpool"][i].clone()
+            d["clip_avgpool"] = feats["clip_avgpool"][i].clone()
+            d["clip_attnpool"] = feats["clip_attnpool"][i].clone()
+            out[k] = d
+        return out
+
+    def cache_reachable(self, data_dir: str, output_dir: str) -> str:
+        """{data_dir}/*.png -> {output_dir}/reachable_image_features.pt (reachable_image_features.py:24-25,100)."""
+        from PIL import Image
+        images = {}
+        for path in sorted(glob(os.path.join(data_dir, "*.png"))):
+            images[os.path.splitext(os.path.basename(path))[0]] = np.asarray(Image.open(path).convert("RGB"), dtype=np.uint8)
+        os.makedirs(output_dir, exist_ok=True)
+        out = os.path.join(output_dir, "reachable_image_features.pt")
+        torch.save(self.reachable_features(images), out)
         return out
 
     def cache_split(self, data_dir: str, output_dir: str, split: str) -> str:
@@ -136,13 +183,20 @@ def main(argv=None) -> None:
     ap.add_argument("--output_dir", type=str, default="data")
     ap.add_argument("--weights", type=str, default=os.environ.get("EMBCLIP_CLIP_WEIGHTS"),
                     help="CLIP RN50 state dict (.pt); required -- there is no download path offline")
+    ap.add_argument("--imagenet_weights", type=str, default=os.environ.get("EMBCLIP_IMAGENET_WEIGHTS"),
+                    help="torchvision resnet50 state dict (.pth): adds the imagenet_conv / imagenet_avgpool keys")
+    ap.add_argument("--reachable", action="store_true",
+                    help="reachable_image_features.py mode: --data_dir holds *.png, writes reachable_image_features.pt")
     ap.add_argument("--batch", type=int, default=256)
     args = ap.parse_args(argv)
     if not args.weights:
         raise SystemExit("feature_cacher: pass --weights (or set $EMBCLIP_CLIP_WEIGHTS) to a CLIP RN50 state dict")
-    sd = torch.load(args.weights, map_location="cpu")
-    sd = sd.state_dict() if hasattr(sd, "state_dict") else sd
-    fc = FeatureCacher(ClipRN50Encoder(sd, "cuda:0"), args.batch)
+    load = lambda path: (lambda sd: sd.state_dict() if hasattr(sd, "state_dict") else sd)(torch.load(path, map_location="cpu"))
+    inet = TorchvisionResNet50Encoder(load(args.imagenet_weights), "cuda:0") if args.imagenet_weights else None
+    fc = FeatureCacher(ClipRN50Encoder(load(args.weights), "cuda:0"), args.batch, imagenet_encoder=inet)
+    if args.reachable:
+        print(fc.cache_reachable(args.data_dir, args.output_dir))
+        return
     for split in ("train", "val", "test"):
         print(fc.cache_split(args.data_dir, args.output_dir, split))
 

@@ -177,6 +177,8 @@ typedef struct {
   int32_t hidden;           /* 512  GRU hidden size                                      */
   int32_t num_actions;      /* 6                                                         */
   int32_t num_goals;        /* 12                                                        */
+  int32_t trainable_masked_hidden_state;  /* 0 (the ObjectNav config): an episode starts from h = 0.  1: from the learned
+                             * parameter "state_encoder.init_hidden_state" [1,1,hidden] (RNNStateEncoder kwarg of the same name) */
 } embclip_ac_cfg;
 
 int embclip_ac_create(const embclip_ac_cfg* cfg, embclip_ac_t* out);   /* needs no GPU */
@@ -283,16 +285,18 @@ int embclip_wgrad_f16(const void* a, int lda, int M1, const void* b, int ldb, in
                       long long ldo_m, long long ldo_n, const float* alpha, void* stream);
 /* nn.GRU (1 layer) with RNNStateEncoder's episode masking: gi = x W_ih^T + b_ih precomputed [T,N,3H];
  * out [T,N,H]; save_* [T,N,H] (all NULL for inference); scratch32 = 256 B of device scratch
- * (uint32 [0,32): one barrier counter per sampler group, zeroed by the call; [32]: max |dgi| bits written by the backward). */
+ * (uint32 [0,32): one barrier counter per sampler group, zeroed by the call; [32]: max |dgi| bits written by the backward).
+ * h_init fp32 [H] or NULL: the state an episode starts from where masks == 0 (trainable_masked_hidden_state); the backward
+ * ADDS its gradient into dh_init [H] (both NULL or both set). */
 int embclip_gru_forward(const float* gi, const float* w_hh, const float* b_hh, const float* h0, const float* masks,
-                        int T, int N, int H, float* out, float* save_r, float* save_z, float* save_n, float* save_hn,
-                        void* scratch32, void* stream);
+                        const float* h_init, int T, int N, int H, float* out, float* save_r, float* save_z, float* save_n,
+                        float* save_hn, void* scratch32, void* stream);
 /* BPTT of the above: dout [T,N,H], dh_last [N,H] or NULL -> dgi, dgh [T,N,3H] fp32, hm_f16 [T,N,H] fp16
  * (masked previous hidden state), dh0 [N,H] or NULL. */
 int embclip_gru_backward(const float* w_hh, const float* h0, const float* masks, const float* out, const float* save_r,
                          const float* save_z, const float* save_n, const float* save_hn, const float* dout,
-                         const float* dh_last, int T, int N, int H, float* dgi, float* dgh, void* hm_f16, float* dh0,
-                         void* scratch32, void* stream);
+                         const float* dh_last, const float* h_init, int T, int N, int H, float* dgi, float* dgh, void* hm_f16,
+                         float* dh0, float* dh_init, void* scratch32, void* stream);
 
 #ifdef __cplusplus
 }

@@ -148,11 +148,13 @@ class ResnetTensorNavActorCritic(nn.Module):
 
     def __init__(self, num_actions: int = 6, num_goals: int = 12, hidden_size: int = 512,
                  goal_dims: int = 32, resnet_tensor_shape=(2048, 7, 7),
-                 rgb_uuid: str = "rgb_clip_resnet", goal_uuid: str = "goal_object_type_ind"):
+                 rgb_uuid: str = "rgb_clip_resnet", goal_uuid: str = "goal_object_type_ind",
+                 trainable_masked_hidden_state: bool = False):
         super().__init__()
         self.rgb_uuid, self.goal_uuid = rgb_uuid, goal_uuid
         self.goal_visual_encoder = ResnetTensorGoalEncoder(resnet_tensor_shape, num_goals, goal_dims)
-        self.state_encoder = RNNStateEncoder(self.goal_visual_encoder.output_dims, hidden_size)
+        self.state_encoder = RNNStateEncoder(self.goal_visual_encoder.output_dims, hidden_size,
+                                             trainable_masked_hidden_state=trainable_masked_hidden_state)
         self.actor = LinearActorHead(hidden_size, num_actions)
         self.critic = LinearCriticHead(hidden_size)
 

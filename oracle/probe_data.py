@@ -8,8 +8,9 @@ time, exactly as /root/reference/primitive_probing/generate_data/thor_image_feat
     Normalize(CLIP mean / std) [UPSTREAM clip/clip.py::_transform]; trunk with attnpool replaced by Identity ->
     'clip_conv' [2048,7,7]; attnpool on the trunk output -> 'clip_attnpool' [1024]; AdaptiveAvgPool2d(1) -> 'clip_avgpool'
     [2048]; everything `.float()[0].cpu()`.
-  * `free_space` is copied from the point (:137).  The 'imagenet_*' entries (:101-105, torchvision ResNet-50 with downloaded
-    weights) are NOT restated: that encoder is outside the hot path.
+  * `free_space` is copied from the point (:137).  The 'imagenet_*' entries (:101-105) come from torchvision's own ResNet-50
+    cut after layer4 (oracle/imagenet_resnet.py) on `resnet_preprocess(frame)` (:36-44: same geometry, ImageNet mean / std).
+  * `reachable_features` restates reachable_image_features.py:77-98 (three pooled embeddings per PNG).
 
 Parity unpinned: the reference has no test or fixture for this file.  Only tests/ may import this module.
 """
@@ -56,15 +57,45 @@ def clip_preprocess(frame: np.ndarray) -> torch.Tensor:
     return (x - torch.tensor(CLIP_MEAN).view(3, 1, 1)) / torch.tensor(CLIP_STD).view(3, 1, 1)
 
 
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def resnet_preprocess(frame: np.ndarray) -> torch.Tensor:
+    """thor_image_features.py:36-44: the same Resize / CenterCrop as clip_preprocess, ImageNet normalisation."""
+    x = clip_preprocess(frame) * torch.tensor(CLIP_STD).view(3, 1, 1) + torch.tensor(CLIP_MEAN).view(3, 1, 1)     # back to [0, 1]
+    return (x - torch.tensor(IMAGENET_MEAN).view(3, 1, 1)) / torch.tensor(IMAGENET_STD).view(3, 1, 1)
+
+
 @torch.no_grad()
-def scene_features(points: Sequence[dict], visual, target_objects: Sequence[str]) -> List[Dict[str, torch.Tensor]]:
-    """One dict per point, batch 1 like the reference loop (:99-138).  `visual` = oracle.clip_model ModifiedResNet."""
+def reachable_features(images: Dict[str, np.ndarray], visual, resnet_trunk=None) -> Dict[str, Dict[str, torch.Tensor]]:
+    """reachable_image_features.py:77-98, one image at a time."""
+    out = {}
+    for name, frame in images.items():
+        d = {}
+        if resnet_trunk is not None:
+            d["imagenet_avgpool"] = resnet_trunk(resnet_preprocess(frame).unsqueeze(0)).mean(dim=(2, 3))[0].cpu()
+        t = visual.trunk(clip_preprocess(frame).unsqueeze(0))
+        d["clip_avgpool"] = t.float().mean(dim=(2, 3))[0].cpu()
+        d["clip_attnpool"] = visual.attnpool(t).float()[0].cpu()
+        out[name] = d
+    return out
+
+
+@torch.no_grad()
+def scene_features(points: Sequence[dict], visual, target_objects: Sequence[str], resnet_trunk=None) -> List[Dict[str, torch.Tensor]]:
+    """One dict per point, batch 1 like the reference loop (:99-138).  `visual` = oracle.clip_model ModifiedResNet;
+    `resnet_trunk` = oracle.imagenet_resnet trunk (adds the imagenet_* keys)."""
     out = []
     for point in points:
         x = clip_preprocess(point["frame"]).unsqueeze(0)
         t = visual.trunk(x)
         masks = np.array([class_mask(point["semantic_frame"], point["object_id_to_color"].get(o, None)) for o in target_objects])
-        out.append({
+        inet = {}
+        if resnet_trunk is not None:
+            r = resnet_trunk(resnet_preprocess(point["frame"]).unsqueeze(0))
+            inet = {"imagenet_conv": r[0].cpu(), "imagenet_avgpool": r.mean(dim=(2, 3))[0].cpu()}
+        out.append({**inet, **{
             "clip_conv": t.float()[0].cpu(),
             "clip_attnpool": visual.attnpool(t).float()[0].cpu(),
             "clip_avgpool": t.float().mean(dim=(2, 3))[0].cpu(),
@@ -72,5 +103,5 @@ def scene_features(points: Sequence[dict], visual, target_objects: Sequence[str]
             "object_localization": torch.tensor(np.array([obj_presence(masks[:, y1:y2, x1:x2])
                                                           for (y1, y2, x1, x2) in grid_bboxes(masks.shape[1:3], (3, 3))]), dtype=int),
             "free_space": point["valid_moves_forward"],
-        })
+        }})
     return out

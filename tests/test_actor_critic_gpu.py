@@ -74,11 +74,11 @@ def test_wgrad_transposed_store(lib):
 
 
 # ----------------------------------------------------------------------------------------------- GRU
-def _gru_case(lib, T, N, H, seed, mask_p=0.15):
+def _gru_case(lib, T, N, H, seed, mask_p=0.15, trainable=False):
     from oracle.allenact_models import RNNStateEncoder
     torch.manual_seed(seed)
     I = 40
-    enc = RNNStateEncoder(I, H)
+    enc = RNNStateEncoder(I, H, trainable_masked_hidden_state=trainable)
     with torch.no_grad():
         enc.rnn.bias_ih_l0.normal_(0, 0.1)
         enc.rnn.bias_hh_l0.normal_(0, 0.1)
@@ -99,7 +99,10 @@ def _gru_case(lib, T, N, H, seed, mask_p=0.15):
     out = torch.empty(T, N, H, device=dev)
     sv = [torch.empty(T, N, H, device=dev) for _ in range(4)]
     scratch = torch.zeros(64, dtype=torch.int32, device=dev)
-    _check(lib, lib.embclip_gru_forward(gi.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(), h0d.data_ptr(), md.data_ptr(), T, N, H,
+    hi = enc.init_hidden_state.detach().reshape(H).to(dev).contiguous() if trainable else None
+    dhi = torch.zeros(H, device=dev) if trainable else None
+    _check(lib, lib.embclip_gru_forward(gi.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(), h0d.data_ptr(), md.data_ptr(),
+                                        hi.data_ptr() if trainable else None, T, N, H,
                                         out.data_ptr(), *[s.data_ptr() for s in sv], scratch.data_ptr(), _st()))
     torch.cuda.synchronize()
     assert rel(out, out_ref) <= 2e-5, f"gru forward rel {rel(out, out_ref):.3g}"
@@ -110,8 +113,9 @@ def _gru_case(lib, T, N, H, seed, mask_p=0.15):
     dh0 = torch.empty(N, H, device=dev)
     dout_d, dhT_d = dout.to(dev).contiguous(), dhT[0].to(dev).contiguous()    # named: temporaries would be freed (and reused) before the launch
     _check(lib, lib.embclip_gru_backward(w_hh.data_ptr(), h0d.data_ptr(), md.data_ptr(), out.data_ptr(), *[s.data_ptr() for s in sv],
-                                         dout_d.data_ptr(), dhT_d.data_ptr(), T, N, H,
-                                         dgi.data_ptr(), dgh.data_ptr(), hm.data_ptr(), dh0.data_ptr(), scratch.data_ptr(), _st()))
+                                         dout_d.data_ptr(), dhT_d.data_ptr(), hi.data_ptr() if trainable else None, T, N, H,
+                                         dgi.data_ptr(), dgh.data_ptr(), hm.data_ptr(), dh0.data_ptr(),
+                                         dhi.data_ptr() if trainable else None, scratch.data_ptr(), _st()))
     torch.cuda.synchronize()
     dgi_c, dgh_c = dgi.cpu().reshape(T * N, 3 * H), dgh.cpu().reshape(T * N, 3 * H)
     # dgi -> gradients of W_ih, b_ih, x exactly as autograd forms them
@@ -120,6 +124,9 @@ def _gru_case(lib, T, N, H, seed, mask_p=0.15):
     assert rel(dgi_c @ enc.rnn.weight_ih_l0.detach(), x.grad.reshape(T * N, I)) <= 5e-5
     # dgh -> gradients of W_hh, b_hh; hm (fp16 copy of the masked previous state) within half precision
     hprev = torch.cat([h0, out_ref[:-1].detach()], 0) * masks
+    if trainable:
+        hprev = hprev + (1 - masks) * enc.init_hidden_state.detach()
+        assert rel(dhi, enc.init_hidden_state.grad.reshape(H)) <= 5e-5
     assert rel(hm, hprev) <= 1e-3
     assert rel(dgh_c.t() @ hprev.reshape(T * N, H), enc.rnn.weight_hh_l0.grad) <= 5e-5
     assert rel(dgh_c.sum(0), enc.rnn.bias_hh_l0.grad) <= 5e-5
@@ -132,11 +139,17 @@ def test_gru_forward_backward_vs_torch(lib, T, N, H):
     _gru_case(lib, T, N, H, seed=T * 100 + N)
 
 
+@pytest.mark.parametrize("T,N,H", [(5, 7, 128), (16, 60, 512)])
+def test_gru_trainable_masked_hidden_state(lib, T, N, H):
+    """RNNStateEncoder(trainable_masked_hidden_state=True): episodes start from a learned state; its gradient comes out of BPTT."""
+    _gru_case(lib, T, N, H, seed=T * 7 + N, mask_p=0.3, trainable=True)
+
+
 def test_gru_rejects_bad_shapes(lib):
     z = torch.zeros(64, device="cuda")
-    assert lib.embclip_gru_forward(z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), 1, 1, 100, z.data_ptr(),
+    assert lib.embclip_gru_forward(z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), None, 1, 1, 100, z.data_ptr(),
                                    None, None, None, None, z.data_ptr(), _st()) < 0       # H not a multiple of 64
-    assert lib.embclip_gru_forward(z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), 1, 1000, 512, z.data_ptr(),
+    assert lib.embclip_gru_forward(z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), None, 1, 1000, 512, z.data_ptr(),
                                    None, None, None, None, z.data_ptr(), _st()) < 0       # too many samplers for one launch
 
 
@@ -693,6 +706,38 @@ def test_backward_after_interleaved_forward_recomputes(models):
     (loB2.sum() + vaB2.square().sum()).backward()
     assert rel(gB, ours.flat_params.grad) <= 1e-5
     ours.zero_grad()
+
+
+def test_actor_critic_trainable_masked_hidden_state(lib):
+    """The model-level wiring of RNNStateEncoder(trainable_masked_hidden_state=True): an extra upstream-named parameter
+    `state_encoder.init_hidden_state` [1,1,512], used by forward / act, with its gradient from BPTT."""
+    from embclip_b200.actor_critic import ResnetTensorNavActorCritic
+    from oracle.allenact_models import ResnetTensorNavActorCritic as RefAC, ppo_loss
+    torch.manual_seed(21)
+    ref = RefAC(trainable_masked_hidden_state=True)
+    ours = ResnetTensorNavActorCritic(device="cuda:0", trainable_masked_hidden_state=True)
+    assert "state_encoder.init_hidden_state" in ours.state_dict() and ours.state_dict()["state_encoder.init_hidden_state"].shape == (1, 1, 512)
+    ours.load_state_dict(ref.state_dict())
+    T, N = 6, 5
+    ro = _rollout(T, N, seed=77)
+    ro["masks"][2:4, 1:4] = 0
+    batch = _loss_batch(ref, ro, seed=3)
+    distr, v, h = _ref_forward(ref, ro)
+    ppo_loss(distr, v, batch)[0].backward()
+    logits, values, h_last = ours.forward_tensors(ro["features"].cuda(), ro["goals"].cuda(), ro["memory"].cuda(), ro["masks"].cuda())
+    from embclip_b200.actor_critic import CategoricalDistr
+    ppo_loss(CategoricalDistr(logits=logits), values.unsqueeze(-1), {k: t.cuda() for k, t in batch.items()})[0].backward()
+    torch.cuda.synchronize()
+    assert rel(values, v[..., 0]) <= 1e-3 and rel(h_last, h[0]) <= 1e-3
+    off, n = next((o, n_) for name, _, o, n_ in ours._plan.params if name == "state_encoder.init_hidden_state")
+    e = rel(ours.flat_params.grad[off:off + n], ref.state_encoder.init_hidden_state.grad.reshape(-1))
+    print(f"init_hidden_state gradient rel-L2 {e:.2e}")
+    assert e <= 3e-3
+    # a model without the option has no such key and rejects a checkpoint that carries it
+    plain = ResnetTensorNavActorCritic(device="cuda:0")
+    assert "state_encoder.init_hidden_state" not in plain.state_dict()
+    with pytest.raises(RuntimeError):
+        plain.load_state_dict(ref.state_dict())
 
 
 def test_sampler_frequencies(lib):

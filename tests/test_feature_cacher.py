@@ -96,3 +96,40 @@ def test_scene_features_vs_oracle(built_lib, rn50_visual, tmp_path):
     saved = torch.load(path)
     assert path.endswith("thor_val.pt") and list(saved) == ["FloorPlan21"] and len(saved["FloorPlan21"]) == 5
     assert torch.equal(saved["FloorPlan21"][2]["clip_attnpool"], ours[2]["clip_attnpool"])
+
+
+@pytest.mark.gpu
+def test_imagenet_keys_and_reachable_twin(built_lib, rn50_visual, tmp_path):
+    """thor_{split}.pt with the imagenet_conv / imagenet_avgpool keys (thor_image_features.py:101-105,129-131) and the
+    reachable_image_features.py twin (PNG directory -> {image: 3 pooled embeddings}), against the restated loops driven by
+    torchvision's own ResNet-50."""
+    from PIL import Image
+    from embclip_b200.encoder import ClipRN50Encoder, TorchvisionResNet50Encoder
+    from embclip_b200.feature_cacher import FeatureCacher, TARGET_OBJECTS
+    from oracle.imagenet_resnet import build_imagenet_rn50
+    from oracle.probe_data import reachable_features, scene_features
+    trunk, _, sd = build_imagenet_rn50()
+    fc = FeatureCacher(ClipRN50Encoder(rn50_visual.state_dict(), "cuda:0"), batch=4, imagenet_encoder=TorchvisionResNet50Encoder(sd, "cuda:0"))
+    points = _scene(3, seed=21)
+    ours = fc.scene_features(points)
+    ref = scene_features(points, rn50_visual, TARGET_OBJECTS, resnet_trunk=trunk)
+    assert list(ours[0]) == list(ref[0]) == ["imagenet_conv", "imagenet_avgpool", "clip_conv", "clip_attnpool", "clip_avgpool",
+                                             "object_presence", "object_localization", "free_space"]
+    rl = lambda a, b: ((a - b).norm() / b.norm()).item()
+    for o, r in zip(ours, ref):
+        for k in ("imagenet_conv", "imagenet_avgpool", "clip_conv", "clip_attnpool", "clip_avgpool"):
+            assert o[k].shape == r[k].shape and rl(o[k], r[k]) <= 1e-3, (k, rl(o[k], r[k]))
+    d = tmp_path / "edge_full"
+    d.mkdir()
+    images = {}
+    for i, p in enumerate(points):
+        Image.fromarray(p["frame"]).save(d / f"img_{i:03d}.png")
+        images[f"img_{i:03d}"] = p["frame"]
+    path = fc.cache_reachable(str(d), str(tmp_path / "out"))
+    saved = torch.load(path)
+    ref_r = reachable_features(images, rn50_visual, resnet_trunk=trunk)
+    assert path.endswith("reachable_image_features.pt") and list(saved) == list(ref_r)
+    for name in saved:
+        assert list(saved[name]) == ["imagenet_avgpool", "clip_avgpool", "clip_attnpool"]
+        for k in saved[name]:
+            assert rl(saved[name][k], ref_r[name][k]) <= 1e-3, (name, k)

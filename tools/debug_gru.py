@@ -39,8 +39,8 @@ def case(T, N, H, seed=0):
     w, b = W_hh.to(dev).contiguous(), b_hh.to(dev).contiguous()
     h0d, md = h0[0].to(dev).contiguous(), masks[..., 0].to(dev).contiguous()
     out = torch.zeros(T, N, H, device=dev); sv = [torch.zeros(T, N, H, device=dev) for _ in range(4)]
-    scratch = torch.zeros(16, dtype=torch.int32, device=dev)
-    rc = lib.embclip_gru_forward(gi.data_ptr(), w.data_ptr(), b.data_ptr(), h0d.data_ptr(), md.data_ptr(), T, N, H, out.data_ptr(),
+    scratch = torch.zeros(64, dtype=torch.int32, device=dev)
+    rc = lib.embclip_gru_forward(gi.data_ptr(), w.data_ptr(), b.data_ptr(), h0d.data_ptr(), md.data_ptr(), None, T, N, H, out.data_ptr(),
                                  *[s.data_ptr() for s in sv], scratch.data_ptr(), st())
     torch.cuda.synchronize()
     print(f"--- T={T} N={N} H={H} fwd rc={rc} {lib.embclip_last_error().decode() if rc else ''}")
@@ -53,7 +53,7 @@ def case(T, N, H, seed=0):
     hm = torch.zeros(T, N, H, device=dev, dtype=torch.float16); dh0 = torch.zeros(N, H, device=dev)
     o2d = o2.detach().to(dev).contiguous()
     rc = lib.embclip_gru_backward(w.data_ptr(), h0d.data_ptr(), md.data_ptr(), out.data_ptr(), *[s.data_ptr() for s in sv], doutd.data_ptr(),
-                                  dhTd.data_ptr(), T, N, H, dgi.data_ptr(), dgh.data_ptr(), hm.data_ptr(), dh0.data_ptr(), scratch.data_ptr(), st())
+                                  dhTd.data_ptr(), None, T, N, H, dgi.data_ptr(), dgh.data_ptr(), hm.data_ptr(), dh0.data_ptr(), None, scratch.data_ptr(), st())
     torch.cuda.synchronize()
     print(f" bwd rc={rc} {lib.embclip_last_error().decode() if rc else ''}")
     for name, got, ref in (("dgi", dgi, dgi_ref), ("dgh", dgh, dgh_ref)):

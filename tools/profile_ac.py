@@ -63,15 +63,15 @@ def main():
     # GRU alone
     gi = torch.randn(T, N, 1536, device=dev)
     out = torch.empty(T, N, 512, device=dev); sv = [torch.empty(T, N, 512, device=dev) for _ in range(4)]
-    scratch = torch.zeros(16, dtype=torch.int32, device=dev)
+    scratch = torch.zeros(64, dtype=torch.int32, device=dev)
     w_hh = torch.randn(1536, 512, device=dev) * 0.04; b_hh = torch.zeros(1536, device=dev)
-    res["gru_forward_ms"] = timed(lambda: lib.embclip_gru_forward(gi.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(), h0.data_ptr(), masks.data_ptr(), T, N, 512,
+    res["gru_forward_ms"] = timed(lambda: lib.embclip_gru_forward(gi.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(), h0.data_ptr(), masks.data_ptr(), None, T, N, 512,
                                                                  out.data_ptr(), *[s.data_ptr() for s in sv], scratch.data_ptr(), st))
     dout = torch.randn(T, N, 512, device=dev) * 1e-4
     dgi = torch.empty(T, N, 1536, device=dev); dgh = torch.empty(T, N, 1536, device=dev); hm = torch.empty(T, N, 512, device=dev, dtype=torch.float16)
     res["gru_backward_ms"] = timed(lambda: lib.embclip_gru_backward(w_hh.data_ptr(), h0.data_ptr(), masks.data_ptr(), out.data_ptr(), *[s.data_ptr() for s in sv],
-                                                                   dout.data_ptr(), None, T, N, 512, dgi.data_ptr(), dgh.data_ptr(), hm.data_ptr(), None,
-                                                                   scratch.data_ptr(), st))
+                                                                   dout.data_ptr(), None, None, T, N, 512, dgi.data_ptr(), dgh.data_ptr(), hm.data_ptr(), None,
+                                                                   None, scratch.data_ptr(), st))
     res["frames"] = F
     res["hbm_floor_update_pass_ms"] = 2 * F * 49 * 2048 * 2 / 6.5329e12 * 1e3     # features read by forward GEMM and by dW1
     print(json.dumps(res, indent=1))
