@@ -526,7 +526,9 @@ class PPOTrainer:
         mdl.mark_params_changed()                              # raw-pointer update: torch's version counter does not see it
 
     def _loss_info(self, rows: int) -> Dict[str, torch.Tensor]:
-        return self._loss_info(rows)
+        s = self.loss_sums / rows
+        return {"action": s[0], "value": s[1], "entropy": -s[2],
+                "total": s[0] + self.value_loss_coef * s[1] - self.entropy_coef * s[2], "grad_norm": self.sumsq.sqrt()[0]}
 
     def update_from_storage(self, storage: Any, global_rows: Optional[int] = None) -> Dict[str, torch.Tensor]:
         """OnPolicyTrainer.update(rollouts) [UPSTREAM engine.py]: ``update_repeats`` x ``storage.recurrent_generator(...,
