@@ -35,6 +35,13 @@ HEADS = ("trunk", "avgpool", "attnpool")
 METRIC = "frames/sec CLIP-RN50 encode (224x224, batch 256/GPU): trunk[2048,7,7] + attnpool-1024 + avgpool-2048"
 
 
+def workload_config():
+    """The `config` object of BOTH arms' JSON lines (identical keys and values, so the driver's same_config check holds)."""
+    return {"workload": "clip_rn50_encode_b256", "batch_per_gpu": BATCH, "resolution": RES, "heads": list(HEADS),
+            "weights": "seeded synthetic (seed 1234)", "input": "224x224x3 frames (fp32 NHWC mean/std-normalised for `value`; raw uint8 NHWC for `e2e`)",
+            "l2": "per-step working set (154 MB frames + 6.6 GB activations) exceeds the 126 MB L2"}
+
+
 def synthetic_frames_u8(batch, seed=0):
     import torch
     g = torch.Generator().manual_seed(seed)
@@ -81,6 +88,8 @@ def time_gpu_eager_oracle(model, dev, batch, iters=10, warmup=3):
     import copy
     import torch
     out = {}
+    prev_bench = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True                        # let cuDNN pick its fastest algorithms: the strongest library setting
     x32 = synthetic_frames(batch, seed=1).permute(0, 3, 1, 2).contiguous().to(dev)
     for name, dtype, fmt in (("fp32_nchw", torch.float32, torch.contiguous_format), ("fp16_channels_last", torch.float16, torch.channels_last)):
         try:
@@ -104,7 +113,9 @@ def time_gpu_eager_oracle(model, dev, batch, iters=10, warmup=3):
         except Exception as e:                                   # a baseline must never take the bench down
             out[name] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     out["what"] = (f"oracle/clip_model.py ModifiedResNet (trunk + attnpool + avgpool) under torch {torch.__version__} eager on the same GPU, "
-                   f"batch {batch}, cudnn.allow_tf32={torch.backends.cudnn.allow_tf32}, matmul.allow_tf32={torch.backends.cuda.matmul.allow_tf32}")
+                   f"batch {batch}, cudnn.benchmark=True, cudnn.allow_tf32={torch.backends.cudnn.allow_tf32}, "
+                   f"matmul.allow_tf32={torch.backends.cuda.matmul.allow_tf32}")
+    torch.backends.cudnn.benchmark = prev_bench
     return out
 
 
@@ -168,7 +179,7 @@ class ClockSampler:
         return out
 
 
-def run_ppo_block(enc, dev, rank, world, rollouts, max_over_ranks, barrier, T=128, N=60, global_samplers=None):
+def run_ppo_block(enc, dev, rank, world, rollouts, max_over_ranks, barrier, T=128, N=60, global_samplers=None, packed=True):
     """BASELINE configs 3 / 4: end-to-end PPO step on synthetic rollouts -- T x N frames encoded in T rollout steps of N
     (the faithful AllenAct schedule: the preprocessor sees one step of all samplers at a time), T act() calls, GAE, and
     4 update passes with the flat-bucket gradient all-reduce.  Weak scaling: N samplers per GPU.
@@ -182,7 +193,7 @@ def run_ppo_block(enc, dev, rank, world, rollouts, max_over_ranks, barrier, T=12
     from embclip_b200.harness import SyntheticPPOStep
     model = ResnetTensorNavActorCritic(device=dev, seed=1)
     trainer = PPOTrainer(model, lr=3e-4, max_grad_norm=0.5, update_repeats=4)
-    stepper = SyntheticPPOStep(enc, model, trainer, T=T, N=N, seed=10 + rank)
+    stepper = SyntheticPPOStep(enc, model, trainer, T=T, N=N, seed=10 + rank, packed_rollout=packed)
     host = synthetic_frames_u8(N, seed=200 + rank).pin_memory()     # e2e leg: raw uint8 frames, normalised in the stem kernel
     frames = synthetic_frames(N, seed=200 + rank).to(dev)           # device-resident leg: fp32 normalised (the AllenAct boundary dtype)
     grows = T * global_samplers if strong else T * N * world
@@ -253,7 +264,8 @@ def run_ppo_block(enc, dev, rank, world, rollouts, max_over_ranks, barrier, T=12
         "collect_ms": collect_ms, "update_ms": update_ms, "scaling": "strong" if strong else "weak",
         "config": {"workload": "objectnav_ppo_step", "steps": T, "samplers_per_gpu": N, "samplers_total": grows // T, "update_repeats": 4, "num_mini_batch": 1,
                    "global_rows": grows,
-                   "rollout_storage": "fp16 pixel rows on device (encode_rows -> act -> PackedFeatures); the AllenAct fp32 NCHW flow is SyntheticPPOStep(packed_rollout=False)",
+                   "rollout_storage": ("embclip_b200.storage.RolloutStorage, fp16 pixel rows on device (encode_rows -> act -> PackedFeatures)" if packed else
+                                       "embclip_b200.storage.RolloutStorage, AllenAct data flow verbatim: fp32 [N,2048,7,7] features, forward + torch sampling, pack per update"),
                    "collective": "1 flat fp32 gradient all-reduce (13.9 MB) per update pass" if world > 1 else "none (1 GPU)"},
         "e2e": {"value": frames_per_step / (e2e_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": T * host.numel(), "d2h_bytes_per_step": 5 * 4, "input": "uint8 NHWC raw RGB",
@@ -417,17 +429,19 @@ def run_reference(args, rank, world):
         return
     import torch
     model = oracle_model()
-    sample = 32
+    # one step = the full 256-frame batch whenever the whole run (warm-up + steps at ~70 frames/s on 16 cores) stays within a few
+    # minutes; a longer run falls back to a 32-frame sample per step (frames/s is size-independent on the CPU).  Said in cpu_baseline.sample.
+    sample = BATCH if (args.steps + args.warmup) * BATCH <= 12000 else 32
     fps, sec = time_cpu_oracle(model, sample, args.steps, args.warmup)
     cores = torch.get_num_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 * (BATCH / sample), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "clip_rn50_encode_b256", "batch_per_gpu": BATCH, "resolution": RES, "heads": list(HEADS),
-                   "weights": "seeded synthetic (seed 1234)", "step_sample": f"{sample} of {BATCH} frames per step"},
+        "config": workload_config(),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"fp32 PyTorch oracle (oracle/clip_model.py), {sample} frames/step x {args.steps} steps, {cores} threads"},
+                         "sample": f"fp32 PyTorch oracle (oracle/clip_model.py: trunk + attnpool + avgpool), {sample} of {BATCH} frames per step x "
+                                   f"{args.steps} steps ({args.warmup} warm-up), {cores} threads; ms_per_step is scaled to {BATCH} frames"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "linear_probe_cpu": time_linear_probe_cpu(),
@@ -518,69 +532,90 @@ def run_ours(args, rank, local_rank, world):
     ms_step = ms_total / K
     value = world * BATCH * K / (ms_total * 1e-3)
 
-    # ---------------- end to end through the public API with host buffers (e2e): pinned fp32 NHWC frames in,
-    # all three results back in pinned host memory; copies double-buffered against compute on side streams.
+    # ---------------- end to end through the public API with host buffers (e2e)
+    # Every step: H2D of that step's frames from pinned host memory, ClipRN50Encoder.forward computing ALL THREE heads, D2H
+    # of the results the caller asked to have on the host; copies double-buffered against compute on side streams.
+    #   e2e (headline)           raw uint8 frames in (the boundary's native input: normalised in the stem kernel), the two pooled
+    #                            embeddings (attnpool 1024-d + avgpool 2048-d, what the reference's probes read) back to the host;
+    #                            the [2048,7,7] trunk tensor stays on the device, where its consumer (the policy / rollout storage) lives
+    #   e2e_fp32_all_to_host     fp32 normalised frames in, all three results incl. the 103 MB trunk tensor back (round 1's definition)
     copy_in, copy_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    dev_in = [torch.empty_like(frames) for _ in range(2)]
-    dev_out = [enc._outputs(BATCH, HEADS) for _ in range(2)]
-    host_out = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in dev_out[0].items()} for _ in range(2)]
-    ev_in = [torch.cuda.Event() for _ in range(2)]
-    ev_done = [torch.cuda.Event() for _ in range(2)]
-    ev_out = [torch.cuda.Event() for _ in range(2)]
     main = torch.cuda.current_stream(dev)
-
-    def e2e_steps(n):
-        for i in range(n):
-            s = i & 1
-            with torch.cuda.stream(copy_in):
-                copy_in.wait_event(ev_done[s])            # slot's previous compute has consumed its input
-                dev_in[s].copy_(host_frames, non_blocking=True)
-                ev_in[s].record(copy_in)
-            main.wait_event(ev_in[s])
-            main.wait_event(ev_out[s])                    # slot's previous results have left the device
-            enc.forward(dev_in[s], HEADS, out=dev_out[s])
-            ev_done[s].record(main)
-            with torch.cuda.stream(copy_out):
-                copy_out.wait_event(ev_done[s])
-                for k in HEADS:
-                    host_out[s][k].copy_(dev_out[s][k], non_blocking=True)
-                ev_out[s].record(copy_out)
-        copy_out.synchronize()
-
-    e2e_steps(max(W, 2))
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    t0.record(main)
-    e2e_steps(K)
-    main.wait_stream(copy_out)
-    t1.record(main)
-    barrier()
-    e2e_ms = max_over_ranks(t0.elapsed_time(t1))
-    e2e_value = world * BATCH * K / (e2e_ms * 1e-3)
-    h2d = host_frames.numel() * 4
-    d2h = sum(v.numel() * 4 for v in dev_out[0].values())
-
-    # same end-to-end loop from RAW uint8 frames (section 8f item 1): 4x fewer H2D bytes, normalisation in the stem kernel
+    dev_out = [enc._outputs(BATCH, HEADS) for _ in range(2)]
     host_u8 = synthetic_frames_u8(BATCH, seed=100 + rank).pin_memory()
-    host_f32, dev_in_f32 = host_frames, dev_in
-    host_frames, dev_in = host_u8, [torch.empty(host_u8.shape, dtype=torch.uint8, device=dev) for _ in range(2)]
-    e2e_steps(max(W, 2))
-    barrier()
-    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    u0.record(main)
-    e2e_steps(K)
-    main.wait_stream(copy_out)
-    u1.record(main)
-    barrier()
-    e2e_u8_ms = max_over_ranks(u0.elapsed_time(u1))
-    host_frames, dev_in = host_f32, dev_in_f32
+
+    def e2e_leg(host_in, to_host):
+        dev_in = [torch.empty(host_in.shape, dtype=host_in.dtype, device=dev) for _ in range(2)]
+        host_out = [{k: torch.empty(dev_out[0][k].shape, dtype=torch.float32).pin_memory() for k in to_host} for _ in range(2)]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+
+        def steps(n):
+            for i in range(n):
+                sl = i & 1
+                with torch.cuda.stream(copy_in):
+                    copy_in.wait_event(ev_done[sl])           # slot's previous compute has consumed its input
+                    dev_in[sl].copy_(host_in, non_blocking=True)
+                    ev_in[sl].record(copy_in)
+                main.wait_event(ev_in[sl])
+                main.wait_event(ev_out[sl])                   # slot's previous results have left the device
+                enc.forward(dev_in[sl], HEADS, out=dev_out[sl])
+                ev_done[sl].record(main)
+                with torch.cuda.stream(copy_out):
+                    copy_out.wait_event(ev_done[sl])
+                    for k in to_host:
+                        host_out[sl][k].copy_(dev_out[sl][k], non_blocking=True)
+                    ev_out[sl].record(copy_out)
+            copy_out.synchronize()
+
+        steps(max(W, 2))
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(main)
+        steps(K)
+        main.wait_stream(copy_out)
+        t1.record(main)
+        barrier()
+        ms = max_over_ranks(t0.elapsed_time(t1))
+        h2d_b = host_in.numel() * host_in.element_size()
+        d2h_b = sum(dev_out[0][k].numel() * 4 for k in to_host)
+        return {"value": world * BATCH * K / (ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
+                "ms_per_step": ms / K, "input": "uint8 NHWC raw RGB, normalised in the stem kernel" if host_in.dtype == torch.uint8 else "fp32 NHWC, mean/std-normalised on the host",
+                "heads_computed": list(HEADS), "heads_to_host": list(to_host),
+                "achieved_h2d_gbs_per_rank": h2d_b / (ms / K * 1e-3) / 1e9, "achieved_d2h_gbs_per_rank": d2h_b / (ms / K * 1e-3) / 1e9}
+
+    e2e = e2e_leg(host_u8, ("avgpool", "attnpool"))
+    e2e["api"] = "ClipRN50Encoder.forward on pinned host frames, double-buffered H2D/D2H"
+    e2e["cpu_affinity"] = f"rank bound to its GPU's {numa} NVML-local cores" if numa else "unbound"
+    e2e_all = e2e_leg(host_frames, HEADS)
+
+    # what the host link gives with EVERY rank copying at once and no compute (names the limiter of the host-fed legs at N > 1)
+    def copy_gbs(dst, src, n=8):
+        for _ in range(2):
+            dst.copy_(src, non_blocking=True)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(main)
+        for _ in range(n):
+            dst.copy_(src, non_blocking=True)
+        b.record(main)
+        barrier()
+        return n * src.numel() * src.element_size() / (max_over_ranks(a.elapsed_time(b)) * 1e-3) / 1e9
+    pin_out = torch.empty(frames.shape, dtype=torch.float32).pin_memory()
+    host_io = {"h2d_gbs_per_rank_all_ranks_copying": copy_gbs(torch.empty_like(frames), host_frames),
+               "d2h_gbs_per_rank_all_ranks_copying": copy_gbs(pin_out, frames), "ranks": world,
+               "what": "154 MB pinned <-> device copies, max over ranks, all ranks at once, no compute"}
+    del pin_out
 
     # ---------------- BASELINE configs 3 / 4: end-to-end PPO step (all ranks: the update all-reduces gradients)
     ppo = None if args.no_ppo else run_ppo_block(enc, dev, rank, world, args.ppo_rollouts, max_over_ranks, barrier)
     # BASELINE config 4 as written (60 samplers in total over the ranks); identical to `ppo` on one GPU, so only timed for N > 1
     ppo_strong = None if (args.no_ppo or world == 1) else run_ppo_block(enc, dev, rank, world, args.ppo_rollouts, max_over_ranks,
                                                                        barrier, global_samplers=60)
+    # the AllenAct data flow verbatim (fp32 NCHW features in storage), 1 GPU only: the number next to the packed one
+    ppo_allenact = None if (args.no_ppo or world > 1) else run_ppo_block(enc, dev, rank, world, max(1, args.ppo_rollouts - 1), max_over_ranks,
+                                                                      barrier, packed=False)
     vit = None if args.no_vit else run_vit_block(dev, rank, world, max(10, K // 4), 5, max_over_ranks, barrier)
     parity_n = None if (args.no_ppo or world == 1) else run_multi_rank_parity(dev, rank, world)
 
@@ -597,6 +632,12 @@ def run_ours(args, rank, local_rank, world):
     gemm_flop = (FLOP_TRUNK - FLOP_STEM_CONV1) * BATCH          # algorithmic conv FLOPs executed by conv_gemm launches
     sustained, burst, hbm, src = measured_peaks()
     achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12
+    # which measured peak the timed window is comparable to: the burst figure when the SM clock stayed near its maximum with no
+    # power cap active (a kernel timed in isolation), the sustained one when the window ran power-capped like the seconds-long loop
+    capped = bool(clocks) and ("sw_power_cap" in (clocks.get("reasons") or []) or (clocks.get("sm_mhz") or 0) < 0.9 * (clocks.get("sm_max_mhz") or 1))
+    peak = sustained if capped else burst
+    peak_why = (f"MEASURED_PEAKS.json {'bf16_tflops_sustained' if capped else 'bf16_tflops (burst)'} ({src}): timed window at "
+                f"{clocks.get('sm_mhz') if clocks else '?'} MHz, reasons {clocks.get('reasons') if clocks else '?'}")
     step_tflops = (FLOP_TRUNK + FLOP_ATTNPOOL_MIN) * BATCH / (ms_step * 1e-3) / 1e12
     top = sorted(prof, key=lambda x: -x[1])[:8]
     traffic, traffic_src = committed_traffic()
@@ -609,23 +650,20 @@ def run_ours(args, rank, local_rank, world):
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 operands, f32 accumulate (tcgen05 kind::f16)", "data": "synthetic",
-        "config": {"workload": "clip_rn50_encode_b256", "batch_per_gpu": BATCH, "resolution": RES, "heads": list(HEADS),
-                   "weights": "seeded synthetic (seed 1234)", "input": "fp32 NHWC, mean/std-normalised",
-                   "l2": "per-step working set (154 MB frames + 6.6 GB activations) exceeds the 126 MB L2"},
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / K, "api": "ClipRN50Encoder.forward on pinned host frames, double-buffered H2D/D2H",
-                "cpu_affinity": f"rank bound to its GPU's {numa} NVML-local cores" if numa else "unbound"},
-        "e2e_u8": {"value": world * BATCH * K / (e2e_u8_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": host_u8.numel(),
-                   "d2h_bytes_per_step": d2h, "ms_per_step": e2e_u8_ms / K, "input": "uint8 NHWC raw RGB, normalised in the stem kernel"},
+        "config": workload_config(),
+        "e2e": e2e,
+        "e2e_fp32_all_to_host": e2e_all,
+        "host_io": host_io,
         "gpu_launches": enc.launches_per_forward(HEADS) * K,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "tcgen05 conv kernels: conv_gemm + gemm2sm + conv3x3_halo + bneck_tail (all %d launches of a step)" % n_gemm,
-                     "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_step": int((154.1 + 47.2 + 29.6 + 105.9) * 1e6),
-                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src})",
-                     "frac_of_burst": achieved / burst, "gemm_ms_per_step": gemm_ms,
-                     "whole_step_tflops": step_tflops, "whole_step_frac": step_tflops / sustained},
+                     "peak_source": peak_why,
+                     "frac_of_burst": achieved / burst, "frac_of_sustained": achieved / sustained, "gemm_ms_per_step": gemm_ms,
+                     "whole_step_tflops": step_tflops, "whole_step_frac_of_burst": step_tflops / burst,
+                     "whole_step_frac_of_sustained": step_tflops / sustained},
         "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": "fp32 PyTorch oracle, 32 frames x 4 iterations (1 warm-up)"},
         "gpu_eager_baseline": gpu_eager,
@@ -634,7 +672,20 @@ def run_ours(args, rank, local_rank, world):
         "ppo_step": line_ppo,
         "ppo_step_60_samplers_total": ppo_strong,
         "vit_zero_shot": vit,
+        "ppo_step_allenact_flow": ppo_allenact,
         "multi_rank_parity": parity_n,
+    }
+    # compact recap LAST, so a tail of the line carries every block's headline (frames/s; device-resident / host-fed)
+    pick = lambda d: None if not d else {"value": round(d["value"], 1), "e2e": round(d["e2e"]["value"], 1), "ms_per_step": round(d["ms_per_step"], 3)}
+    line["summary"] = {
+        "n_gpus": world, "encode": {"value": round(value, 1), "e2e": round(e2e["value"], 1), "e2e_fp32_all_to_host": round(e2e_all["value"], 1),
+                                    "ms_per_step": round(ms_step, 3)},
+        "roofline_frac": round(achieved / peak, 4), "frac_of_burst": round(achieved / burst, 4), "frac_of_sustained": round(achieved / sustained, 4),
+        "ppo_weak_60_per_gpu": pick(ppo), "ppo_strong_60_total": pick(ppo_strong), "ppo_allenact_flow": pick(ppo_allenact),
+        "vit_512_total": pick(vit),
+        "parity": None if not parity_n else {"bit_identical": parity_n["params_bit_identical_across_ranks"],
+                                             "grad_rel_l2": parity_n["grad_rel_l2_pass1_vs_1rank"]},
+        "host_io_gbs": [round(host_io["h2d_gbs_per_rank_all_ranks_copying"], 1), round(host_io["d2h_gbs_per_rank_all_ranks_copying"], 1)],
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -88,6 +88,7 @@ int blocks_for(long long total, int threads, int cap_per_sm = 16) {
 
 extern "C" int embclip_wgrad_f16(const void* a, int lda, int M1, const void* b, int ldb, int N1, long long Kdim, float* out,
                                  long long ldo_m, long long ldo_n, const float* alpha, void* stream) {
+  EMBCLIP_TRACE();
   if (!a || !b || !out) return fail(EMBCLIP_EINVAL, "wgrad: null pointer");
   WgradOp op{a, lda, M1, b, ldb, N1, Kdim, out, ldo_m, ldo_n, -1, alpha};
   return launch_wgrad(op, (cudaStream_t)stream);
@@ -153,6 +154,7 @@ int launch_gru_backward(GruBwdParams p, cudaStream_t st) {
 extern "C" int embclip_gru_forward(const float* gi, const float* w_hh, const float* b_hh, const float* h0, const float* masks,
                                    const float* h_init, int T, int N, int H, float* out, float* save_r, float* save_z, float* save_n,
                                    float* save_hn, void* scratch32, void* stream) {
+  EMBCLIP_TRACE();
   if (!gi || !w_hh || !b_hh || !h0 || !masks || !out || !scratch32) return fail(EMBCLIP_EINVAL, "gru_forward: null pointer");
   if (T <= 0) return fail(EMBCLIP_EINVAL, "gru_forward: T must be positive");
   GruFwdParams p;
@@ -168,6 +170,7 @@ extern "C" int embclip_gru_backward(const float* w_hh, const float* h0, const fl
                                     const float* save_z, const float* save_n, const float* save_hn, const float* dout,
                                     const float* dh_last, const float* h_init, int T, int N, int H, float* dgi, float* dgh,
                                     void* hm_f16, float* dh0, float* dh_init, void* scratch32, void* stream) {
+  EMBCLIP_TRACE();
   if (!w_hh || !h0 || !masks || !out || !save_r || !save_z || !save_n || !save_hn || !dout || !dgi || !dgh || !hm_f16 || !scratch32)
     return fail(EMBCLIP_EINVAL, "gru_backward: null pointer");
   if (T <= 0) return fail(EMBCLIP_EINVAL, "gru_backward: T must be positive");
@@ -372,6 +375,7 @@ extern "C" uint64_t embclip_ac_workspace_bytes(embclip_ac_t h, int T, int N) {
 }
 
 extern "C" int embclip_ac_pack_features(embclip_ac_t h, const float* feats_nchw, long long frames, void* feats_f16, void* stream) {
+  EMBCLIP_TRACE();
   if (!h || !feats_nchw || !feats_f16 || frames <= 0) return fail(EMBCLIP_EINVAL, "ac_pack_features: bad argument");
   const int C = h->cfg.feat_channels, Pp = h->cfg.feat_pixels;
   const size_t smem = (size_t)128 * (Pp + 1) * 4;
@@ -464,6 +468,7 @@ static int ac_forward_impl(embclip_ac_t h, const float* params, uint64_t params_
 extern "C" int embclip_ac_forward(embclip_ac_t h, const float* params, const void* feats_f16, const long long* goals,
                                   const float* masks, const float* h0, int T, int N, float* logits, float* values, float* h_last,
                                   void* workspace, uint64_t workspace_bytes, int save_for_backward, void* stream) {
+  EMBCLIP_TRACE();
   return ac_forward_impl(h, params, 0, feats_f16, goals, masks, h0, T, N, logits, values, h_last, workspace, workspace_bytes,
                          save_for_backward, stream);
 }
@@ -472,6 +477,7 @@ extern "C" int embclip_ac_act(embclip_ac_t h, const float* params, uint64_t para
                               const long long* goals, const float* masks, const float* h0, int N, const float* uniforms,
                               long long* actions, float* action_log_probs, float* values, float* h_out, float* logits,
                               void* workspace, uint64_t workspace_bytes, void* stream) {
+  EMBCLIP_TRACE();
   if (!uniforms || !actions || !action_log_probs || !h_out || !logits) return fail(EMBCLIP_EINVAL, "ac_act: null pointer");
   int rc = ac_forward_impl(h, params, params_version, feats_f16, goals, masks, h0, 1, N, logits, values, h_out, workspace,
                            workspace_bytes, 0, stream);
@@ -486,6 +492,7 @@ extern "C" int embclip_ac_ppo_loss(embclip_ac_t h, const float* params, int T, i
                                    const float* returns, float clip_param, float value_loss_coef, float entropy_coef,
                                    float grad_scale, float* logits, float* values, float* loss_sums, void* workspace,
                                    uint64_t workspace_bytes, void* stream) {
+  EMBCLIP_TRACE();
   int rc;
   if ((rc = check_block(h, T, N, workspace, workspace_bytes))) return rc;
   if (!params || !actions || !old_action_log_probs || !norm_adv || !old_values || !returns || !logits || !values || !loss_sums)
@@ -511,6 +518,7 @@ extern "C" int embclip_ac_ppo_loss(embclip_ac_t h, const float* params, int T, i
 extern "C" int embclip_ac_backward(embclip_ac_t h, const float* params, const void* feats_f16, const long long* goals,
                                    const float* masks, const float* h0, int T, int N, const float* dlogits, const float* dvalues,
                                    const float* dh_last, float* grads, void* workspace, uint64_t workspace_bytes, void* stream) {
+  EMBCLIP_TRACE();
   int rc;
   if ((rc = check_block(h, T, N, workspace, workspace_bytes))) return rc;
   h->packed_version = 0;                                       // the backward pass reuses workspace regions
@@ -602,6 +610,7 @@ extern "C" int embclip_ac_backward(embclip_ac_t h, const float* params, const vo
 // =============================================================================================
 extern "C" int embclip_gae(const float* rewards, const float* values, const float* masks, int T, int N, float gamma, float tau,
                            float* returns, float* advantages, float* norm_advantages, float eps, void* stream) {
+  EMBCLIP_TRACE();
   if (!rewards || !values || !masks || !returns || !advantages || T <= 0 || N <= 0) return fail(EMBCLIP_EINVAL, "gae: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   gae_kernel<<<(N + 127) / 128, 128, 0, st>>>(rewards, values, masks, returns, advantages, T, N, gamma, tau);
@@ -614,6 +623,7 @@ extern "C" int embclip_gae(const float* rewards, const float* values, const floa
 }
 
 extern "C" int embclip_sumsq_f32(const float* x, long long n, float* out, void* stream) {
+  EMBCLIP_TRACE();
   if (!x || !out || n < 0) return fail(EMBCLIP_EINVAL, "sumsq: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float), st));
@@ -625,6 +635,7 @@ extern "C" int embclip_sumsq_f32(const float* x, long long n, float* out, void* 
 extern "C" int embclip_adam_clip_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                                       const float* grad_sumsq, float max_grad_norm, float lr, float beta1, float beta2, float eps,
                                       int step, void* stream) {
+  EMBCLIP_TRACE();
   if (!params || !grads || !exp_avg || !exp_avg_sq || n <= 0 || step < 1) return fail(EMBCLIP_EINVAL, "adam: bad argument");
   if (max_grad_norm > 0.f && !grad_sumsq) return fail(EMBCLIP_EINVAL, "adam: clipping needs the gradient sum of squares");
   const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);

@@ -489,6 +489,7 @@ static int launch_bneck_tail(const TailOp& op, cudaStream_t st) {
 // =============================================================================================
 extern "C" int embclip_gemm_f16(const void* a0, const void* a1, const void* w, const float* bias, const void* residual,
                                 void* out, int M, int N, int K0, int K1, int relu, int out_f32, void* stream) {
+  EMBCLIP_TRACE();
   if (!a0 || !w || !out || M <= 0) return fail(EMBCLIP_EINVAL, "gemm: null pointer or empty M");
   GemmOp op;
   op.a0 = a0; op.n = 1; op.h = 1; op.w = M; op.c0 = K0; op.lda0 = K0;
@@ -512,6 +513,7 @@ extern "C" int embclip_gemm_grouped_f16(const void* a, int lda, const void* w, i
 
 extern "C" int embclip_conv3x3_f16(const void* in, const void* w, const float* bias, void* out, int B, int H, int W,
                                    int Cin, int Cout, int relu, int pool, void* stream) {
+  EMBCLIP_TRACE();
   if (!in || !w || !out || B <= 0) return fail(EMBCLIP_EINVAL, "conv3x3: null pointer or empty batch");
   static const bool legacy = getenv("EMBCLIP_CONV3_LEGACY") != nullptr;   // 9-box-loads implicit GEMM (first version), for A/B timing
   if (legacy && !pool) {
@@ -527,6 +529,7 @@ extern "C" int embclip_conv3x3_f16(const void* in, const void* w, const float* b
 
 extern "C" int embclip_bneck_tail_f16(const void* y2, const void* x0, const void* w3, const float* b3, const void* residual, void* out,
                                       const void* w1, const float* b1, void* y1, int64_t M, int n1, void* stream) {
+  EMBCLIP_TRACE();
   TailOp op;
   op.a0 = y2; op.a1 = x0; op.w3 = w3; op.b3 = b3; op.residual = residual; op.out = out;
   op.w1 = w1; op.b1 = b1; op.y1 = y1; op.M = M; op.n1 = n1;
@@ -1125,6 +1128,7 @@ static int forward_impl(embclip_rn50* m, const FramesIn& frames, int B, float* o
 extern "C" int embclip_rn50_forward(embclip_rn50_t h, const float* frames_nhwc, int batch, float* out_trunk_nchw,
                                     float* out_avgpool, float* out_attnpool, void* workspace, uint64_t workspace_bytes,
                                     void* stream) {
+  EMBCLIP_TRACE();
   const FramesIn in{frames_nhwc, 0, {1, 1, 1, 0, 0, 0}};
   const int rc = forward_impl(h, in, batch, out_trunk_nchw, out_avgpool, out_attnpool, workspace, workspace_bytes,
                               (cudaStream_t)stream, nullptr, nullptr, 0);
@@ -1133,6 +1137,7 @@ extern "C" int embclip_rn50_forward(embclip_rn50_t h, const float* frames_nhwc, 
 extern "C" int embclip_rn50_forward_u8(embclip_rn50_t h, const uint8_t* frames_nhwc_u8, const float* mean3, const float* std3, int batch,
                                        float* out_trunk_nchw, float* out_avgpool, float* out_attnpool, void* workspace,
                                        uint64_t workspace_bytes, void* stream) {
+  EMBCLIP_TRACE();
   if (!mean3 || !std3) return fail(EMBCLIP_EINVAL, "forward_u8: mean / std required");
   FramesIn in{frames_nhwc_u8, 1, {0, 0, 0, 0, 0, 0}};
   for (int c = 0; c < 3; ++c) {
@@ -1147,6 +1152,7 @@ extern "C" int embclip_rn50_forward_u8(embclip_rn50_t h, const uint8_t* frames_n
 extern "C" int embclip_rn50_profile(embclip_rn50_t h, const float* frames_nhwc, int batch, float* out_trunk_nchw,
                                     float* out_avgpool, float* out_attnpool, void* workspace, uint64_t workspace_bytes,
                                     void* stream, float* op_ms, char* names, int max_ops) {
+  EMBCLIP_TRACE();
   if (!op_ms || max_ops <= 0) return fail(EMBCLIP_EINVAL, "profile: need op_ms buffer");
   const FramesIn in{frames_nhwc, 0, {1, 1, 1, 0, 0, 0}};
   return forward_impl(h, in, batch, out_trunk_nchw, out_avgpool, out_attnpool, workspace, workspace_bytes,
@@ -1154,6 +1160,7 @@ extern "C" int embclip_rn50_profile(embclip_rn50_t h, const float* frames_nhwc, 
 }
 extern "C" int embclip_rn50_export_rows_f16(embclip_rn50_t h, int batch, const void* workspace, uint64_t workspace_bytes,
                                             void* out_rows_f16, void* stream) {
+  EMBCLIP_TRACE();
   if (!h || !workspace || !out_rows_f16 || batch <= 0) return fail(EMBCLIP_EINVAL, "export_rows: null argument or empty batch");
   if (workspace_bytes < embclip_rn50_workspace_bytes(h, batch)) return fail(EMBCLIP_ENOSPC, "export_rows: workspace too small for batch %d", batch);
   if (reinterpret_cast<uintptr_t>(out_rows_f16) % 16) return fail(EMBCLIP_EINVAL, "export_rows: output must be 16-B aligned");

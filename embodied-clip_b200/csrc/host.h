@@ -7,6 +7,8 @@
 
 #include <utility>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/embclip_b200.h"
 
 namespace embclip {
@@ -17,6 +19,16 @@ int fail(int code, const char* fmt, ...);
     cudaError_t e_ = (expr);                                                                            \
     if (e_ != cudaSuccess) return ::embclip::fail(EMBCLIP_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
   } while (0)
+
+// NVTX range over one C-ABI entry point (SURVEY.md section 5 "tracing"): shows up as a named span on the host timeline of
+// Nsight Systems / any NVTX consumer; a no-op (one relaxed load) when no tool is attached.  Header-only NVTX v3: no link dependency.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define EMBCLIP_TRACE() ::embclip::NvtxRange nvtx_range_(__func__)
 
 int num_sms();         // SM count of the CURRENT device (cached per device ordinal)
 bool pdl_enabled();   // false when $EMBCLIP_NO_PDL is set

@@ -240,6 +240,7 @@ extern "C" uint64_t embclip_tf_workspace_bytes(embclip_tf_t h, int batch) {
 
 extern "C" int embclip_vit_forward(embclip_tf_t h, const float* frames_nhwc, int batch, float* out, void* workspace,
                                    uint64_t workspace_bytes, void* stream) {
+  EMBCLIP_TRACE();
   int rc;
   if ((rc = tf_check(h, EMBCLIP_TF_VISION, batch, frames_nhwc, out, workspace, workspace_bytes))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -265,6 +266,7 @@ extern "C" int embclip_vit_forward(embclip_tf_t h, const float* frames_nhwc, int
 
 extern "C" int embclip_text_forward(embclip_tf_t h, const long long* token_ids, int prompts, float* out, void* workspace,
                                     uint64_t workspace_bytes, void* stream) {
+  EMBCLIP_TRACE();
   int rc;
   if ((rc = tf_check(h, EMBCLIP_TF_TEXT, prompts, token_ids, out, workspace, workspace_bytes))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -282,6 +284,7 @@ extern "C" int embclip_text_forward(embclip_tf_t h, const long long* token_ids, 
 
 extern "C" int embclip_clip_logits(const float* image_features, const float* text_features, int batch, int prompts, int embed_dim,
                                    float logit_scale, float* logits, void* stream) {
+  EMBCLIP_TRACE();
   if (!image_features || !text_features || !logits || batch <= 0 || prompts <= 0 || embed_dim <= 0)
     return fail(EMBCLIP_EINVAL, "clip_logits: bad argument");
   const int total = batch * prompts;
