@@ -468,7 +468,7 @@ class PPOTrainer:
         self.grads = torch.zeros_like(p.data)
         self.exp_avg = torch.zeros_like(p.data)
         self.exp_avg_sq = torch.zeros_like(p.data)
-        self.sumsq = torch.zeros(1, dtype=torch.float32, device=p.device)
+        self.sumsq = torch.zeros(1024, dtype=torch.float32, device=p.device)   # [0] = sum g^2; the rest is the kernel's scratch (EMBCLIP_SUMSQ_FLOATS)
         self.loss_sums = torch.zeros(3, dtype=torch.float32, device=p.device)
         self.step_count = 0
         self.kernel_launch_estimate = 0

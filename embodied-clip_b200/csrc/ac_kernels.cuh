@@ -371,18 +371,41 @@ adv_norm_kernel(const float* __restrict__ ret, const float* __restrict__ val, fl
 // ------------------------------------------------------------------------------------------------
 // clip_grad_norm_ + Adam on flat fp32 buffers.
 // ------------------------------------------------------------------------------------------------
+// DETERMINISTIC: every rank of a data-parallel job must turn the (bit-identical, all-reduced) gradient into the bit-identical
+// clip coefficient, or the replicas' parameters drift apart ulp by ulp (measured on 2 GPUs with the first version, which
+// combined the block partials with atomicAdd in arrival order).  Each block writes its partial to scratch[blockIdx]; the block
+// that finishes last (a counter) adds the partials in index order.  out: [0] result, [1] counter (zeroed by the launcher),
+// [2 ..] one partial per block.
+constexpr int kSumsqMaxBlocks = 1022;
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += g[i] * g[i];
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   __shared__ float sh[8];
+  __shared__ bool last;
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += sh[i];
-    atomicAdd(out, t);
+    out[2 + blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(reinterpret_cast<unsigned int*>(out + 1), 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    float t = 0.f;
+    for (int i = threadIdx.x; i < int(gridDim.x); i += 256) t += __ldcg(out + 2 + i);      // fixed assignment of partials to threads
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float r = 0.f;
+      for (int i = 0; i < 8; ++i) r += sh[i];
+      out[0] = r;
+    }
   }
 }
 

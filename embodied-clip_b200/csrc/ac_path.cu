@@ -626,8 +626,12 @@ extern "C" int embclip_sumsq_f32(const float* x, long long n, float* out, void* 
   EMBCLIP_TRACE();
   if (!x || !out || n < 0) return fail(EMBCLIP_EINVAL, "sumsq: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float), st));
-  if (n) sumsq_kernel<<<blocks_for(n, 256, 4), 256, 0, st>>>(x, n, out);
+  CUDA_TRY(cudaMemsetAsync(out, 0, 2 * sizeof(float), st));               // result + the arrival counter
+  if (n) {
+    int blocks = blocks_for(n, 256, 4);
+    if (blocks > kSumsqMaxBlocks) blocks = kSumsqMaxBlocks;
+    sumsq_kernel<<<blocks, 256, 0, st>>>(x, n, out);
+  }
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -270,7 +270,10 @@ int embclip_clip_logits(const float* image_features, const float* text_features,
  * -> returns [T,N], advantages [T,N] and (if non-NULL) norm_advantages = (A - mean) / (std + eps). */
 int embclip_gae(const float* rewards, const float* values, const float* masks, int T, int N, float gamma, float tau,
                 float* returns, float* advantages, float* norm_advantages, float eps, void* stream);
-/* out[0] = sum x^2 (the squared global gradient norm of clip_grad_norm_). */
+/* out[0] = sum x^2 (the squared global gradient norm of clip_grad_norm_), DETERMINISTIC: the same input gives the same bits on
+ * every launch / rank (block partials are combined in index order, not arrival order), so data-parallel replicas that hold the
+ * same all-reduced gradient apply the same clip coefficient.  `out` must hold EMBCLIP_SUMSQ_FLOATS floats ([1 ..] is scratch). */
+#define EMBCLIP_SUMSQ_FLOATS 1024
 int embclip_sumsq_f32(const float* x, long long n, float* out, void* stream);
 /* clip_grad_norm_(max_grad_norm) from *grad_sumsq (skipped when max_grad_norm <= 0), then torch.optim.Adam
  * (no weight decay / amsgrad) step number `step` (1-based) on flat buffers; grads are scaled in place. */

@@ -180,7 +180,7 @@ def test_adam_clip_vs_torch(lib, max_norm):
     opt = torch.optim.Adam([p_ref], lr=3e-4)
     p = p0.clone().cuda()
     m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
-    ss = torch.zeros(1, device="cuda")
+    ss = torch.zeros(1024, device="cuda")                  # EMBCLIP_SUMSQ_FLOATS: [0] result, rest scratch
     for step in range(1, 4):
         g = torch.randn(n) * (0.1 if step != 2 else 1e-3)
         p_ref.grad = g.clone()
@@ -191,8 +191,22 @@ def test_adam_clip_vs_torch(lib, max_norm):
         _check(lib, lib.embclip_adam_clip_step(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, ss.data_ptr(), max_norm,
                                                3e-4, 0.9, 0.999, 1e-8, step, _st()))
         torch.cuda.synchronize()
-        assert rel(ss.sqrt(), g.norm()) <= 1e-5
+        assert rel(ss[:1].sqrt(), g.norm()) <= 1e-5
         assert (p.cpu() - p_ref.detach()).abs().max().item() <= 1e-6, f"step {step}"
+
+
+def test_sumsq_is_deterministic(lib):
+    """The squared gradient norm must be bit-identical launch after launch (and therefore rank by rank): data-parallel replicas
+    turn the same all-reduced gradient into the same clip coefficient, or their parameters drift apart."""
+    g = torch.randn(3_480_775, device="cuda") * torch.logspace(-6, 2, 3_480_775, device="cuda")
+    ss = torch.zeros(1024, device="cuda")
+    seen = set()
+    for _ in range(20):
+        _check(lib, lib.embclip_sumsq_f32(g.data_ptr(), g.numel(), ss.data_ptr(), _st()))
+        torch.cuda.synchronize()
+        seen.add(ss[:1].view(torch.int32).item())
+    assert len(seen) == 1
+    assert rel(ss[:1], g.double().square().sum().float()) <= 1e-5
 
 
 # ----------------------------------------------------------------------------------------------- full model
