@@ -96,6 +96,7 @@ SIGNATURES = {
     "embclip_sumsq_f32": (_I, [_FP, _LL, _FP, _VP]),
     "embclip_adam_clip_step": (_I, [_FP, _FP, _FP, _FP, _LL, _FP, _F, _F, _F, _F, _F, _I, _VP]),
     "embclip_wgrad_f16": (_I, [_VP, _I, _I, _VP, _I, _I, _LL, _FP, _LL, _LL, _FP, _VP]),
+    "embclip_gru_geometry": (_I, [_I, _I, C.POINTER(C.c_int)]),
     "embclip_gru_forward": (_I, [_FP, _FP, _FP, _FP, _FP, _FP, _I, _I, _I, _FP, _FP, _FP, _FP, _FP, _VP, _VP]),
     "embclip_gru_backward": (_I, [_FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _I, _I, _I, _FP, _FP, _VP, _FP, _FP, _VP, _VP]),
 }

@@ -13,6 +13,7 @@
 #include "host.h"
 #include "ac_kernels.cuh"
 #include "gru_kernels.cuh"
+#include "gru_cluster.cuh"
 #include "wgrad_gemm.cuh"
 
 using namespace embclip;
@@ -124,7 +125,78 @@ int gru_geometry(int N, int H, GruGeom* g) {
 size_t gru_fwd_smem(int H) { return sizeof(float) * (size_t(3 * kGruUB + kGruNS) * (H + 4) + 8 * kGruNS * 24); }
 size_t gru_bwd_smem(int H) { return sizeof(float) * (size_t(3 * H) * kGruUB + size_t(kGruNS) * (3 * H / 2 + 4)); }
 
+// ---- cluster path (gru_cluster.cuh): CS = H / 32 CTAs per cluster, <= 12 samplers per cluster, no cooperative launch
+struct GruClusterGeom { int cs, groups, ns, nsp, max_clusters; };
+size_t gru_cluster_fwd_smem(int H, int nsp) { return sizeof(float) * (size_t(3 * kGcUB) * H + size_t(nsp) * H + size_t(nsp) * 96 + size_t(nsp) * kGcUB); }
+size_t gru_cluster_bwd_smem(int H, int nsp) { return sizeof(float) * (size_t(3 * kGcUB) * H + size_t(16) * nsp * kGcUB + size_t(nsp) * 96); }
+
+template <typename Kernel>
+bool gru_cluster_geometry(Kernel kernel, int N, int H, size_t smem_max, GruClusterGeom* g) {
+  static const bool off = getenv("EMBCLIP_GRU_NO_CLUSTER") != nullptr;       // A/B switch: the cooperative kernels of gru_kernels.cuh
+  if (off || H % 32 || H / 32 > 16 || H / 32 < 1 || smem_max > 232448) return false;
+  const int cs = H / 32;
+  if (ensure_smem((const void*)kernel, smem_max)) return false;
+  if (cs > 8 && cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3(cs); cfg.blockDim = dim3(kGcThreads); cfg.dynamicSmemBytes = smem_max; cfg.attrs = attr; cfg.numAttrs = 1;
+  int max_clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, (const void*)kernel, &cfg) != cudaSuccess || max_clusters < 1) {
+    cudaGetLastError();
+    return false;
+  }
+  // one wave when it fits (as many clusters as the device keeps resident, samplers spread evenly); otherwise full clusters
+  int groups = max_clusters < N ? max_clusters : N;
+  int ns = (N + groups - 1) / groups;
+  if (ns > kGcMaxNS) { groups = (N + kGcMaxNS - 1) / kGcMaxNS; ns = (N + groups - 1) / groups; }
+  g->ns = ns;
+  g->groups = (N + ns - 1) / ns;
+  g->nsp = (ns + kGcSPT - 1) / kGcSPT * kGcSPT;
+  g->cs = cs;
+  g->max_clusters = max_clusters;
+  return true;
+}
+template <typename Kernel, typename Params>
+int launch_gru_cluster(Kernel kernel, const Params& p, const GruClusterGeom& g, size_t smem, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = g.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3(g.cs * g.groups); cfg.blockDim = dim3(kGcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, p));
+  return 0;
+}
+// the backward kernel keeps a thread's partial sums in registers: samplers per cluster is a template parameter (multiples of 3)
+bool gru_cluster_bwd_geometry(int N, int H, GruClusterGeom* g) {
+  return gru_cluster_geometry(gru_cluster_backward_kernel<kGcMaxNS>, N, H, gru_cluster_bwd_smem(H, kGcMaxNS), g);
+}
+int launch_gru_cluster_bwd(const GruBwdParams& p, const GruClusterGeom& g, cudaStream_t st) {
+  const size_t smem = gru_cluster_bwd_smem(p.H, g.nsp);
+#define EMBCLIP_GCB(NS_)                                                                                            \
+  if (g.nsp == NS_) {                                                                                                \
+    { const int rc_ = ensure_smem((const void*)gru_cluster_backward_kernel<NS_>, smem); if (rc_) return rc_; }       \
+    if (g.cs > 8) CUDA_TRY(cudaFuncSetAttribute((const void*)gru_cluster_backward_kernel<NS_>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); \
+    return launch_gru_cluster(gru_cluster_backward_kernel<NS_>, p, g, smem, st);                                      \
+  }
+  EMBCLIP_GCB(3) EMBCLIP_GCB(6) EMBCLIP_GCB(9) EMBCLIP_GCB(12)
+#undef EMBCLIP_GCB
+  return fail(EMBCLIP_EINVAL, "gru: no cluster kernel for %d samplers per cluster", g.nsp);
+}
+
 int launch_gru_forward(GruFwdParams p, cudaStream_t st) {
+  if (p.H % 64 || p.H <= 0) return fail(EMBCLIP_EINVAL, "gru: hidden size must be a multiple of 64");
+  if (p.N <= 0) return fail(EMBCLIP_EINVAL, "gru: no samplers");
+  GruClusterGeom cg;
+  if (gru_cluster_geometry(gru_cluster_forward_kernel, p.N, p.H, gru_cluster_fwd_smem(p.H, kGcMaxNS), &cg)) {
+    p.groups = cg.groups; p.ns = cg.ns;
+    return launch_gru_cluster(gru_cluster_forward_kernel, p, cg, gru_cluster_fwd_smem(p.H, cg.nsp), st);
+  }
   GruGeom g;
   int rc;
   if ((rc = gru_geometry(p.N, p.H, &g))) return rc;
@@ -137,6 +209,13 @@ int launch_gru_forward(GruFwdParams p, cudaStream_t st) {
   return 0;
 }
 int launch_gru_backward(GruBwdParams p, cudaStream_t st) {
+  if (p.H % 64 || p.H <= 0) return fail(EMBCLIP_EINVAL, "gru: hidden size must be a multiple of 64");
+  if (p.N <= 0) return fail(EMBCLIP_EINVAL, "gru: no samplers");
+  GruClusterGeom cg;
+  if (gru_cluster_bwd_geometry(p.N, p.H, &cg)) {
+    p.groups = cg.groups; p.ns = cg.ns;
+    return launch_gru_cluster_bwd(p, cg, st);
+  }
   GruGeom g;
   int rc;
   if ((rc = gru_geometry(p.N, p.H, &g))) return rc;
@@ -150,6 +229,19 @@ int launch_gru_backward(GruBwdParams p, cudaStream_t st) {
 }
 
 }  // namespace
+
+/* Geometry the GRU launchers would use for (N samplers, hidden H) on the current device: out[0] = CTAs per cluster (0: the
+ * cooperative kernels are used instead), out[1] = clusters (sampler groups), out[2] = samplers per cluster, out[3] = clusters
+ * the device can keep resident at once (forward kernel), out[4] = the same for the backward kernel. */
+extern "C" int embclip_gru_geometry(int N, int H, int* out5) {
+  if (!out5 || N <= 0 || H <= 0) return fail(EMBCLIP_EINVAL, "gru_geometry: bad argument");
+  GruClusterGeom f, b;
+  memset(out5, 0, 5 * sizeof(int));
+  if (gru_cluster_geometry(gru_cluster_forward_kernel, N, H, gru_cluster_fwd_smem(H, kGcMaxNS), &f) && gru_cluster_bwd_geometry(N, H, &b)) {
+    out5[0] = f.cs; out5[1] = f.groups; out5[2] = f.ns; out5[3] = f.max_clusters; out5[4] = b.max_clusters;
+  }
+  return 0;
+}
 
 extern "C" int embclip_gru_forward(const float* gi, const float* w_hh, const float* b_hh, const float* h0, const float* masks,
                                    const float* h_init, int T, int N, int H, float* out, float* save_r, float* save_z, float* save_n,

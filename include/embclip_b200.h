@@ -294,6 +294,10 @@ int embclip_wgrad_f16(const void* a, int lda, int M1, const void* b, int ldb, in
 int embclip_gru_forward(const float* gi, const float* w_hh, const float* b_hh, const float* h0, const float* masks,
                         const float* h_init, int T, int N, int H, float* out, float* save_r, float* save_z, float* save_n,
                         float* save_hn, void* scratch32, void* stream);
+/* Launch geometry of the two GRU kernels for (N samplers, hidden H) on the current device: out5 = {CTAs per thread-block cluster
+ * (H / 32; 0 = the cooperative grid-barrier kernels run instead), clusters, samplers per cluster, resident clusters (forward),
+ * resident clusters (backward)}. */
+int embclip_gru_geometry(int N, int H, int* out5);
 /* BPTT of the above: dout [T,N,H], dh_last [N,H] or NULL -> dgi, dgh [T,N,3H] fp32, hm_f16 [T,N,H] fp16
  * (masked previous hidden state), dh0 [N,H] or NULL. */
 int embclip_gru_backward(const float* w_hh, const float* h0, const float* masks, const float* out, const float* save_r,

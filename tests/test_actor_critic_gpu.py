@@ -149,8 +149,9 @@ def test_gru_rejects_bad_shapes(lib):
     z = torch.zeros(64, device="cuda")
     assert lib.embclip_gru_forward(z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), None, 1, 1, 100, z.data_ptr(),
                                    None, None, None, None, z.data_ptr(), _st()) < 0       # H not a multiple of 64
-    assert lib.embclip_gru_forward(z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), None, 1, 1000, 512, z.data_ptr(),
-                                   None, None, None, None, z.data_ptr(), _st()) < 0       # too many samplers for one launch
+    assert lib.embclip_gru_forward(z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), None, 1, 1000, 1024, z.data_ptr(),
+                                   None, None, None, None, z.data_ptr(), _st()) < 0       # H = 1024: beyond the cluster path (H <= 512), and too many
+                                                                                           # samplers for one cooperative launch
 
 
 # ----------------------------------------------------------------------------------------------- GAE / Adam
