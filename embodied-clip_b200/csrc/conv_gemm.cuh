@@ -65,9 +65,12 @@ struct ConvGemmCfg {
   // kRes: a ring of 4 staging CHUNKS (128 rows x kCS columns) instead of two whole-tile buffers
   static constexpr int kResBufs = 4;
   static constexpr int kChunksPerTile = BN / kCS;
-  static constexpr int kWarpsPerChunk = kEpiWarps / kChunksPerTile;
+  // warps writing into one staging chunk: the 4 TMEM lane quarters x the column halves that fall inside the chunk
+  static constexpr int kWarpsPerChunk = 4 * (kColsPerWarp >= kCS ? 1 : kCS / kColsPerWarp);
   static constexpr int kCTotal = kRes ? kResBufs * kCChunkBytes : kCBufs * kCBytes;
-  static constexpr int kBudget = 200 * 1024;
+  // (kRes, BN = 256: 48-KB stages -- three of them need the larger budget; K = 256 layers are bound by the L2 -> smem fill, and
+  //  a 128 x 256 tile moves 20 % fewer operand bytes per FLOP than two 128 x 128 tiles)
+  static constexpr int kBudget = (kRes && BN == 256) ? 214 * 1024 : 200 * 1024;
   static constexpr int kStagesRaw = (kBudget - kCTotal) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
@@ -261,7 +264,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int row = q * 32 + lane;
       const int wi = warp - 2;                                   // 0..7
       const int col_base = (wi >> 2) * Cfg::kColsPerWarp;        // this warp's half of the tile's columns
-      const int cc = col_base / Cfg::kCS;                        // its staging chunk inside the tile
+      // the warp's columns as segments that each lie inside ONE staging chunk (BN = 256: two 64-column chunks per warp)
+      constexpr int SEG = Cfg::kColsPerWarp < Cfg::kCS ? Cfg::kColsPerWarp : Cfg::kCS;
+      constexpr int NSEG = Cfg::kColsPerWarp / SEG;
       float* const bias_w = sBias_ptr + wi * Cfg::kColsPerWarp;  // private bias slice
       int acc = 0;
       uint32_t acc_phase = 0;
@@ -271,74 +276,78 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int n0 = (tt % p.num_n_blks) * BN;
         const int grow = (tt / p.num_n_blks) * 128 + row;
         const bool row_ok = grow < p.M;
-        const int step = it * NC + cc;
-        const uint32_t sCt = sC + uint32_t(step & 3) * Cfg::kCChunkBytes;
         for (int i = lane; i < Cfg::kColsPerWarp; i += 32) bias_w[i] = p.bias ? __ldg(p.bias + n0 + col_base + i) : 0.f;
         __syncwarp();
         mbar_wait(bar_tfull + 8 * acc, acc_phase);
         tcgen05_fence_after();
-        mbar_wait(bar_res + 8 * (step & 3), uint32_t(step >> 2) & 1u);
 #pragma unroll 1
-        for (int c = 0; c < Cfg::kColsPerWarp / CH; ++c) {
-          const int col = col_base + c * CH;
-          uint32_t v[CH];
-          tmem_ld_32x32b<CH>(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + col), v);
-          const int piece0 = (col % Cfg::kCS) / 8;
-          uint4 rres[NP];
-#pragma unroll
-          for (int i = 0; i < NP; ++i) {
-            const uint32_t a = sCt + swizzle_off<Cfg::kCSwz>(uint32_t(row), uint32_t(piece0 + i));
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rres[i].x), "=r"(rres[i].y), "=r"(rres[i].z), "=r"(rres[i].w) : "r"(a));
-          }
-          tmem_ld_wait();
-          float f[CH];
-#pragma unroll
-          for (int i = 0; i < CH; ++i) f[i] = __uint_as_float(v[i]) + bias_w[c * CH + i];
-#pragma unroll
-          for (int i = 0; i < NP; ++i) {
-            const __half2* h = reinterpret_cast<const __half2*>(&rres[i]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 r2 = __half22float2(h[j]);
-              if (p.res_mode == 0) {
-                f[i * 8 + j * 2] += r2.x;
-                f[i * 8 + j * 2 + 1] += r2.y;
-              } else {
-                f[i * 8 + j * 2] = r2.x > 0.f ? f[i * 8 + j * 2] : 0.f;
-                f[i * 8 + j * 2 + 1] = r2.y > 0.f ? f[i * 8 + j * 2 + 1] : 0.f;
-              }
-            }
-          }
-          if (p.relu == 1) {
-#pragma unroll
-            for (int i = 0; i < CH; ++i) f[i] = fmaxf(f[i], 0.f);
-          } else if (p.relu == 2) {
-#pragma unroll
-            for (int i = 0; i < CH; ++i) f[i] = __fdividef(f[i], 1.f + __expf(-1.702f * f[i]));
-          }
-          if (p.out_f32) {
-            if (row_ok) {
-              float4* op = reinterpret_cast<float4*>(p.out_f32_ptr + size_t(grow) * p.ldo + n0 + col);
-#pragma unroll
-              for (int i = 0; i < CH / 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-            }
-          } else {
+        for (int sg = 0; sg < NSEG; ++sg) {
+          const int seg_col = col_base + sg * SEG;
+          const int step = it * NC + seg_col / Cfg::kCS;           // position of this chunk in the ring of 4
+          const uint32_t sCt = sC + uint32_t(step & 3) * Cfg::kCChunkBytes;
+          mbar_wait(bar_res + 8 * (step & 3), uint32_t(step >> 2) & 1u);
+#pragma unroll 1
+          for (int c = 0; c < SEG / CH; ++c) {
+            const int col = seg_col + c * CH;
+            uint32_t v[CH];
+            tmem_ld_32x32b<CH>(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + col), v);
+            const int piece0 = (col % Cfg::kCS) / 8;
+            uint4 rres[NP];
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
               const uint32_t a = sCt + swizzle_off<Cfg::kCSwz>(uint32_t(row), uint32_t(piece0 + i));
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
-                           "r"(pack_half2(f[8 * i], f[8 * i + 1])), "r"(pack_half2(f[8 * i + 2], f[8 * i + 3])),
-                           "r"(pack_half2(f[8 * i + 4], f[8 * i + 5])), "r"(pack_half2(f[8 * i + 6], f[8 * i + 7]))
-                           : "memory");
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rres[i].x), "=r"(rres[i].y), "=r"(rres[i].z), "=r"(rres[i].w) : "r"(a));
+            }
+            tmem_ld_wait();
+            float f[CH];
+#pragma unroll
+            for (int i = 0; i < CH; ++i) f[i] = __uint_as_float(v[i]) + bias_w[col - col_base + i];
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+              const __half2* h = reinterpret_cast<const __half2*>(&rres[i]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 r2 = __half22float2(h[j]);
+                if (p.res_mode == 0) {
+                  f[i * 8 + j * 2] += r2.x;
+                  f[i * 8 + j * 2 + 1] += r2.y;
+                } else {
+                  f[i * 8 + j * 2] = r2.x > 0.f ? f[i * 8 + j * 2] : 0.f;
+                  f[i * 8 + j * 2 + 1] = r2.y > 0.f ? f[i * 8 + j * 2 + 1] : 0.f;
+                }
+              }
+            }
+            if (p.relu == 1) {
+#pragma unroll
+              for (int i = 0; i < CH; ++i) f[i] = fmaxf(f[i], 0.f);
+            } else if (p.relu == 2) {
+#pragma unroll
+              for (int i = 0; i < CH; ++i) f[i] = __fdividef(f[i], 1.f + __expf(-1.702f * f[i]));
+            }
+            if (p.out_f32) {
+              if (row_ok) {
+                float4* op = reinterpret_cast<float4*>(p.out_f32_ptr + size_t(grow) * p.ldo + n0 + col);
+#pragma unroll
+                for (int i = 0; i < CH / 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < NP; ++i) {
+                const uint32_t a = sCt + swizzle_off<Cfg::kCSwz>(uint32_t(row), uint32_t(piece0 + i));
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
+                             "r"(pack_half2(f[8 * i], f[8 * i + 1])), "r"(pack_half2(f[8 * i + 2], f[8 * i + 3])),
+                             "r"(pack_half2(f[8 * i + 4], f[8 * i + 5])), "r"(pack_half2(f[8 * i + 6], f[8 * i + 7]))
+                             : "memory");
+              }
             }
           }
-        }
-        tcgen05_fence_before();
-        if (!p.out_f32) fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(bar_tempty + 8 * acc);                     // accumulator columns of this warp drained
-          mbar_arrive(bar_cready + 8 * (step & 3));              // its share of the chunk is in the staging buffer
+          if (sg == NSEG - 1) tcgen05_fence_before();              // (last TMEM read of this tile is behind us)
+          if (!p.out_f32) fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (sg == NSEG - 1) mbar_arrive(bar_tempty + 8 * acc);   // accumulator columns of this warp drained
+            mbar_arrive(bar_cready + 8 * (step & 3));              // its share of the chunk is in the staging buffer
+          }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }

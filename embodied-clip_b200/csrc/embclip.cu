@@ -274,10 +274,17 @@ int embclip::launch_gemm(const GemmOp& op, cudaStream_t st, int force_bn) {
   const bool res = op.residual != nullptr;
   static const int big_bn = getenv("EMBCLIP_BN256") ? atoi(getenv("EMBCLIP_BN256")) : 0;
   if (big_bn && !force_bn && !res && !op.grp_n && op.cout % 256 == 0 && bk == 64) bn = 256;
-  if (res && bn > 128) bn = 128;                       // residual variant double-buffers the staging tile
+  if (res && bn > 128) bn = 128;
+  // residual GEMMs with short K (conv3 of layers 2-4: K = 128 .. 512) are bound by the L2 -> shared-memory fill (ncu: 9.3 TB/s
+  // through the crossbar, tensor pipe 25 %): a 128 x 256 tile moves 20 % fewer operand bytes per FLOP than two 128 x 128 tiles
+  static const int res_bn256 = getenv("EMBCLIP_RES_BN256") ? atoi(getenv("EMBCLIP_RES_BN256")) : 1;
+  if (res_bn256 && res && !force_bn && !op.grp_n && !op.out_f32 && bk == 64 && op.cout % 256 == 0 && op.taps == 1 &&
+      op.c0 + op.c1 >= 256 &&                            // (K = 128, layer 2: HBM-bound, measured 2 % slower on the wide tile)
+      (((long long)op.n * op.h * op.w + 127) / 128) * (op.cout / 256) >= num_sms())
+    bn = 256;
 #define EMBCLIP_CASE(BN_, BK_) \
   if (bn == BN_ && bk == BK_) return res ? launch_cfg<BN_, BK_, true>(op, st) : launch_cfg<BN_, BK_, false>(op, st);
-  if (bn == 256 && bk == 64) return launch_cfg<256, 64, false>(op, st);   // (no residual variant: staging would not fit)
+  if (bn == 256 && bk == 64) return res ? launch_cfg<256, 64, true>(op, st) : launch_cfg<256, 64, false>(op, st);
   EMBCLIP_CASE(128, 64)
   EMBCLIP_CASE(64, 64)
   EMBCLIP_CASE(32, 64)

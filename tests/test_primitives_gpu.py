@@ -94,6 +94,13 @@ def test_gemm_epilogues(lib):
     _gemm_case(lib, 300, 128, 64, out_f32=True, res=True)
 
 
+@pytest.mark.parametrize("M,N,K", [(128 * 37 + 5, 1024, 256), (128 * 19, 2048, 256), (128 * 150, 256, 256)])
+def test_gemm_residual_wide_tile(lib, M, N, K):
+    """conv3 + identity residual of layers 3 / 4 at batch size: enough 128 x 256 tiles for every SM -> conv_gemm_kernel<256, 64, true>
+    (two staging chunks per epilogue warp, ring of four = one tile; ragged last M tile; persistent loop over several tiles per CTA)."""
+    _gemm_case(lib, M, N, K, res=True, relu=True, seed=M % 89)
+
+
 def test_gemm_k_concat(lib):
     """[W3 | Wd] . [t ; x]: the fused conv3 + downsample of a bottleneck's first block"""
     _gemm_case(lib, 784, 512, 128, K1=256, relu=True)
