@@ -10,7 +10,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libembclip_b200.so")
 SOURCES = ["embclip.cu", "ac_path.cu", "tf_path.cu"]
 HEADERS = ["ptx.cuh", "conv_gemm.cuh", "conv3x3_halo.cuh", "aux_kernels.cuh", "host.h", "ac_kernels.cuh", "gru_kernels.cuh", "gru_cluster.cuh",
-           "wgrad_gemm.cuh", "tf_kernels.cuh", "gemm2sm.cuh", "bneck_tail.cuh", "tv_kernels.cuh", os.path.join("..", "..", "include", "embclip_b200.h")]
+           "wgrad_gemm.cuh", "tf_kernels.cuh", "gemm2sm.cuh", "bneck_tail.cuh", "bneck_tail_stream.cuh", "tv_kernels.cuh", os.path.join("..", "..", "include", "embclip_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

@@ -20,6 +20,7 @@
 #include "gemm2sm.cuh"
 #include "bneck_tail.cuh"
 #include "tv_kernels.cuh"
+#include "bneck_tail_stream.cuh"
 
 using namespace embclip;
 
@@ -491,9 +492,58 @@ static int launch_bneck_tail(const TailOp& op, cudaStream_t st) {
   return op.n1 == 64 ? launch_tail_cfg<1, 64, true>(op, st) : launch_tail_cfg<1, 128, true>(op, st);
 }
 
+// bneck_tail_stream: identity-residual conv3 [M, K3] -> [M, N3] + the next conv1 [M, N3] -> [M, N1], weights streamed per quarter
+struct TailStreamOp {
+  const void* a = nullptr; const void* w3 = nullptr; const float* b3 = nullptr; const void* residual = nullptr; void* out = nullptr;
+  const void* w1 = nullptr; const float* b1 = nullptr; void* y1 = nullptr;
+  long long M = 0;
+  int k3 = 0, n3 = 0, n1 = 0, reverse = 0;
+};
+template <int K3C, int N1>
+static int launch_tail_stream_cfg(const TailStreamOp& op, cudaStream_t st) {
+  using Cfg = TailStreamCfg<K3C, N1>;
+  { const int rc_ = ensure_smem((const void*)bneck_tail_stream_kernel<K3C, N1>, Cfg::kSmemBytes); if (rc_) return rc_; }
+  const int M = (int)op.M;
+  CUtensorMap tmA, tmW3, tmW1, tmR, tmC;
+  int rc;
+  if ((rc = make_map_2d(&tmA, op.a, M, op.k3, op.k3, 64, 128))) return rc;
+  if ((rc = make_map_2d(&tmW3, op.w3, op.n3, op.k3, op.k3, 64, 64))) return rc;
+  if ((rc = make_map_2d(&tmW1, op.w1, N1, op.n3, op.n3, 64, N1))) return rc;
+  if ((rc = make_map_2d(&tmR, op.residual, M, op.n3, op.n3, 64, 128))) return rc;
+  if ((rc = make_map_2d(&tmC, op.out, M, op.n3, op.n3, 64, 128))) return rc;
+  TailStreamParams p;
+  memset(&p, 0, sizeof p);
+  p.num_tiles = (M + 127) / 128;
+  p.M = M; p.nq = op.n3 / 64; p.reverse = op.reverse;
+  p.bias3 = op.b3; p.bias1 = op.b1;
+  p.y1 = reinterpret_cast<__half*>(op.y1);
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  if (grid <= 0) return 0;
+  CUDA_TRY(launch_pdl(bneck_tail_stream_kernel<K3C, N1>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, tmA, tmW3, tmW1, tmR, tmC, p));
+  return 0;
+}
+static bool tail_stream_supported(int k3, int n3, int n1) { return k3 == 128 && n1 == 128 && n3 % 64 == 0 && n3 >= 256 && n3 <= 1024; }
+static int launch_bneck_tail_stream(const TailStreamOp& op, cudaStream_t st) {
+  if (op.M <= 0) return 0;
+  if (op.M > 0x7fffffffLL) return fail(EMBCLIP_EINVAL, "bneck_tail_stream: M too large");
+  if (!op.a || !op.w3 || !op.b3 || !op.residual || !op.out || !op.w1 || !op.b1 || !op.y1) return fail(EMBCLIP_EINVAL, "bneck_tail_stream: null argument");
+  if (!tail_stream_supported(op.k3, op.n3, op.n1))
+    return fail(EMBCLIP_EINVAL, "bneck_tail_stream: built for K3 = 128, N1 = 128, N3 a multiple of 64 in [256, 1024] (got %d, %d, %d)", op.k3, op.n1, op.n3);
+  return launch_tail_stream_cfg<2, 128>(op, st);
+}
+
 // =============================================================================================
 // primitive-op entry points
 // =============================================================================================
+extern "C" int embclip_bneck_tail_stream_f16(const void* y2, const void* w3, const float* b3, const void* residual, void* out, const void* w1,
+                                             const float* b1, void* y1, int64_t M, int K3, int N3, int n1, void* stream) {
+  EMBCLIP_TRACE();
+  TailStreamOp op;
+  op.a = y2; op.w3 = w3; op.b3 = b3; op.residual = residual; op.out = out; op.w1 = w1; op.b1 = b1; op.y1 = y1;
+  op.M = M; op.k3 = K3; op.n3 = N3; op.n1 = n1;
+  return launch_bneck_tail_stream(op, (cudaStream_t)stream);
+}
+
 extern "C" int embclip_gemm_f16(const void* a0, const void* a1, const void* w, const float* bias, const void* residual,
                                 void* out, int M, int N, int K0, int K1, int relu, int out_f32, void* stream) {
   EMBCLIP_TRACE();
@@ -682,6 +732,7 @@ struct Op {
   int force_bn = 0;
   int reverse = 0;               // tile walk direction (alternates layer to layer: snake order through L2)
   int fuse_next = -1;            // conv3 only: index of the next block's conv1 op, computed by the same launch (bneck_tail)
+  int fuse_stream = 0;           // ... by bneck_tail_stream (weights streamed: layer 2) instead of bneck_tail (weights resident: layer 1)
   int side = 0;                  // independent of the ops that follow it: launched on the handle's side stream (fork / join)
   int fused_away = 0;            // conv1 only: produced by the previous block's bneck_tail launch, not launched itself
 };
@@ -909,6 +960,19 @@ extern "C" int embclip_rn50_create(const embclip_rn50_cfg* cfg, embclip_rn50_t* 
       c3.fuse_next = (int)j;
       c1.fused_away = 1;
     }
+    // the same fusion where the weights must stream (layer 2 identity blocks: conv3 128 -> 512, next conv1 512 -> 128)
+    static const bool stream_fuse = getenv("EMBCLIP_NO_TAILSTREAM") == nullptr;
+    for (size_t i = 0; stream_fuse && i + 1 < m->ops.size(); ++i) {
+      Op& c3 = m->ops[i];
+      Op& c1 = m->ops[i + 1];
+      if (c3.kind != K_GEMM || c1.kind != K_GEMM || c3.rows_mode || c1.rows_mode || c3.head || c1.head || c3.fuse_next >= 0) continue;
+      if (c3.taps != 1 || c3.in1 >= 0 || c3.res < 0 || !c3.relu || c3.out_f32 || c3.grp_n) continue;
+      if (c1.taps != 1 || c1.in0 != c3.out || c1.in1 >= 0 || c1.res >= 0 || !c1.relu || c1.out_f32 || c1.grp_n || c1.c0 != c3.cout) continue;
+      if (!tail_stream_supported(c3.c0, c3.cout, c1.cout)) continue;
+      c3.fuse_next = (int)(i + 1);
+      c3.fuse_stream = 1;
+      c1.fused_away = 1;
+    }
   }
   static const bool snake = getenv("EMBCLIP_NO_SNAKE") == nullptr;
   int dir = 0;
@@ -989,6 +1053,14 @@ static int run_op(embclip_rn50* m, const Op& op, const std::vector<uint64_t>& of
         Conv3Op c{act_ptr(op.in0), param_ptr(op.wp), (const float*)param_ptr(op.bp), act_ptr(op.out), B, a.h, a.w, op.c0, op.cout, op.relu, op.pool};
         c.reverse = op.reverse;
         return launch_conv3x3_halo(c, st);
+      }
+      if (op.fuse_next >= 0 && op.fuse_stream) {
+        const Op& c1 = m->ops[op.fuse_next];
+        TailStreamOp t;
+        t.a = act_ptr(op.in0); t.w3 = param_ptr(op.wp); t.b3 = (const float*)param_ptr(op.bp); t.residual = act_ptr(op.res);
+        t.out = act_ptr(op.out); t.w1 = param_ptr(c1.wp); t.b1 = (const float*)param_ptr(c1.bp); t.y1 = act_ptr(c1.out);
+        t.M = (long long)B * a.h * a.w; t.k3 = op.c0; t.n3 = op.cout; t.n1 = c1.cout; t.reverse = op.reverse;
+        return launch_bneck_tail_stream(t, st);
       }
       if (op.fuse_next >= 0) {
         const Op& c1 = m->ops[op.fuse_next];

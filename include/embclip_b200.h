@@ -136,6 +136,11 @@ int embclip_gemm_grouped_f16(const void* a, int lda, const void* w, int ldw, int
  * BatchNorm + ReLU (+ AvgPool2d) of clip/model.py Bottleneck / ModifiedResNet stem. */
 int embclip_conv3x3_f16(const void* in, const void* w, const float* bias, void* out, int B, int H, int W,
                         int Cin, int Cout, int relu, int pool, void* stream);
+/* The same fusion with STREAMED weights, for stages whose conv3 / next-conv1 matrices do not fit shared memory (layer 2):
+ *   out[M,N3] = relu(y2[M,K3] . w3[N3,K3]^T + b3 + residual[M,N3]);   y1[M,n1] = relu(out . w1[n1,N3]^T + b1)
+ * Built for K3 = 128, n1 = 128, N3 a multiple of 64 in [256, 1024]. */
+int embclip_bneck_tail_stream_f16(const void* y2, const void* w3, const float* b3, const void* residual, void* out, const void* w1,
+                                  const float* b1, void* y1, int64_t M, int K3, int N3, int n1, void* stream);
 /* 2x2-window pools on NHWC fp16 [B,H,W,C] -> [B,H/2,W/2,C] (H, W even, C % 8 == 0).  mode 1: nn.AvgPool2d(2) (CLIP's
  * anti-aliasing pool); 2: x[:, ::2, ::2] (what a stride-2 1x1 conv reads); 3: nn.MaxPool2d(3, stride 2, padding 1)
  * (torchvision ResNet stem). */

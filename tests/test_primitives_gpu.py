@@ -264,6 +264,40 @@ def test_bneck_tail(lib, M, n1, down):
     _tail_case(lib, M, n1, down, seed=M % 97)
 
 
+def _tail_stream_case(lib, M, n3, seed=0):
+    """bneck_tail_stream: out = relu(y2 W3^T + b3 + res) rounded to fp16; y1 = relu(out W1^T + b1) from that fp16 tile."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    k3, n1 = 128, 128
+    y2 = rn(M, k3).relu().half()
+    w3 = (rn(n3, k3) * k3 ** -0.5).half()
+    b3 = rn(n3)
+    res = rn(M, n3).relu().half()
+    w1 = (rn(n1, n3) * n3 ** -0.5).half()
+    b1 = rn(n1)
+    out = torch.full((M, n3), float("nan"), device="cuda", dtype=torch.float16)
+    y1 = torch.full((M, n1), float("nan"), device="cuda", dtype=torch.float16)
+    _check(lib, lib.embclip_bneck_tail_stream_f16(_ptr(y2), _ptr(w3), _ptr(b3), _ptr(res), _ptr(out), _ptr(w1), _ptr(b1), _ptr(y1),
+                                                  M, k3, n3, n1, _stream()))
+    torch.cuda.synchronize()
+    ref_out = (y2.float() @ w3.float().t() + b3 + res.float()).relu()
+    _close(out, ref_out, f"bneck_tail_stream out M{M} n3 {n3}")
+    ref_y1 = (out.float() @ w1.float().t() + b1).relu()          # fed with the kernel's own fp16 x' (its rounding point)
+    _close(y1, ref_y1, f"bneck_tail_stream y1 M{M} n3 {n3}")
+
+
+@pytest.mark.parametrize("M,n3", [
+    (128, 512),                  # one tile, 8 quarters: both rings wrap, lagged conv1' flush
+    (128, 256),                  # 4 quarters (= ring depth)
+    (784, 512),                  # one layer-2 frame: partial last tile
+    (128 * 148 * 3 + 77, 512),   # three tiles per CTA + ragged tail: accumulator parity, A ring of two tiles
+    (128 * 148 * 2, 1024),       # 16 quarters per tile
+    (50, 512),                   # fewer rows than one tile
+])
+def test_bneck_tail_stream(lib, M, n3):
+    _tail_stream_case(lib, M, n3, seed=M % 97)
+
+
 def test_bneck_tail_rejects_bad_arguments(lib):
     z = torch.zeros(128, 256, device="cuda", dtype=torch.float16)
     b = torch.zeros(256, device="cuda")
