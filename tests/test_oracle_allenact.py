@@ -1,6 +1,7 @@
 """Pins the AllenAct-side oracle (oracle/allenact_models.py) and the in-tree probe restatement (oracle/probe.py)
 with independent checks available offline: torch.nn.GRU step semantics, a float64 closed form of GAE, a hand
 computation of the PPO loss, and train.py's documented quirks."""
+import pytest
 import torch
 import torch.nn.functional as F
 
@@ -138,3 +139,70 @@ def test_probe_matches_train_py_quirks():
     opt = torch.optim.Adam(fs.parameters(), lr=1e-3)                   # train.py:111-113, lr :137
     l0 = probe.probe_train_step(fs, opt, (torch.randn(B, 2048), torch.randint(0, 11, (B,))))
     assert l0 > 0
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# RolloutStorage bookkeeping on the CPU (the product class is pure torch indexing apart from compute_returns / feature
+# packing, which need the CUDA library): insert / recurrent_generator / after_update against oracle/allenact_storage.py with
+# a stub in place of the actor-critic (fp32 features, packed_features=False).
+# --------------------------------------------------------------------------------------------------------------------
+class _StubAC:
+    resnet_uuid, goal_uuid, hidden_size = "rgb_clip_resnet", "goal_object_type_ind", 16
+    resnet_tensor_shape = (8, 2, 2)
+
+    def __init__(self):
+        self.flat_params = torch.zeros(1)
+
+    def _recurrent_memory_specification(self):
+        return dict(rnn=((("layer", 1), ("sampler", None), ("hidden", self.hidden_size)), torch.float32))
+
+
+def test_rollout_storage_bookkeeping_cpu():
+    from embclip_b200.actor_critic import Memory
+    from embclip_b200.storage import RolloutStorage
+    from oracle.allenact_storage import RefRolloutStorage
+    T, N = 4, 5
+    ours = RolloutStorage(T, N, _StubAC(), packed_features=False, seed=7)
+    ref = RefRolloutStorage(T, N, hidden=16, seed=7)
+    g = torch.Generator().manual_seed(0)
+    for rollout in range(2):
+        for t in range(T):
+            obs = {"rgb_clip_resnet": torch.randn(N, 8, 2, 2, generator=g), "goal_object_type_ind": torch.randint(0, 12, (N,), generator=g)}
+            mem = torch.randn(1, N, 16, generator=g)
+            a, lp, v = torch.randint(0, 6, (N, 1), generator=g), torch.randn(N, 1, generator=g), torch.randn(N, 1, generator=g)
+            r, m = torch.randn(N, 1, generator=g), (torch.rand(N, 1, generator=g) > 0.2).float()
+            ref.insert(obs, mem, a, lp, v, r, m)
+            ours.insert(obs, Memory(rnn=(mem, 1)), a, lp, v, r, m)
+        assert ours.step == ref.step == 0
+        for k in ("actions", "prev_actions", "masks", "action_log_probs", "value_preds", "rewards"):
+            assert torch.equal(getattr(ours, k), getattr(ref, k)), k
+        assert torch.equal(ours.memory.tensor("rnn"), ref.memory["rnn"])
+        ref.compute_returns(torch.zeros(N, 1), True, 0.99, 0.95)
+        ours.returns.copy_(ref.returns)                      # (compute_returns is the CUDA kernel: covered by tests/test_storage.py)
+        adv = ref.returns[:-1] - ref.value_preds[:-1]
+        for nmb in (1, 2, 5):
+            ob = list(ours.recurrent_generator(adv, adv.mean(), adv.std(), nmb))
+            rb = list(ref.recurrent_generator(adv, adv.mean(), adv.std(), nmb))
+            assert [b["samplers"] for b in ob] == [b["samplers"] for b in rb]
+            for o, r_ in zip(ob, rb):
+                for k in ("actions", "prev_actions", "values", "returns", "masks", "old_action_log_probs", "adv_targ", "norm_adv_targ"):
+                    assert torch.equal(o[k], r_[k]), k
+                assert torch.equal(o["memory"].tensor("rnn"), r_["memory"]["rnn"])
+                for k in o["observations"]:
+                    assert torch.equal(o["observations"][k], r_["observations"][k]), k
+        ours.after_update()
+        ref.after_update()
+        assert torch.equal(ours.masks[0], ref.masks[0]) and torch.equal(ours.prev_actions[0], ref.prev_actions[0])
+        assert torch.equal(ours.observations["rgb_clip_resnet"][0], ref.observations["rgb_clip_resnet"][0])
+    with pytest.raises(RuntimeError):
+        ours.to("cpu").compute_returns(torch.zeros(N, 1))    # no CPU path for the arithmetic
+    with pytest.raises(AssertionError):
+        list(ours.recurrent_generator(adv, adv.mean(), adv.std(), N + 1))
+
+
+def test_linear_decay_matches_upstream_definition():
+    from embclip_b200.actor_critic import LinearDecay
+    ld = LinearDecay(steps=1000, startp=1.0, endp=0.0)
+    assert ld(0) == 1.0 and ld(250) == 0.75 and ld(1000) == 0.0 and ld(5000) == 0.0 and ld(-3) == 1.0
+    ld2 = LinearDecay(steps=10, startp=0.5, endp=0.1)
+    assert abs(ld2(5) - 0.3) < 1e-12
