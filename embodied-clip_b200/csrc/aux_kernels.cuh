@@ -294,12 +294,25 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
 constexpr int kStemRowsStages = 3;
 template <typename TIn>
 constexpr int stem_rows_stage_bytes(int R) { return ((R * 3 * int(sizeof(TIn)) + 127) / 128 * 128) * 3; }
+// n / d for n < 2^31 without the integer-division sequence (which goes through the 1/8-rate conversion unit)
+struct FastDiv { uint32_t d, m, l; };
+inline FastDiv make_fastdiv(uint32_t d) {
+  uint32_t l = 0;
+  while ((1u << l) < d) ++l;
+  const uint64_t m = ((uint64_t(1) << 32) * ((uint64_t(1) << l) - d)) / d + 1;
+  return FastDiv{d, uint32_t(m), l};
+}
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv& f) { return (__umulhi(f.m, n) + n) >> f.l; }
 // COUT = 32 (width 64) or 64 (width 96: 48 real channels + 16 zero-weight pad channels).  An output row longer than 128
 // pixels (R = 384) is cut into equal segments; every segment's tile loads the three full input rows.
-template <typename TIn, int COUT>
+// Software-pipelined over tiles: two im2col buffers [128][hi(32) | lo(32)] and two TMEM accumulators, so the gather of tile
+// n+1 runs while the UMMAs of tile n are in flight and the MMA -> commit -> mbarrier latency is off the per-tile chain.
+// The six UMMAs per tile are hi x w_hi, lo x w_hi (k-block 0 of the weights) and hi x w_lo (the first half of k-block 1,
+// reading the SAME hi columns again: no second copy of hi in shared memory).
+template <typename TIn, int COUT, bool kFastU8 = false>
 __global__ void __launch_bounds__(128)
 stem_conv1_rows_kernel(const TIn* __restrict__ x, const __half* __restrict__ wtc, const float* __restrict__ bias,
-                       __half* __restrict__ y, int B, int R, int segs, const StemNorm norm) {
+                       __half* __restrict__ y, int B, int R, const FastDiv dsegs, const FastDiv dro, const StemNorm norm) {
   constexpr int S = kStemRowsStages;
   constexpr int kWBytes = 2 * COUT * 128;
   constexpr bool kRaw = sizeof(TIn) == 1;
@@ -309,14 +322,14 @@ stem_conv1_rows_kernel(const TIn* __restrict__ x, const __half* __restrict__ wtc
   const uint32_t row_bytes = uint32_t(R) * 3u * uint32_t(sizeof(TIn));
   const uint32_t row_pitch = (row_bytes + 127u) & ~127u;
   const uint32_t stage_bytes = row_pitch * 3u;
-  const uint32_t sA = base;                        // 2 k-blocks x [128 rows][128 B]
-  const uint32_t sW = base + 32768;                // 2 k-blocks x [32 rows][128 B]
+  const uint32_t sA = base;                        // 2 buffers x [128 rows][128 B]
+  const uint32_t sW = base + 32768;                // 2 k-blocks x [COUT rows][128 B]
   const uint32_t sIn = sW + kWBytes;               // S stages x 3 rows
-  const uint32_t sBar = sIn + S * stage_bytes;     // S full barriers, 1 MMA barrier, TMEM slot
-  const uint32_t bar_mma = sBar + 8 * S, tmem_slot = bar_mma + 8;
+  const uint32_t sBar = sIn + S * stage_bytes;     // S full barriers, 2 MMA barriers, TMEM slot
+  const uint32_t bar_mma = sBar + 8 * S, tmem_slot = bar_mma + 16;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int Ro = R / 2;
-  const int seg_len = Ro / segs;                   // <= 128 output pixels per tile
+  const uint32_t Ro = dro.d, segs = dsegs.d;
+  const int seg_len = int(Ro / segs);              // <= 128 output pixels per tile
 
   for (int i = tid; i < COUT * 16; i += 128) {     // weights -> swizzled K-major tiles (as in stem_conv1_tc_kernel)
     const int n = i >> 4, piece = i & 15;
@@ -328,9 +341,10 @@ stem_conv1_rows_kernel(const TIn* __restrict__ x, const __half* __restrict__ wtc
   if (tid == 0) {
     for (int s2 = 0; s2 < S; ++s2) mbar_init(sBar + 8 * s2, 1);
     mbar_init(bar_mma, 1);
+    mbar_init(bar_mma + 8, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<COUT>(tmem_slot);
+  if (warp == 0) tmem_alloc<2 * COUT>(tmem_slot);
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
@@ -339,35 +353,96 @@ stem_conv1_rows_kernel(const TIn* __restrict__ x, const __half* __restrict__ wtc
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   griddep_wait();
 
-  const long long num_tiles = (long long)B * Ro * segs;
+  const uint32_t num_tiles = uint32_t(B) * Ro * segs;              // < 2^31 (checked by the launcher)
   float bv[COUT];
 #pragma unroll
   for (int c = 0; c < COUT; ++c) bv[c] = __ldg(bias + c);
+  __half2 fk[3], fsh[3], fsl[3], fcl[3];           // kFastU8: per pair phase (channels (0,1), (2,0), (1,2)) constants
+  if constexpr (kFastU8) {
+    float k1[3], s_h[3], s_l[3], c_l[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float s = norm.scale[c], m = -norm.offset[c] / s, mr = rintf(m);
+      k1[c] = 1024.f + mr;                         // exact in fp16 for |mr| <= 1023 (checked by the launcher)
+      s_h[c] = __half2float(__float2half_rn(s));
+      s_l[c] = s - s_h[c];
+      c_l[c] = -s * (m - mr);
+    }
+#pragma unroll
+    for (int ph = 0; ph < 3; ++ph) {
+      const int ca = (2 * ph) % 3, cb = (2 * ph + 1) % 3;
+      fk[ph] = __floats2half2_rn(k1[ca], k1[cb]);
+      fsh[ph] = __floats2half2_rn(s_h[ca], s_h[cb]);
+      fsl[ph] = __floats2half2_rn(s_l[ca], s_l[cb]);
+      fcl[ph] = __floats2half2_rn(c_l[ca], c_l[cb]);
+    }
+  }
 
   // tile -> (image, output row); input rows 2*oh-1 .. 2*oh+1 (row -1 is the zero pad: not loaded, not read)
-  auto issue = [&](long long tile, int stage) {
-    const long long rowi = tile / segs;
-    const int oh = int(rowi % Ro);
-    const long long b = rowi / Ro;
+  auto issue = [&](uint32_t tile, int stage) {
+    const uint32_t rowi = fast_div(tile, dsegs);                       // = b * Ro + oh
+    const uint32_t oh = rowi - fast_div(rowi, dro) * Ro;
     const int first = oh == 0 ? 1 : 0;
     const uint32_t bar = sBar + 8 * stage;
     mbar_arrive_expect_tx(bar, row_bytes * uint32_t(3 - first));
     for (int kh = first; kh < 3; ++kh)
-      bulk_load_1d(sIn + stage * stage_bytes + kh * row_pitch, x + ((size_t)b * R + (2 * oh - 1 + kh)) * R * 3, row_bytes, bar);
+      bulk_load_1d(sIn + stage * stage_bytes + kh * row_pitch, x + ((size_t)rowi * 2 + size_t(kh) - 1) * R * 3, row_bytes, bar);   // R = 2 Ro: input row b R + 2 oh - 1 + kh
   };
-  if (tid == 0) {
-    long long t = blockIdx.x;
-    for (int s2 = 0; s2 < S && t < num_tiles; ++s2, t += gridDim.x) issue(t, s2);
-  }
-  int stage = 0;
-  uint32_t in_phase = 0, mma_phase = 0;
-  for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int oh = int((tile / segs) % Ro);
-    const int ow = int(tile % segs) * seg_len + tid;                  // this thread's output column
-    mbar_wait(sBar + 8 * stage, in_phase);
-    if (tid < seg_len) {
+  // im2col rows of one tile (thread <-> output pixel) -> A buffer `buf`
+  auto gather = [&](uint32_t tile, int stage, int buf) {
+    const uint32_t rowi = fast_div(tile, dsegs);
+    const int oh = int(rowi - fast_div(rowi, dro) * Ro);
+    const int ow = int(tile - rowi * segs) * seg_len + tid;           // this thread's output column
+    if (tid >= seg_len) return;
+    uint32_t hi[16], lo[16];
+    if constexpr (kFastU8) {
+      // Raw uint8 frames without the conversion unit (I2F / F2F issue at 1/8 rate and bounded this kernel): bytes become
+      // fp16 through the exponent trick 0x6400 | b = 1024 + b, and  v = s (b - m)  is split into fp16 halves in half2
+      // arithmetic:  d = b - round(m) exact,  hi = fl(s_h d),  lo = fma(s_h, d, -hi) + fma(s_l, d, -s (m - round(m))).
+      const uint32_t q = uint32_t(6 * ow - 3);                         // first byte of the 9-byte run (row-relative)
+      const uint32_t sh = (q & 3u) * 8u;
+      uint32_t xr[3][3];
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const uint32_t a = sIn + stage * stage_bytes + kh * row_pitch + (q & ~3u);   // ow == 0 reads 4 B before the row: masked
+        uint32_t w0, w1, w2;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(a));
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(a + 4u));
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w2) : "r"(a + 8u));
+        xr[kh][0] = __funnelshift_r(w0, w1, sh);
+        xr[kh][1] = __funnelshift_r(w1, w2, sh);
+        xr[kh][2] = w2 >> sh;
+      }
+      uint32_t sb[7];                                                  // the 27 bytes as one stream: pair i = bytes 2i, 2i+1
+      sb[0] = xr[0][0];
+      sb[1] = xr[0][1];
+      sb[2] = __byte_perm(xr[0][2], xr[1][0], 0x6540);
+      sb[3] = __byte_perm(xr[1][0], xr[1][1], 0x6543);
+      sb[4] = __byte_perm(__byte_perm(xr[1][1], xr[1][2], 0x0043), xr[2][0], 0x5410);
+      sb[5] = __byte_perm(xr[2][0], xr[2][1], 0x5432);
+      sb[6] = __byte_perm(xr[2][1], xr[2][2], 0x0432);
+      const uint32_t mrow = oh > 0 ? 0xffffffffu : 0u, mcol = ow > 0 ? 0xffffffffu : 0u;
+#pragma unroll
+      for (int i = 0; i < 14; ++i) {
+        const uint32_t raw = __byte_perm(sb[i >> 1], 0x64646464u, (i & 1) ? 0x4342 : 0x4140);
+        const __half2 d = __hsub2(*reinterpret_cast<const __half2*>(&raw), fk[i % 3]);
+        const __half2 h = __hmul2(fsh[i % 3], d);
+        const __half2 l = __hadd2(__hfma2(fsh[i % 3], d, __hneg2(h)), __hfma2(fsl[i % 3], d, fcl[i % 3]));
+        uint32_t mk = 0u;                                              // zero padding taps: row -1, column -1, element 27
+#pragma unroll
+        for (int e2 = 0; e2 < 2; ++e2) {
+          const int e = 2 * i + e2, kh = e / 9, j = e % 9;
+          uint32_t m1 = e < 27 ? 0xffffu : 0u;
+          if (kh == 0) m1 &= mrow;
+          if (j < 3) m1 &= mcol;
+          mk |= m1 << (16 * e2);
+        }
+        hi[i] = *reinterpret_cast<const uint32_t*>(&h) & mk;
+        lo[i] = *reinterpret_cast<const uint32_t*>(&l) & mk;
+      }
+      hi[14] = hi[15] = lo[14] = lo[15] = 0u;
+    } else {
       const uint8_t* st = gen + (sIn - base) + stage * stage_bytes;
-      uint32_t hi[16], lo[16];
       float v[28];
       v[27] = 0.f;
 #pragma unroll
@@ -385,50 +460,44 @@ stem_conv1_rows_kernel(const TIn* __restrict__ x, const __half* __restrict__ wtc
         }
       }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < 16; ++i) {                                   // pairwise F2FP packs (scalar F2F issues at 1/8 rate)
         const float a = i < 14 ? v[2 * i] : 0.f, b2 = i < 14 ? v[2 * i + 1] : 0.f;
-        const __half ha = __float2half_rn(a), hb = __float2half_rn(b2);
-        const __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b2 - __half2float(hb));
-        hi[i] = uint32_t(__half_as_ushort(ha)) | (uint32_t(__half_as_ushort(hb)) << 16);
-        lo[i] = uint32_t(__half_as_ushort(la)) | (uint32_t(__half_as_ushort(lb)) << 16);
-      }
-#pragma unroll
-      for (int piece = 0; piece < 8; ++piece) {    // k-block 0: [hi | lo]
-        const uint32_t* src = piece < 4 ? hi + 4 * piece : lo + 4 * (piece - 4);
-        const uint32_t a = sA + swizzle_off<128>(uint32_t(tid), uint32_t(piece));
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(src[0]), "r"(src[1]), "r"(src[2]), "r"(src[3]) : "memory");
-      }
-#pragma unroll
-      for (int piece = 0; piece < 4; ++piece) {    // k-block 1: [hi | 0]  (the zero half was written once above)
-        const uint32_t a = sA + 16384 + swizzle_off<128>(uint32_t(tid), uint32_t(piece));
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hi[4 * piece]), "r"(hi[4 * piece + 1]), "r"(hi[4 * piece + 2]), "r"(hi[4 * piece + 3]) : "memory");
+        const __half2 h = __floats2half2_rn(a, b2);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(a - hf.x, b2 - hf.y);
+        hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[i] = *reinterpret_cast<const uint32_t*>(&l);
       }
     }
-    fence_proxy_async_smem();
-    tcgen05_fence_before();
-    __syncthreads();                               // A rows written, input stage fully read, previous accumulator drained
-    if (tid == 0) {
-      tcgen05_fence_after();
-      constexpr uint32_t idesc = make_idesc_f16_f32(128, COUT);
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma_f16_ss(tmem_base, make_kmajor_desc<128>(sA + uint32_t(k >> 2) * 16384u + 32u * uint32_t(k & 3)),
-                    make_kmajor_desc<128>(sW + uint32_t(k >> 2) * uint32_t(COUT * 128) + 32u * uint32_t(k & 3)), idesc, k != 0);
-      umma_commit(bar_mma);
-      const long long nxt = tile + (long long)S * gridDim.x;      // refill the stage just consumed
-      if (nxt < num_tiles) issue(nxt, stage);
+    for (int piece = 0; piece < 8; ++piece) {      // [hi | lo]
+      const uint32_t* src = piece < 4 ? hi + 4 * piece : lo + 4 * (piece - 4);
+      const uint32_t a = sA + uint32_t(buf) * 16384u + swizzle_off<128>(uint32_t(tid), uint32_t(piece));
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(src[0]), "r"(src[1]), "r"(src[2]), "r"(src[3]) : "memory");
     }
-    __syncwarp();
-    mbar_wait(bar_mma, mma_phase);
-    mma_phase ^= 1u;
+  };
+  auto mma = [&](int buf) {                        // one thread
     tcgen05_fence_after();
+    constexpr uint32_t idesc = make_idesc_f16_f32(128, COUT);
+    const uint32_t a0 = sA + uint32_t(buf) * 16384u, acc = tmem_base + uint32_t(buf * COUT);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)                    // hi x w_hi, lo x w_hi
+      umma_f16_ss(acc, make_kmajor_desc<128>(a0 + 32u * uint32_t(k)), make_kmajor_desc<128>(sW + 32u * uint32_t(k)), idesc, k != 0);
+#pragma unroll
+    for (int k = 0; k < 2; ++k)                    // hi x w_lo
+      umma_f16_ss(acc, make_kmajor_desc<128>(a0 + 32u * uint32_t(k)), make_kmajor_desc<128>(sW + uint32_t(COUT * 128) + 32u * uint32_t(k)), idesc, 1);
+    umma_commit(bar_mma + 8u * uint32_t(buf));
+  };
+  auto epilogue = [&](uint32_t tile, int buf) {
+    const uint32_t rowi = fast_div(tile, dsegs);
+    const int ow = int(tile - rowi * segs) * seg_len + tid;
 #pragma unroll
     for (int c0 = 0; c0 < COUT; c0 += 32) {
       uint32_t acc[32];
-      tmem_ld_32x32b<32>(tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(c0), acc);
+      tmem_ld_32x32b<32>(tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(buf * COUT + c0), acc);
       tmem_ld_wait();
       if (tid < seg_len) {
-        uint4* out = reinterpret_cast<uint4*>(y + ((size_t)(tile / segs) * Ro + ow) * COUT + c0);
+        uint4* out = reinterpret_cast<uint4*>(y + ((size_t)rowi * Ro + ow) * COUT + c0);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 o;
@@ -440,13 +509,58 @@ stem_conv1_rows_kernel(const TIn* __restrict__ x, const __half* __restrict__ wtc
         }
       }
     }
-    if (++stage == S) { stage = 0; in_phase ^= 1u; }
+  };
+
+  if (tid == 0) {
+    uint32_t t = blockIdx.x;
+    for (int s2 = 0; s2 < S && t < num_tiles; ++s2, t += gridDim.x) issue(t, s2);
+  }
+  int stage = 0;
+  uint32_t in_phase = 0, mma_phase = 0;            // mma_phase: one bit per accumulator
+  uint32_t tile = blockIdx.x;
+  if (tile < num_tiles) {                          // prologue: tile 0's rows and UMMAs
+    mbar_wait(sBar, 0);
+    gather(tile, 0, 0);
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      mma(0);
+      const uint64_t nxt = uint64_t(tile) + uint64_t(S) * gridDim.x;
+      if (nxt < num_tiles) issue(uint32_t(nxt), 0);
+    }
+    __syncwarp();
+    stage = 1;
+  }
+  for (int n = 0; tile < num_tiles; tile += gridDim.x, ++n) {
+    const int buf = n & 1;
+    const uint64_t nt = uint64_t(tile) + gridDim.x;
+    const bool more = nt < num_tiles;
+    if (more) {
+      mbar_wait(sBar + 8 * stage, in_phase);
+      gather(uint32_t(nt), stage, buf ^ 1);
+    }
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();                               // next A written, its input stage fully read, accumulator buf^1 drained
+    if (more) {
+      if (tid == 0) {
+        mma(buf ^ 1);
+        const uint64_t nxt = nt + uint64_t(S) * gridDim.x;            // refill the stage just consumed
+        if (nxt < num_tiles) issue(uint32_t(nxt), stage);
+      }
+      __syncwarp();
+      if (++stage == S) { stage = 0; in_phase ^= 1u; }
+    }
+    mbar_wait(bar_mma + 8u * uint32_t(buf), (mma_phase >> buf) & 1u);
+    mma_phase ^= 1u << buf;
+    tcgen05_fence_after();
+    epilogue(tile, buf);
   }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 0) {
     tcgen05_fence_after();
-    tmem_dealloc<COUT>(tmem_base);
+    tmem_dealloc<2 * COUT>(tmem_base);
   }
 }
 

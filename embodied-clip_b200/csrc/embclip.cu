@@ -38,7 +38,7 @@ int embclip::fail(int code, const char* fmt, ...) {
   return code;
 }
 extern "C" const char* embclip_last_error(void) { return g_err.c_str(); }
-extern "C" int embclip_abi_version(void) { return 5; }
+extern "C" int embclip_abi_version(void) { return 6; }
 
 // =============================================================================================
 // TMA descriptors (driver entry point resolved at run time: the library links only against cudart)
@@ -630,22 +630,24 @@ extern "C" int embclip_avgpool2_f16(const void* in, void* out, int B, int H, int
 }
 
 // tensor-core version (hi/lo-split im2col rows); wtc = fp16 [32][128]
-template <typename TIn, int COUT>
+template <typename TIn, int COUT, bool kFast = false>
 static int launch_stem_rows(const void* x, const void* wtc, const float* b, void* y, int B, int R, const StemNorm& nm, cudaStream_t st) {
   const int Ro = R / 2;
   int segs = (Ro + 127) / 128;
   while (Ro % segs) ++segs;                                  // equal segments of <= 128 output pixels
   const size_t smem = 1024 + 32768 + 2 * COUT * 128 + size_t(kStemRowsStages) * stem_rows_stage_bytes<TIn>(R) + 64;
   if (smem > 227u * 1024u) return fail(EMBCLIP_EINVAL, "stem: resolution %d does not fit the row ring", R);
-  { const int rc_ = ensure_smem((const void*)stem_conv1_rows_kernel<TIn, COUT>, (size_t)(smem)); if (rc_) return rc_; }
+  { const int rc_ = ensure_smem((const void*)stem_conv1_rows_kernel<TIn, COUT, kFast>, (size_t)(smem)); if (rc_) return rc_; }
   const long long tiles = (long long)B * Ro * segs;
+  if (tiles >= (1ll << 31)) return fail(EMBCLIP_EINVAL, "stem: batch %d too large for one launch", B);
   int per_sm = int((227u * 1024u) / smem);
   if (per_sm > 4) per_sm = 4;
   long long g = (long long)num_sms() * per_sm;
   if (g > tiles) g = tiles;
   if (g <= 0) return 0;
-  CUDA_TRY(launch_pdl(stem_conv1_rows_kernel<TIn, COUT>, dim3((unsigned)g), dim3(128), smem, st, reinterpret_cast<const TIn*>(x),
-                      reinterpret_cast<const __half*>(wtc), b, reinterpret_cast<__half*>(y), B, R, segs, nm));
+  CUDA_TRY(launch_pdl(stem_conv1_rows_kernel<TIn, COUT, kFast>, dim3((unsigned)g), dim3(128), smem, st, reinterpret_cast<const TIn*>(x),
+                      reinterpret_cast<const __half*>(wtc), b, reinterpret_cast<__half*>(y), B, R, make_fastdiv((uint32_t)segs),
+                      make_fastdiv((uint32_t)Ro), nm));
   return 0;
 }
 
@@ -657,11 +659,20 @@ static int launch_stem_conv1_tc(const void* x, int x_u8, const float* norm6, con
   static const bool gather_only = getenv("EMBCLIP_STEM_GATHER") != nullptr;
   const size_t esz = x_u8 ? 1 : 4;
   const bool rows_ok = (size_t(R) * 3 * esz) % 16 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0;
+  // raw uint8 frames: the half2 split (no conversion-unit instructions) needs 1024 + round(255 mean) exact in fp16
+  static const bool no_fast = getenv("EMBCLIP_STEM_NO_FAST_U8") != nullptr;
+  bool fast = x_u8 && !no_fast;
+  for (int c = 0; c < 3 && fast; ++c) {
+    const float m = -nm.offset[c] / nm.scale[c];
+    fast = std::isfinite(m) && std::fabs(m) <= 1000.f && std::fabs(nm.scale[c]) >= 1e-3f && std::fabs(nm.scale[c]) <= 16.f;
+  }
   if (Cout == 64) {
     if (!rows_ok) return fail(EMBCLIP_EINVAL, "stem: the 64-channel stem needs 16-B aligned frame rows (resolution %d)", R);
+    if (fast) return launch_stem_rows<uint8_t, 64, true>(x, wtc, b, y, B, R, nm, st);
     return x_u8 ? launch_stem_rows<uint8_t, 64>(x, wtc, b, y, B, R, nm, st) : launch_stem_rows<float, 64>(x, wtc, b, y, B, R, nm, st);
   }
   if (Cout != 32) return fail(EMBCLIP_EINVAL, "stem conv1: Cout %d not built (32 or 64)", Cout);
+  if (!gather_only && rows_ok && fast) return launch_stem_rows<uint8_t, 32, true>(x, wtc, b, y, B, R, nm, st);
   if (!gather_only && rows_ok)
     return x_u8 ? launch_stem_rows<uint8_t, 32>(x, wtc, b, y, B, R, nm, st) : launch_stem_rows<float, 32>(x, wtc, b, y, B, R, nm, st);
   { const int rc_ = ensure_smem((const void*)stem_conv1_tc_kernel<float>, (size_t)(kStemTcSmem)); if (rc_) return rc_; }
@@ -1234,6 +1245,21 @@ extern "C" int embclip_rn50_profile(embclip_rn50_t h, const float* frames_nhwc, 
   EMBCLIP_TRACE();
   if (!op_ms || max_ops <= 0) return fail(EMBCLIP_EINVAL, "profile: need op_ms buffer");
   const FramesIn in{frames_nhwc, 0, {1, 1, 1, 0, 0, 0}};
+  return forward_impl(h, in, batch, out_trunk_nchw, out_avgpool, out_attnpool, workspace, workspace_bytes,
+                      (cudaStream_t)stream, op_ms, names, max_ops);
+}
+extern "C" int embclip_rn50_profile_u8(embclip_rn50_t h, const uint8_t* frames_nhwc_u8, const float* mean3, const float* std3, int batch,
+                                       float* out_trunk_nchw, float* out_avgpool, float* out_attnpool, void* workspace,
+                                       uint64_t workspace_bytes, void* stream, float* op_ms, char* names, int max_ops) {
+  EMBCLIP_TRACE();
+  if (!op_ms || max_ops <= 0) return fail(EMBCLIP_EINVAL, "profile: need op_ms buffer");
+  if (!mean3 || !std3) return fail(EMBCLIP_EINVAL, "profile_u8: mean / std required");
+  FramesIn in{frames_nhwc_u8, 1, {0, 0, 0, 0, 0, 0}};
+  for (int c = 0; c < 3; ++c) {
+    if (!(std3[c] > 0.f)) return fail(EMBCLIP_EINVAL, "profile_u8: std must be positive");
+    in.norm[c] = 1.f / (255.f * std3[c]);
+    in.norm[3 + c] = -mean3[c] / std3[c];
+  }
   return forward_impl(h, in, batch, out_trunk_nchw, out_avgpool, out_attnpool, workspace, workspace_bytes,
                       (cudaStream_t)stream, op_ms, names, max_ops);
 }

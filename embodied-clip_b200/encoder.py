@@ -189,9 +189,13 @@ class ClipRN50Encoder:
         ptr = lambda k: outs[k].data_ptr() if k in outs else None
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            n = _lib.check(self.lib.embclip_rn50_profile(self._h, frames.data_ptr(), B, ptr("trunk"), ptr("avgpool"),
-                                                         ptr("attnpool"), ws.data_ptr(), ws.numel(), stream,
-                                                         C.cast(ms, C.c_void_p), C.cast(names, C.c_void_p), max_ops))
+            tail = (ptr("trunk"), ptr("avgpool"), ptr("attnpool"), ws.data_ptr(), ws.numel(), stream,
+                    C.cast(ms, C.c_void_p), C.cast(names, C.c_void_p), max_ops)
+            if frames.dtype == torch.uint8:
+                mean, std = (C.c_float * 3)(*self.CLIP_RGB_MEANS), (C.c_float * 3)(*self.CLIP_RGB_STDS)
+                n = _lib.check(self.lib.embclip_rn50_profile_u8(self._h, frames.data_ptr(), mean, std, B, *tail))
+            else:
+                n = _lib.check(self.lib.embclip_rn50_profile(self._h, frames.data_ptr(), B, *tail))
         return [(names.raw[i * 64:(i + 1) * 64].split(b"\0")[0].decode(), float(ms[i])) for i in range(n)]
 
     def __del__(self):

@@ -106,6 +106,10 @@ int embclip_rn50_act_info(embclip_rn50_t h, int batch, int index, embclip_act_in
 int embclip_rn50_profile(embclip_rn50_t h, const float* frames_nhwc, int batch, float* out_trunk_nchw,
                          float* out_avgpool, float* out_attnpool, void* workspace, uint64_t workspace_bytes,
                          void* stream, float* op_ms, char* names, int max_ops);
+/* The same for raw uint8 frames (arguments as embclip_rn50_forward_u8). */
+int embclip_rn50_profile_u8(embclip_rn50_t h, const uint8_t* frames_nhwc_u8, const float* mean3, const float* std3, int batch,
+                            float* out_trunk_nchw, float* out_avgpool, float* out_attnpool, void* workspace,
+                            uint64_t workspace_bytes, void* stream, float* op_ms, char* names, int max_ops);
 /* fp16 copy of the trunk output of the LAST forward on this workspace, as NHWC pixel rows [batch * fres * fres, embed] -- the
  * layout the actor-critic path consumes (embclip_ac_pack_features output), bit-identical to packing the fp32 NCHW trunk
  * output.  Lets a rollout loop skip the fp32 NCHW round trip. */

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     for s in header_symbols():
         assert hasattr(lib, s), f"{s} declared in the header but not exported"
     from embclip_b200 import _lib
-    assert _lib.load().embclip_abi_version() == 5
+    assert _lib.load().embclip_abi_version() == 6
 
 
 def test_sass_is_blackwell_native(built_lib):

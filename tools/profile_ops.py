@@ -17,6 +17,8 @@ def main():
     tag = sys.argv[2] if len(sys.argv) > 2 else "ops"
     enc = ClipRN50Encoder(synthetic_rn50_state_dict(), "cuda:0")
     frames = torch.randn(B, 224, 224, 3, device="cuda")
+    if os.environ.get("PROFILE_U8"):
+        frames = torch.randint(0, 256, (B, 224, 224, 3), device="cuda", dtype=torch.uint8)
     heads = ("trunk", "avgpool", "attnpool")
     for _ in range(3):
         enc(frames, heads)
