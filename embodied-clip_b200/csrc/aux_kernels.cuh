@@ -978,6 +978,30 @@ nhwc_to_nchw_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int 
   }
 }
 
+// The same with 128 channels of one image per block: the out slab [128][P] (P * 512 B, contiguous and 16-B aligned) is
+// assembled in shared memory in its final order and leaves as float4 rows; loads are 128-B segments (8 lanes x float4) of four
+// pixels per warp, scattered conflict-free (bank = 4 (lane & 7) + k P + pixel: P odd or not, the 8 x 4 lanes hit 32 banks when
+// P is odd; P even costs a 2-way conflict).  Needs C % 128 == 0.
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_f32_wide_kernel(const float* __restrict__ x, float* __restrict__ y, int P, int C) {
+  extern __shared__ float tile[];   // [128][P]
+  const int b = blockIdx.y, c0 = blockIdx.x * 128;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c4 = (warp & 3) * 8 + (lane & 7);       // float4 index within the 128 channels
+  griddep_wait();
+  const float4* xb = reinterpret_cast<const float4*>(x + (size_t)b * P * C + c0) + c4;
+  const int cq = C / 4;
+  for (int p = 4 * (warp >> 2) + (lane >> 3); p < P; p += 8) {
+    const float4 v = __ldg(xb + (size_t)p * cq);
+    float* t = tile + (4 * c4) * P + p;
+    t[0] = v.x; t[P] = v.y; t[2 * P] = v.z; t[3 * P] = v.w;
+  }
+  __syncthreads();
+  float4* yb = reinterpret_cast<float4*>(y + ((size_t)b * C + c0) * P);
+  const float4* t4 = reinterpret_cast<const float4*>(tile);
+  for (int i = threadIdx.x; i < 32 * P; i += 256) yb[i] = t4[i];
+}
+
 // ------------------------------------------------------------------------------------------------
 // fp32 -> fp16 copy (8 elements per thread): the trunk output as the actor-critic path's pixel rows.
 // ------------------------------------------------------------------------------------------------

@@ -20,7 +20,16 @@
 // middle of the NEXT tile's quarters, when the MMAs have long retired.  W3 and W1' stay resident in shared memory.
 //
 // Warp roles (384 threads): warp 0 = A producer (+ weights once), warp 1 = TMEM owner + MMA issuer, warp 2 = R-thread
-// (residual loads, x' stores), warp 3 idle, warps 4..11 = epilogue (two per TMEM lane quarter, 32 columns each).
+// (residual loads, x' stores), warp 3 idle (kPool: the pool warp), warps 4..11 = epilogue (two per TMEM lane quarter, 32
+// columns each).
+//
+// kPool (the LAST block of a stage, whose x' is read only by the next stage's conv1 and by its downsample branch's
+// AvgPool2d(2) / stride-2 subsample): a tile is two image rows (2 W <= 128 pixels; the UMMA still runs 128 rows, the spare ones
+// are ignored) brought in WINDOW-MAJOR order by 5-D tensor maps (dims: channel, dx, dy, window, row pair), so the four pixels
+// of a 2x2 window are four consecutive tile rows = TMEM lanes of ONE epilogue warp.  After staging its rows the warp reduces
+// its eight windows straight from shared memory and writes the POOLED tensor; x' itself never goes to HBM: at 56x56x256 that
+// is one 411 MB write, one 411 MB read and the pool launch saved (clip/model.py Bottleneck.downsample [UPSTREAM]:
+// AvgPool2d(stride) -> conv1x1 -> bn on the block input).
 #pragma once
 #include "ptx.cuh"
 
@@ -30,6 +39,10 @@ struct TailParams {
   int num_tiles;             // ceil(M / 128)
   int M;
   int reverse;
+  int tile_rows;             // 128, or 2 W with kPool
+  int pool_w;                // kPool: W / 2 pooled pixels per tile
+  int pool_mode;             // kPool: 1 = average of the 2x2 window, 2 = its top-left pixel
+  __half* pool_out;          // kPool: [M / 4, 256]
   const float* bias3;        // [256]
   const float* bias1;        // [N1]
   __half* y1;                // [M, N1]
@@ -44,7 +57,7 @@ struct TailCfg {
   static constexpr int kAStages = 4;
   static constexpr int kCQuarter = 128 * 128;
   static constexpr int kBiasBytes = (kN3 + N1) * 4;
-  static constexpr int kBarBytes = 256;
+  static constexpr int kBarBytes = 320;
   static constexpr int kThreads = 384;
   static constexpr int kEpiWarps = 8;
   static constexpr size_t kSmemBytes = 1024 + kW3Bytes + kW1Bytes + kAStages * kAStage + 4 * kCQuarter + kBiasBytes + kBarBytes;
@@ -58,7 +71,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src,
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 
-template <int K3C, int N1, bool kRes>
+template <int K3C, int N1, bool kRes, bool kPool = false>
 __global__ void __launch_bounds__(384, 1)
 bneck_tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ CUtensorMap tmW1,
@@ -93,8 +106,9 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const int my_tiles = (int(blockIdx.x) < num_tiles) ? (num_tiles - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0;
   auto tile_m0 = [&](int it) {
     const int t = int(blockIdx.x) + it * int(gridDim.x);
-    return (p.reverse ? num_tiles - 1 - t : t) * 128;
+    return (p.reverse ? num_tiles - 1 - t : t) * (kPool ? p.tile_rows : 128);
   };
+  const uint32_t a_bytes = kPool ? uint32_t(p.tile_rows) * 128u : uint32_t(Cfg::kAStage);    // one TMA box: tile rows x 64 channels
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -141,8 +155,9 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         for (int kc = 0; kc < K3C; ++kc) {
           mbar_wait(bar_aempty + 8 * stage, phase ^ 1u);
           const uint32_t full = bar_afull + 8 * stage;
-          mbar_arrive_expect_tx(full, Cfg::kAStage);
-          tma_load_2d(kc == 0 ? &tmA0 : &tmA1, full, sA + stage * Cfg::kAStage, 0, m0);
+          mbar_arrive_expect_tx(full, a_bytes);
+          if (kPool) tma_load_5d(kc == 0 ? &tmA0 : &tmA1, full, sA + stage * Cfg::kAStage, 0, 0, 0, 0, m0 / p.tile_rows);
+          else tma_load_2d(kc == 0 ? &tmA0 : &tmA1, full, sA + stage * Cfg::kAStage, 0, m0);
           if (++stage == SA) { stage = 0; phase ^= 1u; }
         }
       }
@@ -155,8 +170,9 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const int m0 = tile_m0(0);
         for (int q = 0; q < 4; ++q) {
           if (kRes) {
-            mbar_arrive_expect_tx(bar_res + 8 * q, Cfg::kCQuarter);
-            tma_load_2d(&tmR, bar_res + 8 * q, sC + q * Cfg::kCQuarter, q * 64, m0);
+            mbar_arrive_expect_tx(bar_res + 8 * q, a_bytes);
+            if (kPool) tma_load_5d(&tmR, bar_res + 8 * q, sC + q * Cfg::kCQuarter, q * 64, 0, 0, 0, m0 / p.tile_rows);
+            else tma_load_2d(&tmR, bar_res + 8 * q, sC + q * Cfg::kCQuarter, q * 64, m0);
           } else {
             mbar_arrive(bar_res + 8 * q);
           }
@@ -168,15 +184,18 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const bool more = it + 1 < my_tiles;
         const int m0n = more ? tile_m0(it + 1) : 0;
         for (int q = 0; q < 4; ++q) {
-          mbar_wait(bar_cready + 8 * q, par);
-          tma_store_2d(&tmC, sC + q * Cfg::kCQuarter, q * 64, m0);
-          tma_store_commit();
+          if (!kPool) {
+            mbar_wait(bar_cready + 8 * q, par);
+            tma_store_2d(&tmC, sC + q * Cfg::kCQuarter, q * 64, m0);
+            tma_store_commit();
+          }
           if (more) {
-            tma_store_wait_read0();                            // the store has finished reading staging[q]
-            mbar_wait(bar_cdone + 8 * q, par);                 // ... and so has conv1'
+            if (!kPool) tma_store_wait_read0();                // the store has finished reading staging[q]
+            mbar_wait(bar_cdone + 8 * q, par);                 // ... and so has conv1' (issued after c_ready: the pooling reads too)
             if (kRes) {
-              mbar_arrive_expect_tx(bar_res + 8 * q, Cfg::kCQuarter);
-              tma_load_2d(&tmR, bar_res + 8 * q, sC + q * Cfg::kCQuarter, q * 64, m0n);
+              mbar_arrive_expect_tx(bar_res + 8 * q, a_bytes);
+              if (kPool) tma_load_5d(&tmR, bar_res + 8 * q, sC + q * Cfg::kCQuarter, q * 64, 0, 0, 0, m0n / p.tile_rows);
+              else tma_load_2d(&tmR, bar_res + 8 * q, sC + q * Cfg::kCQuarter, q * 64, m0n);
             } else {
               mbar_arrive(bar_res + 8 * q);
             }
@@ -255,8 +274,10 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const int m0 = tile_m0(it);
       mbar_wait(bar_acc1f + 8 * (it & 1), uint32_t(it >> 1) & 1u);
       tcgen05_fence_after();
-      const bool ok = m0 + row < p.M;
-      __half* const dst = p.y1 + size_t(m0 + row) * N1;
+      // kPool: tile row r = 4 window + 2 dy + dx  ->  pixel m0 + dy W + 2 window + dx
+      const int prow = kPool ? ((row >> 1) & 1) * (2 * p.pool_w) + 2 * (row >> 2) + (row & 1) : row;
+      const bool ok = m0 + prow < p.M && (!kPool || row < p.tile_rows);
+      __half* const dst = p.y1 + size_t(m0 + prow) * N1;
 #pragma unroll
       for (int c = 0; c < N1 / 64; ++c) {
         const int col = half * (N1 / 2) + c * 32;
@@ -318,6 +339,33 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                        "r"(pack_half2(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f))), "r"(pack_half2(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f))),
                        "r"(pack_half2(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f))), "r"(pack_half2(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f)))
                        : "memory");
+        }
+        if (kPool) {
+          // this warp's 32 rows are 8 whole windows: lane = (window, 16-B chunk of this half's 32 channels).  Same arithmetic
+          // as avgpool2_kernel (fp32 sum in window order, * 0.25, one fp16 rounding): bit-identical to pooling a stored x'.
+          __syncwarp();
+          const int wl = lane >> 2, j = lane & 3;
+          const int r0 = lq * 32 + 4 * wl;
+          if (r0 < p.tile_rows) {
+            float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const int nwin = p.pool_mode == 1 ? 4 : 1;
+            for (int wi = 0; wi < nwin; ++wi) {
+              uint4 v;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                           : "r"(qbase + swizzle_off<128>(uint32_t(r0 + wi), uint32_t(half * 4 + j))));
+              const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h[e]);
+                a[2 * e] += f.x;
+                a[2 * e + 1] += f.y;
+              }
+            }
+            const float sc = p.pool_mode == 1 ? .25f : 1.f;
+            const size_t prow = size_t(tile_m0(it) / p.tile_rows) * size_t(p.pool_w) + size_t(r0 >> 2);
+            *reinterpret_cast<uint4*>(p.pool_out + prow * Cfg::kN3 + col + 8 * j) =
+                make_uint4(pack_half2(a[0] * sc, a[1] * sc), pack_half2(a[2] * sc, a[3] * sc), pack_half2(a[4] * sc, a[5] * sc), pack_half2(a[6] * sc, a[7] * sc));
+          }
         }
         tcgen05_fence_before();
         fence_proxy_async_smem();

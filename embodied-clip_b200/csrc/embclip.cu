@@ -87,6 +87,15 @@ static int make_map_nhwc(CUtensorMap* m, const void* base, int n, int h, int w, 
   const uint32_t box[4] = {(uint32_t)box_c, (uint32_t)box_w, (uint32_t)box_h, (uint32_t)box_n};
   return make_map(m, base, 4, dims, pitch, box);
 }
+// [M = pairs x 2 x W, cols] pixel rows as (channel, dx, dy, window, row pair): a {64, 2, 2, W / 2, 1} box lands in shared memory
+// window-major (tile row = 4 window + 2 dy + dx), the order bneck_tail's pooled-output variant wants
+static int make_map_windows(CUtensorMap* m, const void* base, long long M, int cols, int ld, int W) {
+  const uint64_t row = (uint64_t)ld * 2;
+  const uint64_t dims[5] = {(uint64_t)cols, 2, 2, (uint64_t)(W / 2), (uint64_t)(M / (2 * W))};
+  const uint64_t pitch[4] = {row, row * W, row * 2, row * 2 * W};
+  const uint32_t box[5] = {64, 2, 2, (uint32_t)(W / 2), 1};
+  return make_map(m, base, 5, dims, pitch, box);
+}
 int embclip::make_map_2d(CUtensorMap* m, const void* base, int rows, int cols, int ld, int box_cols, int box_rows) {
   const uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
   const uint64_t pitch[1] = {(uint64_t)ld * 2};
@@ -453,38 +462,54 @@ struct TailOp {
   long long M = 0;
   int n1 = 0;
   int reverse = 0;
+  void* pool_out = nullptr;        // [M / 4, 256]: the 2x2-pooled x' INSTEAD of x' (image width pool_w2, M = images x H x W)
+  int pool_mode = 0;               // 1 average, 2 top-left pixel
+  int pool_w2 = 0;                 // image width W (even, 2 W <= 128; H even)
 };
-template <int K3C, int N1, bool kRes>
+template <int K3C, int N1, bool kRes, bool kPool = false>
 static int launch_tail_cfg(const TailOp& op, cudaStream_t st) {
   using Cfg = TailCfg<K3C, N1>;
-  { const int rc_ = ensure_smem((const void*)bneck_tail_kernel<K3C, N1, kRes>, Cfg::kSmemBytes); if (rc_) return rc_; }
+  { const int rc_ = ensure_smem((const void*)bneck_tail_kernel<K3C, N1, kRes, kPool>, Cfg::kSmemBytes); if (rc_) return rc_; }
   const int M = (int)op.M;
+  const int rows = kPool ? 2 * op.pool_w2 : 128;              // tile = two image rows when the epilogue pools
   CUtensorMap tmA0, tmA1, tmW3, tmW1, tmR, tmC;
   int rc;
-  if ((rc = make_map_2d(&tmA0, op.a0, M, 64, 64, 64, 128))) return rc;
-  if (K3C == 2) { if ((rc = make_map_2d(&tmA1, op.a1, M, 64, 64, 64, 128))) return rc; }
+  if (kPool) { if ((rc = make_map_windows(&tmA0, op.a0, M, 64, 64, op.pool_w2))) return rc; }
+  else if ((rc = make_map_2d(&tmA0, op.a0, M, 64, 64, 64, rows))) return rc;
+  if (K3C == 2) { if ((rc = make_map_2d(&tmA1, op.a1, M, 64, 64, 64, rows))) return rc; }
   else tmA1 = tmA0;
   if ((rc = make_map_2d(&tmW3, op.w3, 256, 64 * K3C, 64 * K3C, 64, 256))) return rc;
   if ((rc = make_map_2d(&tmW1, op.w1, N1, 256, 256, 64, N1))) return rc;
-  if ((rc = make_map_2d(&tmC, op.out, M, 256, 256, 64, 128))) return rc;
-  if (kRes) { if ((rc = make_map_2d(&tmR, op.residual, M, 256, 256, 64, 128))) return rc; }
-  else tmR = tmC;
+  if (kRes && kPool) { if ((rc = make_map_windows(&tmR, op.residual, M, 256, 256, op.pool_w2))) return rc; }
+  else if (kRes) { if ((rc = make_map_2d(&tmR, op.residual, M, 256, 256, 64, rows))) return rc; }
+  if (!kPool) { if ((rc = make_map_2d(&tmC, op.out, M, 256, 256, 64, 128))) return rc; }
+  else tmC = tmR;
+  if (!kRes) tmR = tmC;
   TailParams p;
   memset(&p, 0, sizeof p);
-  p.num_tiles = (M + 127) / 128;
+  p.num_tiles = (M + rows - 1) / rows;
   p.M = M;
   p.reverse = op.reverse;
+  p.tile_rows = rows;
+  p.pool_w = op.pool_w2 / 2; p.pool_mode = op.pool_mode; p.pool_out = reinterpret_cast<__half*>(op.pool_out);
   p.bias3 = op.b3; p.bias1 = op.b1;
   p.y1 = reinterpret_cast<__half*>(op.y1);
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   if (grid <= 0) return 0;
-  CUDA_TRY(launch_pdl(bneck_tail_kernel<K3C, N1, kRes>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, tmA0, tmA1, tmW3, tmW1, tmR, tmC, p));
+  CUDA_TRY(launch_pdl(bneck_tail_kernel<K3C, N1, kRes, kPool>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, tmA0, tmA1, tmW3, tmW1, tmR, tmC, p));
   return 0;
 }
 static int launch_bneck_tail(const TailOp& op, cudaStream_t st) {
   if (op.M <= 0) return 0;
   if (op.M > 0x7fffffffLL) return fail(EMBCLIP_EINVAL, "bneck_tail: M too large");
-  if (!op.a0 || !op.w3 || !op.b3 || !op.out || !op.w1 || !op.b1 || !op.y1) return fail(EMBCLIP_EINVAL, "bneck_tail: null argument");
+  if (!op.a0 || !op.w3 || !op.b3 || (!op.out && !op.pool_out) || !op.w1 || !op.b1 || !op.y1) return fail(EMBCLIP_EINVAL, "bneck_tail: null argument");
+  if (op.pool_out) {
+    const int W = op.pool_w2;
+    if (!op.residual || op.n1 != 128) return fail(EMBCLIP_EINVAL, "bneck_tail: the pooled-output variant is built for the identity residual and a 128-wide next conv1");
+    if (W <= 0 || W % 2 || 2 * W > 128 || (2 * W) % 8 || op.M % (2 * W)) return fail(EMBCLIP_EINVAL, "bneck_tail: pooled output needs an even image width <= 64 and whole row pairs (W %d, M %lld)", W, op.M);
+    if (op.pool_mode != 1 && op.pool_mode != 2) return fail(EMBCLIP_EINVAL, "bneck_tail: pool mode %d", op.pool_mode);
+    return launch_tail_cfg<1, 128, true, true>(op, st);
+  }
   if ((op.a1 != nullptr) == (op.residual != nullptr)) return fail(EMBCLIP_EINVAL, "bneck_tail: exactly one of downsample source / identity residual");
   if (op.n1 != 64 && op.n1 != 128) return fail(EMBCLIP_EINVAL, "bneck_tail: next conv1 width must be 64 or 128 (got %d)", op.n1);
   if (op.a1 && op.n1 != 64) return fail(EMBCLIP_EINVAL, "bneck_tail: the K-concatenated variant is built for a 64-wide next conv1 only");
@@ -723,6 +748,7 @@ struct Act {            // workspace tensor, NHWC; batch dim scales with B
   int dtype;            // EMBCLIP_DTYPE_*
   int h, w, c;          // per image
   int rows_per_image;   // h*w, or tokens etc.
+  int hidden = 0;       // not materialised: the producer hands it to its fused consumers on chip (no workspace bytes)
 };
 struct Param {
   embclip_param_info info;
@@ -743,6 +769,7 @@ struct Op {
   int force_bn = 0;
   int reverse = 0;               // tile walk direction (alternates layer to layer: snake order through L2)
   int fuse_next = -1;            // conv3 only: index of the next block's conv1 op, computed by the same launch (bneck_tail)
+  int fuse_pool = -1;            // conv3 only: index of the K_POOL op whose output this launch writes INSTEAD of its own (bneck_tail kPool)
   int fuse_stream = 0;           // ... by bneck_tail_stream (weights streamed: layer 2) instead of bneck_tail (weights resident: layer 1)
   int side = 0;                  // independent of the ops that follow it: launched on the handle's side stream (fork / join)
   int fused_away = 0;            // conv1 only: produced by the previous block's bneck_tail launch, not launched itself
@@ -970,6 +997,22 @@ extern "C" int embclip_rn50_create(const embclip_rn50_cfg* cfg, embclip_rn50_t* 
       if (c1.c0 != 256 || (c1.cout != 64 && c1.cout != 128) || (c3.in1 >= 0 && c1.cout != 64)) continue;
       c3.fuse_next = (int)j;
       c1.fused_away = 1;
+      // ... and when that pool is the ONLY other reader of x' (the next stage's downsample branch), the launch writes the pooled
+      // tensor instead of x' (bneck_tail kPool): x' is never materialised
+      static const bool tail_pool = getenv("EMBCLIP_NO_TAILPOOL") == nullptr;
+      Op& pl = m->ops[i + 1];
+      const Act& xa = m->acts[c3.out];
+      if (tail_pool && j == i + 2 && pl.kind == K_POOL && pl.in0 == c3.out && (pl.pool == 0 || pl.pool == 1 || pl.pool == 2) &&
+          c3.res >= 0 && c1.cout == 128 && xa.w % 2 == 0 && xa.h % 2 == 0 && 2 * xa.w <= 128 && (2 * xa.w) % 8 == 0) {
+        bool other = false;
+        for (size_t k = 0; k < m->ops.size(); ++k)
+          if (k != i + 1 && k != j && (m->ops[k].in0 == c3.out || m->ops[k].in1 == c3.out || m->ops[k].res == c3.out)) other = true;
+        if (!other) {
+          c3.fuse_pool = (int)(i + 1);
+          pl.fused_away = 1;
+          m->acts[c3.out].hidden = 1;
+        }
+      }
     }
     // the same fusion where the weights must stream (layer 2 identity blocks: conv3 128 -> 512, next conv1 512 -> 128)
     static const bool stream_fuse = getenv("EMBCLIP_NO_TAILSTREAM") == nullptr;
@@ -1014,6 +1057,7 @@ extern "C" int embclip_rn50_bind_weights(embclip_rn50_t h, const void* device_bl
 }
 
 static uint64_t act_bytes(const Act& a, int B) {
+  if (a.hidden) return 0;
   const uint64_t n = (uint64_t)B * a.h * a.w * a.c * (a.dtype == EMBCLIP_DTYPE_F16 ? 2 : 4);
   return (n + 1023) & ~uint64_t(1023);
 }
@@ -1032,7 +1076,7 @@ extern "C" int embclip_rn50_act_info(embclip_rn50_t h, int batch, int index, emb
   const Act& a = h->acts[index];
   memset(out, 0, sizeof *out);
   snprintf(out->name, sizeof out->name, "%s", a.name.c_str());
-  out->dtype = a.dtype; out->n = batch; out->h = a.h; out->w = a.w; out->c = a.c;
+  out->dtype = a.dtype; out->n = a.hidden ? 0 : batch; out->h = a.h; out->w = a.w; out->c = a.c;
   out->offset = act_offset(h, batch, index);
   return 0;
 }
@@ -1080,6 +1124,10 @@ static int run_op(embclip_rn50* m, const Op& op, const std::vector<uint64_t>& of
         t.residual = act_ptr(op.res); t.out = act_ptr(op.out);
         t.w1 = param_ptr(c1.wp); t.b1 = (const float*)param_ptr(c1.bp); t.y1 = act_ptr(c1.out);
         t.M = (long long)B * a.h * a.w; t.n1 = c1.cout; t.reverse = op.reverse;
+        if (op.fuse_pool >= 0) {
+          const Op& pl = m->ops[op.fuse_pool];
+          t.out = nullptr; t.pool_out = act_ptr(pl.out); t.pool_mode = pl.pool ? pl.pool : 1; t.pool_w2 = a.w;
+        }
         return launch_bneck_tail(t, st);
       }
       GemmOp g;
@@ -1133,6 +1181,13 @@ static int run_op(embclip_rn50* m, const Op& op, const std::vector<uint64_t>& of
       return 0;
     }
     case K_NCHW: {
+      const size_t wide_smem = (size_t)P * 128 * 4;
+      if (m->embed % 128 == 0 && wide_smem <= 200u * 1024u && reinterpret_cast<uintptr_t>(o_nchw) % 16 == 0) {
+        { const int rc_ = ensure_smem((const void*)nhwc_to_nchw_f32_wide_kernel, wide_smem); if (rc_) return rc_; }
+        dim3 grid(m->embed / 128, B);
+        CUDA_TRY(launch_pdl(nhwc_to_nchw_f32_wide_kernel, grid, dim3(256), wide_smem, st, (const float*)act_ptr(op.in0), o_nchw, P, m->embed));
+        return 0;
+      }
       dim3 grid(m->embed / 32, B);
       CUDA_TRY(launch_pdl(nhwc_to_nchw_f32_kernel, grid, dim3(256), (size_t)P * 33 * 4, st, (const float*)act_ptr(op.in0), o_nchw, P, m->embed));
       return 0;

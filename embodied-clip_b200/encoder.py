@@ -101,6 +101,8 @@ class ClipRN50Encoder:
         for i in range(n):
             ai = _lib.ActInfo()
             _lib.check(self.lib.embclip_rn50_act_info(self._h, batch, i, C.byref(ai)))
+            if ai.n == 0:       # not materialised: handed to its fused consumers on chip (bneck_tail's pooled-output variant)
+                continue
             dt = torch.float16 if ai.dtype == _lib.DTYPE_F16 else torch.float32
             numel = ai.n * ai.h * ai.w * ai.c
             nbytes = numel * (2 if dt == torch.float16 else 4)

@@ -96,7 +96,7 @@ int embclip_rn50_forward_u8(embclip_rn50_t h, const uint8_t* frames_nhwc_u8, con
 typedef struct {
   char name[64];
   int32_t dtype;
-  int32_t n, h, w, c;   /* NHWC */
+  int32_t n, h, w, c;   /* NHWC; n == 0: the tensor is not materialised (its producer feeds fused consumers on chip) */
   uint64_t offset;      /* bytes from workspace start */
 } embclip_act_info;
 int embclip_rn50_num_acts(embclip_rn50_t h);

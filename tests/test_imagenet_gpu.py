@@ -81,8 +81,15 @@ def test_imagenet_rn50_per_layer_vs_torchvision(tv):
                 rep.append((p + ".conv2", rel_l2(nchw(acts[p + ".conv2"]), b)))
                 idn = nchw(x) if blk.downsample is None else blk.downsample(nchw(x))
                 c = F.relu(blk.bn3(blk.conv3(nchw(acts[p + ".conv2"]))) + idn)
-                rep.append((p + ".conv3", rel_l2(nchw(acts[p + ".conv3"]), c)))
-                x = acts[p + ".conv3"]
+                if p + ".conv3" in acts:
+                    rep.append((p + ".conv3", rel_l2(nchw(acts[p + ".conv3"]), c)))
+                    x = acts[p + ".conv3"]
+                else:
+                    # not materialised: the fused launch writes the next stage's stride-2 subsample of it instead (and the
+                    # next conv1, checked above against this block's reference output)
+                    x = c.half().float().permute(0, 2, 3, 1).contiguous()
+                    nxt = f"layer{li + 2}.0.xpool"
+                    rep.append((nxt, rel_l2(nchw(acts[nxt]), c[:, :, ::2, ::2])))
     bad = [r for r in rep if not r[1] <= 6e-4]
     print("worst per-op rel-L2:", max(rep, key=lambda r: r[1]))
     assert not bad, bad
