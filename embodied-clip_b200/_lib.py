@@ -66,6 +66,7 @@ SIGNATURES = {
     "embclip_avgpool2_f16": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
     "embclip_pool2_f16": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP]),
     "embclip_bneck_tail_f16": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int64, _I, _VP]),
+    "embclip_bneck_tail_pool_f16": (_I, [_VP, _VP, _FP, _VP, _VP, _I, _I, _VP, _FP, _VP, C.c_int64, _I, _VP]),
     "embclip_bneck_tail_stream_f16": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int64, _I, _I, _I, _VP]),
     "embclip_stem_conv1": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     # CLIP transformer towers

@@ -12,16 +12,15 @@
 // Pipeline unit = one 64-column QUARTER of a 128 x 256 output tile (staging buffer q, TMEM accumulator q):
 //   R-thread   residual quarter  --TMA-->  staging[q]                                   (res_full[q])
 //   MMA warp   acc3[q] = A . W3[64q..64q+63]^T      (N = 64, K = 64 or 128)             (acc3_full[q])
-//   epilogue   staging[q] = fp16(relu(acc3[q] + b3 + staging[q]))   in place            (c_ready[q])
+//   epilogue   staging[q] = fp16(relu(acc3[q] + b3 + staging[q]))   in place            (c_ready[q]; 4 warp arrivals)
 //   R-thread   staging[q] --TMA store--> x'                    MMA warp: acc1 += staging[q] . W1'[:, 64q..]^T  (c_mma_done[q])
 //   R-thread   (store read done, MMA retired) -> next tile's residual quarter into staging[q]
 // so three residual quarters are always in flight while one is being consumed.  After the 4th quarter the conv1'
 // accumulator (double-buffered by tile parity) is complete; its epilogue (bias, ReLU, fp16, st.global) runs in the
 // middle of the NEXT tile's quarters, when the MMAs have long retired.  W3 and W1' stay resident in shared memory.
 //
-// Warp roles (384 threads): warp 0 = A producer (+ weights once), warp 1 = TMEM owner + MMA issuer, warp 2 = R-thread
-// (residual loads, x' stores), warp 3 idle (kPool: the pool warp), warps 4..11 = epilogue (two per TMEM lane quarter, 32
-// columns each).
+// Warp roles (640 threads): warp 0 = A producer (+ weights once), warp 1 = TMEM owner + MMA issuer, warp 2 = R-thread
+// (residual loads, x' stores), warp 3 idle, warps 4..19 = epilogue (four per TMEM lane quarter, 16 columns each).
 //
 // kPool (the LAST block of a stage, whose x' is read only by the next stage's conv1 and by its downsample branch's
 // AvgPool2d(2) / stride-2 subsample): a tile is two image rows (2 W <= 128 pixels; the UMMA still runs 128 rows, the spare ones
@@ -58,8 +57,11 @@ struct TailCfg {
   static constexpr int kCQuarter = 128 * 128;
   static constexpr int kBiasBytes = (kN3 + N1) * 4;
   static constexpr int kBarBytes = 320;
-  static constexpr int kThreads = 384;
-  static constexpr int kEpiWarps = 8;
+  static constexpr int kParts = 4;                             // epilogue warps per TMEM lane quarter: 64 / kParts columns each
+  static constexpr int kEpiWarps = 4 * kParts;
+  static constexpr int kThreads = 128 + 32 * kEpiWarps;
+  static constexpr int kCP = 64 / kParts;                      // conv3 columns per epilogue warp and quarter
+  static constexpr int kC1 = N1 / kParts;                      // conv1' columns per epilogue warp
   static constexpr size_t kSmemBytes = 1024 + kW3Bytes + kW1Bytes + kAStages * kAStage + 4 * kCQuarter + kBiasBytes + kBarBytes;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
   static_assert(kAStages % K3C == 0, "a tile's k-chunks must not straddle the ring wrap");
@@ -72,7 +74,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src,
 }
 
 template <int K3C, int N1, bool kRes, bool kPool = false>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(TailCfg<K3C, N1>::kThreads, 1)
 bneck_tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmC, const TailParams p) {
@@ -92,7 +94,7 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const uint32_t bar_aempty = bar_afull + 8 * SA;    // SA
   const uint32_t bar_acc3 = bar_aempty + 8 * SA;     // 4: conv3 quarter accumulated
   const uint32_t bar_res = bar_acc3 + 32;            // 4: staging quarter free (+ residual landed)
-  const uint32_t bar_cready = bar_res + 32;          // 4: x' quarter written to staging (8 warp arrivals)
+  const uint32_t bar_cready = bar_res + 32;          // 4: x' quarter written to staging (4 warp arrivals: one per lane quarter)
   const uint32_t bar_cdone = bar_cready + 32;        // 4: conv1' MMAs on the quarter retired
   const uint32_t bar_acc1f = bar_cdone + 32;         // 2
   const uint32_t bar_acc1e = bar_acc1f + 16;         // 2 (8 warp arrivals)
@@ -104,10 +106,11 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_tiles;
   const int my_tiles = (int(blockIdx.x) < num_tiles) ? (num_tiles - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0;
-  auto tile_m0 = [&](int it) {
+  auto tile_idx = [&](int it) {
     const int t = int(blockIdx.x) + it * int(gridDim.x);
-    return (p.reverse ? num_tiles - 1 - t : t) * (kPool ? p.tile_rows : 128);
+    return p.reverse ? num_tiles - 1 - t : t;
   };
+  auto tile_m0 = [&](int it) { return tile_idx(it) * (kPool ? p.tile_rows : 128); };
   const uint32_t a_bytes = kPool ? uint32_t(p.tile_rows) * 128u : uint32_t(Cfg::kAStage);    // one TMA box: tile rows x 64 channels
 
   if (warp == 0 && lane == 0) {
@@ -122,7 +125,7 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     for (int q = 0; q < 4; ++q) {
       mbar_init(bar_acc3 + 8 * q, 1);
       mbar_init(bar_res + 8 * q, 1);
-      mbar_init(bar_cready + 8 * q, Cfg::kEpiWarps);
+      mbar_init(bar_cready + 8 * q, 4);
       mbar_init(bar_cdone + 8 * q, 1);
     }
     for (int a = 0; a < 2; ++a) { mbar_init(bar_acc1f + 8 * a, 1); mbar_init(bar_acc1e + 8 * a, Cfg::kEpiWarps); }
@@ -156,7 +159,7 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           mbar_wait(bar_aempty + 8 * stage, phase ^ 1u);
           const uint32_t full = bar_afull + 8 * stage;
           mbar_arrive_expect_tx(full, a_bytes);
-          if (kPool) tma_load_5d(kc == 0 ? &tmA0 : &tmA1, full, sA + stage * Cfg::kAStage, 0, 0, 0, 0, m0 / p.tile_rows);
+          if (kPool) tma_load_5d(kc == 0 ? &tmA0 : &tmA1, full, sA + stage * Cfg::kAStage, 0, 0, 0, 0, tile_idx(it));
           else tma_load_2d(kc == 0 ? &tmA0 : &tmA1, full, sA + stage * Cfg::kAStage, 0, m0);
           if (++stage == SA) { stage = 0; phase ^= 1u; }
         }
@@ -171,7 +174,7 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         for (int q = 0; q < 4; ++q) {
           if (kRes) {
             mbar_arrive_expect_tx(bar_res + 8 * q, a_bytes);
-            if (kPool) tma_load_5d(&tmR, bar_res + 8 * q, sC + q * Cfg::kCQuarter, q * 64, 0, 0, 0, m0 / p.tile_rows);
+            if (kPool) tma_load_5d(&tmR, bar_res + 8 * q, sC + q * Cfg::kCQuarter, q * 64, 0, 0, 0, tile_idx(0));
             else tma_load_2d(&tmR, bar_res + 8 * q, sC + q * Cfg::kCQuarter, q * 64, m0);
           } else {
             mbar_arrive(bar_res + 8 * q);
@@ -194,7 +197,7 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             mbar_wait(bar_cdone + 8 * q, par);                 // ... and so has conv1' (issued after c_ready: the pooling reads too)
             if (kRes) {
               mbar_arrive_expect_tx(bar_res + 8 * q, a_bytes);
-              if (kPool) tma_load_5d(&tmR, bar_res + 8 * q, sC + q * Cfg::kCQuarter, q * 64, 0, 0, 0, m0n / p.tile_rows);
+              if (kPool) tma_load_5d(&tmR, bar_res + 8 * q, sC + q * Cfg::kCQuarter, q * 64, 0, 0, 0, tile_idx(it + 1));
               else tma_load_2d(&tmR, bar_res + 8 * q, sC + q * Cfg::kCQuarter, q * 64, m0n);
             } else {
               mbar_arrive(bar_res + 8 * q);
@@ -265,10 +268,13 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
     if (my_tiles > 0) mma1(my_tiles - 1, 3);
   } else if (warp >= 4) {
-    // ============================ epilogue (warps 4..11) ============================
+    // ============================ epilogue (warps 4 .. 4 + kEpiWarps - 1) ============================
+    // kParts warps share a TMEM lane quarter (32 tile rows); warp (lq, part) owns quarter `part` of every tile and a 1/kParts
+    // column slice of the conv1' output.
+    constexpr int CP = Cfg::kCP, C1 = Cfg::kC1;
     const int lq = warp & 3;                                   // TMEM lane quarter
     const int row = lq * 32 + lane;
-    const int half = (warp - 4) >> 2;
+    const int part = (warp - 4) >> 2;
     const uint32_t lane_addr = tmem_base + (uint32_t(lq * 32) << 16);
     auto epi1 = [&](int it) {                                  // conv1' of tile `it`: bias, ReLU, fp16, straight to global
       const int m0 = tile_m0(it);
@@ -278,53 +284,56 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const int prow = kPool ? ((row >> 1) & 1) * (2 * p.pool_w) + 2 * (row >> 2) + (row & 1) : row;
       const bool ok = m0 + prow < p.M && (!kPool || row < p.tile_rows);
       __half* const dst = p.y1 + size_t(m0 + prow) * N1;
+      const int col = part * C1;
+      uint32_t v[C1];
+      tmem_ld_32x32b<C1>(lane_addr + uint32_t(256 + (it & 1) * N1 + col), v);
+      tmem_ld_wait();
+      if (ok) {
 #pragma unroll
-      for (int c = 0; c < N1 / 64; ++c) {
-        const int col = half * (N1 / 2) + c * 32;
-        uint32_t v[32];
-        tmem_ld_32x32b<32>(lane_addr + uint32_t(256 + (it & 1) * N1 + col), v);
-        tmem_ld_wait();
-        if (ok) {
+        for (int i = 0; i < C1 / 8; ++i) {
+          uint32_t h[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint32_t h[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              h[j] = pack_half2(fmaxf(__uint_as_float(v[8 * i + 2 * j]) + sBias1[col + 8 * i + 2 * j], 0.f),
-                                fmaxf(__uint_as_float(v[8 * i + 2 * j + 1]) + sBias1[col + 8 * i + 2 * j + 1], 0.f));
-            *reinterpret_cast<uint4*>(dst + col + 8 * i) = make_uint4(h[0], h[1], h[2], h[3]);
-          }
+          for (int j = 0; j < 4; ++j)
+            h[j] = pack_half2(fmaxf(__uint_as_float(v[8 * i + 2 * j]) + sBias1[col + 8 * i + 2 * j], 0.f),
+                              fmaxf(__uint_as_float(v[8 * i + 2 * j + 1]) + sBias1[col + 8 * i + 2 * j + 1], 0.f));
+          *reinterpret_cast<uint4*>(dst + col + 8 * i) = make_uint4(h[0], h[1], h[2], h[3]);
         }
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc1e + 8 * (it & 1));
     };
+    // Quarter q of EVERY tile belongs to the four warps with part == q (one per TMEM lane quarter): the four quarter chains
+    // (accumulator wait -> TMEM load -> residual -> fp16 -> staging -> c_ready) of a tile run side by side instead of one after
+    // the other in each warp, which is what bounded the tile period (measured ~1 us per quarter whatever the byte count).
+    const int q = part;
+    const uint32_t qbase = sC + uint32_t(q) * Cfg::kCQuarter;
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t par = uint32_t(it & 1);
-      for (int q = 0; q < 4; ++q) {
-        if (q == 2 && it > 0) epi1(it - 1);
-        const int col = q * 64 + half * 32;
-        mbar_wait(bar_acc3 + 8 * q, par);
-        tcgen05_fence_after();
-        uint32_t v[32];
-        tmem_ld_32x32b<32>(lane_addr + uint32_t(col), v);
-        mbar_wait(bar_res + 8 * q, par);
-        const uint32_t qbase = sC + uint32_t(q) * Cfg::kCQuarter;
-        uint4 r[4];
+      mbar_wait(bar_acc3 + 8 * q, par);
+      tcgen05_fence_after();
+      uint32_t v[2][CP];
+      tmem_ld_32x32b<CP>(lane_addr + uint32_t(q * 64), v[0]);
+      mbar_wait(bar_res + 8 * q, par);
+#pragma unroll
+      for (int sub = 0; sub < 64 / CP; ++sub) {
+        const int col = q * 64 + sub * CP;
+        uint4 r[CP / 8];
         if (kRes) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t a = qbase + swizzle_off<128>(uint32_t(row), uint32_t(half * 4 + i));
+          for (int i = 0; i < CP / 8; ++i) {
+            const uint32_t a = qbase + swizzle_off<128>(uint32_t(row), uint32_t(sub * (CP / 8) + i));
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[i].x), "=r"(r[i].y), "=r"(r[i].z), "=r"(r[i].w) : "r"(a));
           }
         }
         tmem_ld_wait();
+        if (sub + 1 < 64 / CP) tmem_ld_32x32b<CP>(lane_addr + uint32_t(col + CP), v[(sub + 1) & 1]);   // next chunk in flight
+        const uint32_t (&vv)[CP] = v[sub & 1];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < CP / 8; ++i) {
           float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[8 * i + j]) + sBias3[col + 8 * i + j];
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(vv[8 * i + j]) + sBias3[col + 8 * i + j];
           if (kRes) {
             const __half2* h = reinterpret_cast<const __half2*>(&r[i]);
 #pragma unroll
@@ -334,44 +343,54 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               f[2 * j + 1] += r2.y;
             }
           }
-          const uint32_t a = qbase + swizzle_off<128>(uint32_t(row), uint32_t(half * 4 + i));
+          const uint32_t a = qbase + swizzle_off<128>(uint32_t(row), uint32_t(sub * (CP / 8) + i));
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
                        "r"(pack_half2(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f))), "r"(pack_half2(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f))),
                        "r"(pack_half2(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f))), "r"(pack_half2(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f)))
                        : "memory");
         }
-        if (kPool) {
-          // this warp's 32 rows are 8 whole windows: lane = (window, 16-B chunk of this half's 32 channels).  Same arithmetic
-          // as avgpool2_kernel (fp32 sum in window order, * 0.25, one fp16 rounding): bit-identical to pooling a stored x'.
-          __syncwarp();
-          const int wl = lane >> 2, j = lane & 3;
+      }
+      if (kPool) {
+        // this warp's 32 rows are 8 whole windows: item = (window, 16-B chunk of the quarter's 64 channels), two per lane.
+        // Same arithmetic as avgpool2_kernel (fp32 sum in window order, * 0.25, one fp16 rounding): bit-identical to
+        // pooling a stored x'.
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int wl = (lane >> 3) + 4 * k, j = lane & 7;
           const int r0 = lq * 32 + 4 * wl;
           if (r0 < p.tile_rows) {
-            float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            const int nwin = p.pool_mode == 1 ? 4 : 1;
-            for (int wi = 0; wi < nwin; ++wi) {
-              uint4 v;
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                           : "r"(qbase + swizzle_off<128>(uint32_t(r0 + wi), uint32_t(half * 4 + j))));
-              const __half2* h = reinterpret_cast<const __half2*>(&v);
+            uint4 x4[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(h[e]);
-                a[2 * e] += f.x;
-                a[2 * e + 1] += f.y;
+            for (int wi = 0; wi < 4; ++wi)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x4[wi].x), "=r"(x4[wi].y), "=r"(x4[wi].z), "=r"(x4[wi].w)
+                           : "r"(qbase + swizzle_off<128>(uint32_t(r0 + wi), uint32_t(j))));
+            uint4 o = x4[0];                                   // pool_mode 2: the window's top-left pixel
+            if (p.pool_mode == 1) {
+              float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+              for (int wi = 0; wi < 4; ++wi) {
+                const __half2* h = reinterpret_cast<const __half2*>(&x4[wi]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __half22float2(h[e]);
+                  a[2 * e] += f.x;
+                  a[2 * e + 1] += f.y;
+                }
               }
+              o = make_uint4(pack_half2(a[0] * .25f, a[1] * .25f), pack_half2(a[2] * .25f, a[3] * .25f),
+                             pack_half2(a[4] * .25f, a[5] * .25f), pack_half2(a[6] * .25f, a[7] * .25f));
             }
-            const float sc = p.pool_mode == 1 ? .25f : 1.f;
-            const size_t prow = size_t(tile_m0(it) / p.tile_rows) * size_t(p.pool_w) + size_t(r0 >> 2);
-            *reinterpret_cast<uint4*>(p.pool_out + prow * Cfg::kN3 + col + 8 * j) =
-                make_uint4(pack_half2(a[0] * sc, a[1] * sc), pack_half2(a[2] * sc, a[3] * sc), pack_half2(a[4] * sc, a[5] * sc), pack_half2(a[6] * sc, a[7] * sc));
+            const size_t prow = size_t(tile_idx(it)) * size_t(p.pool_w) + size_t(r0 >> 2);
+            *reinterpret_cast<uint4*>(p.pool_out + prow * Cfg::kN3 + q * 64 + 8 * j) = o;
           }
         }
-        tcgen05_fence_before();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_cready + 8 * q);
       }
+      tcgen05_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_cready + 8 * q);
+      if (it > 0) epi1(it - 1);
     }
     if (my_tiles > 0) epi1(my_tiles - 1);
   }

@@ -618,6 +618,16 @@ extern "C" int embclip_bneck_tail_f16(const void* y2, const void* x0, const void
   return launch_bneck_tail(op, (cudaStream_t)stream);
 }
 
+extern "C" int embclip_bneck_tail_pool_f16(const void* y2, const void* w3, const float* b3, const void* residual, void* pool_out, int pool_mode,
+                                           int width, const void* w1, const float* b1, void* y1, int64_t M, int n1, void* stream) {
+  EMBCLIP_TRACE();
+  if (!pool_out) return fail(EMBCLIP_EINVAL, "bneck_tail_pool: null pooled output");
+  TailOp op;
+  op.a0 = y2; op.w3 = w3; op.b3 = b3; op.residual = residual; op.pool_out = pool_out; op.pool_mode = pool_mode; op.pool_w2 = width;
+  op.w1 = w1; op.b1 = b1; op.y1 = y1; op.M = M; op.n1 = n1;
+  return launch_bneck_tail(op, (cudaStream_t)stream);
+}
+
 // mode 1: nn.AvgPool2d(2); 2: x[:, ::2, ::2] (input of a stride-2 1x1 conv); 3: nn.MaxPool2d(3, 2, 1)
 static int launch_avgpool2(const void* in, void* out, int B, int H, int W, int C, cudaStream_t st, int mode = 1) {
   if (H % 2 || W % 2 || C % 8) return fail(EMBCLIP_EINVAL, "pool: H, W must be even and C a multiple of 8");

@@ -140,6 +140,13 @@ int embclip_gemm_grouped_f16(const void* a, int lda, const void* w, int ldw, int
  * BatchNorm + ReLU (+ AvgPool2d) of clip/model.py Bottleneck / ModifiedResNet stem. */
 int embclip_conv3x3_f16(const void* in, const void* w, const float* bias, void* out, int B, int H, int W,
                         int Cin, int Cout, int relu, int pool, void* stream);
+/* bneck_tail for the LAST block of a stage: the same two fused convs, but instead of x' the launch writes pool(x'), the input of
+ * the next stage's downsample branch (clip/model.py Bottleneck.downsample [UPSTREAM]: AvgPool2d(2) before the 1x1 conv;
+ * torchvision's stride-2 1x1 conv reads x'[:, ::2, ::2]).  The M rows are pixels of images `width` wide (width even, <= 64;
+ * M a multiple of 2 * width); pool_mode 1 = 2x2 average, 2 = top-left pixel of each window; pool_out is [M / 4, 256] fp16.
+ * Identity residual and n1 == 128 only. */
+int embclip_bneck_tail_pool_f16(const void* y2, const void* w3, const float* b3, const void* residual, void* pool_out, int pool_mode,
+                                int width, const void* w1, const float* b1, void* y1, int64_t M, int n1, void* stream);
 /* The same fusion with STREAMED weights, for stages whose conv3 / next-conv1 matrices do not fit shared memory (layer 2):
  *   out[M,N3] = relu(y2[M,K3] . w3[N3,K3]^T + b3 + residual[M,N3]);   y1[M,n1] = relu(out . w1[n1,N3]^T + b1)
  * Built for K3 = 128, n1 = 128, N3 a multiple of 64 in [256, 1024]. */

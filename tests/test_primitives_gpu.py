@@ -264,6 +264,68 @@ def test_bneck_tail(lib, M, n1, down):
     _tail_case(lib, M, n1, down, seed=M % 97)
 
 
+def _tail_pool_case(lib, B, H, W, mode, seed=0):
+    """bneck_tail, pooled-output variant: the launch writes pool(x') (2x2 average, or the window's top-left pixel) and the next
+    conv1 of x', but not x' itself.  The same launch without the pooling gives x' bit for bit (same tiles' arithmetic), so the
+    pooled tensor must EQUAL the pool of that x', and y1 must equal the plain launch's y1."""
+    import torch.nn.functional as F
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    M, n1 = B * H * W, 128
+    y2 = rn(M, 64).relu().half()
+    w3 = (rn(256, 64) / 8).half()
+    b3 = rn(256)
+    res = rn(M, 256).relu().half()
+    w1 = (rn(n1, 256) / 16).half()
+    b1 = rn(n1)
+    out = torch.full((M, 256), float("nan"), device="cuda", dtype=torch.float16)
+    y1_plain = torch.full((M, n1), float("nan"), device="cuda", dtype=torch.float16)
+    _check(lib, lib.embclip_bneck_tail_f16(_ptr(y2), None, _ptr(w3), _ptr(b3), _ptr(res), _ptr(out), _ptr(w1), _ptr(b1),
+                                           _ptr(y1_plain), M, n1, _stream()))
+    pooled = torch.full((M // 4, 256), float("nan"), device="cuda", dtype=torch.float16)
+    y1 = torch.full((M, n1), float("nan"), device="cuda", dtype=torch.float16)
+    _check(lib, lib.embclip_bneck_tail_pool_f16(_ptr(y2), _ptr(w3), _ptr(b3), _ptr(res), _ptr(pooled), mode, W, _ptr(w1), _ptr(b1),
+                                                _ptr(y1), M, n1, _stream()))
+    torch.cuda.synchronize()
+    x = out.view(B, H, W, 256)
+    if mode == 1:
+        x = x.float()
+        ref = ((((x[:, 0::2, 0::2] + x[:, 0::2, 1::2]) + x[:, 1::2, 0::2]) + x[:, 1::2, 1::2]) * 0.25).half()
+    else:
+        ref = x[:, 0::2, 0::2]
+    assert torch.equal(pooled.view(B, H // 2, W // 2, 256), ref), f"pooled output differs (B{B} {H}x{W} mode {mode})"
+    assert torch.equal(y1, y1_plain), f"conv1' output differs from the plain launch (B{B} {H}x{W} mode {mode})"
+    ref_out = (y2.float() @ w3.float().t() + b3 + res.float()).relu()
+    _close(out, ref_out, f"bneck_tail (plain, for the pooled case) out B{B} {H}x{W}")
+
+
+@pytest.mark.parametrize("B,H,W,mode", [
+    (1, 2, 56, 1),               # one tile of two image rows
+    (2, 56, 56, 1),              # layer 1 of CLIP RN50: AvgPool2d(2) in front of layer2.0's downsample conv
+    (2, 56, 56, 2),              # torchvision: stride-2 1x1 downsample conv reads x'[:, ::2, ::2]
+    (160, 4, 56, 1),             # several tiles per CTA: accumulator / staging parities
+    (3, 8, 32, 1),               # narrower rows: 64-row tiles
+    (1, 6, 64, 2),               # the widest supported row: 128-row tiles
+])
+def test_bneck_tail_pool(lib, B, H, W, mode):
+    _tail_pool_case(lib, B, H, W, mode, seed=B * 7 + W)
+
+
+def test_bneck_tail_pool_rejects_bad_arguments(lib):
+    z = torch.zeros(2 * 2 * 56, 256, device="cuda", dtype=torch.float16)
+    b = torch.zeros(256, device="cuda")
+    call = lambda mode, W, M, n1: lib.embclip_bneck_tail_pool_f16(_ptr(z), _ptr(z), _ptr(b), _ptr(z), _ptr(z), mode, W, _ptr(z), _ptr(b),
+                                                                  _ptr(z), M, n1, _stream())
+    assert call(1, 56, 224, 128) == 0
+    assert call(3, 56, 224, 128) != 0        # max pooling is not a downsample-branch mode
+    assert call(1, 57, 228, 128) != 0        # odd width
+    assert call(1, 72, 144, 128) != 0        # two rows do not fit one 128-row tile
+    assert call(1, 56, 168, 128) != 0        # M is not whole row pairs
+    assert call(1, 56, 224, 64) != 0         # only the 128-wide next conv1 is built
+    assert b"bneck_tail" in lib.embclip_last_error()
+    torch.cuda.synchronize()
+
+
 def _tail_stream_case(lib, M, n3, seed=0):
     """bneck_tail_stream: out = relu(y2 W3^T + b3 + res) rounded to fp16; y1 = relu(out W1^T + b1) from that fp16 tile."""
     g = torch.Generator(device="cuda").manual_seed(seed)
