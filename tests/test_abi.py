@@ -63,9 +63,9 @@ def test_plan_queries_without_gpu(built_lib):
     assert 0 < w1 and 7.9 * w1 < w8 <= 8 * w1
     # trunk launches: 3 stem convs (pool fused into conv3), 16 x 3 convs minus the 3 conv1s that layer 1's bneck_tail launches
     # compute (layer1.1, layer1.2, layer2.0) and the 2 that layer 2's bneck_tail_stream launches compute (layer2.2, layer2.3),
-    # 3 identity-path pools; + heads
-    assert lib.embclip_rn50_launches_per_forward(h, 0, 0, 0) == 3 + 48 - 3 - 2 + 3
-    assert lib.embclip_rn50_launches_per_forward(h, 1, 1, 1) == 3 + 48 - 3 - 2 + 3 + 2 + 6
+    # 3 identity-path pools minus the one layer1.2's bneck_tail writes itself (pooled-output variant); + heads
+    assert lib.embclip_rn50_launches_per_forward(h, 0, 0, 0) == 3 + 48 - 3 - 2 + 3 - 1
+    assert lib.embclip_rn50_launches_per_forward(h, 1, 1, 1) == 3 + 48 - 3 - 2 + 3 - 1 + 2 + 6
     # error paths: state and argument checks happen before any CUDA call
     assert lib.embclip_rn50_forward(h, None, 1, None, None, None, None, 0, None) == -1
     bad = _lib.RN50Cfg()
