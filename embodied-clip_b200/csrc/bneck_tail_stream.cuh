@@ -14,8 +14,9 @@
 // 256 KB of L2 -> smem traffic next to 160 KB of activations -- they come from L2, not HBM).  The conv1' UMMA of quarter u is issued
 // kLag = 3 quarters behind the conv3 UMMA, so the epilogue always has two quarters of slack.
 //
-// Warp roles (384 threads): warp 0 = A producer, warp 1 = TMEM owner + MMA issuer, warp 2 = R-thread (residual loads, x' stores),
-// warp 3 = W1' producer (warp 0 also streams W3), warps 4..11 = epilogue.
+// Warp roles (640 threads): warp 0 = A producer, warp 1 = TMEM owner + MMA issuer, warp 2 = R-thread (residual loads, x' stores),
+// warp 3 = W1' producer (warp 0 also streams W3), warps 4..19 = epilogue: ring slot s (units u with u % 4 == s) belongs to the
+// four warps with part == s, one per TMEM lane quarter, so four units are in flight in the epilogue at once (as in bneck_tail).
 #pragma once
 #include "bneck_tail.cuh"
 
@@ -43,8 +44,10 @@ struct TailStreamCfg {
   static constexpr int kCQuarter = 128 * 128;
   static constexpr int kBiasBytes = (kMaxNQ * 64 + N1) * 4;
   static constexpr int kBarBytes = 384;
-  static constexpr int kThreads = 384;
-  static constexpr int kEpiWarps = 8;
+  static constexpr int kEpiWarps = 16;
+  static constexpr int kThreads = 128 + 32 * kEpiWarps;
+  static constexpr int kCP = 16;                               // conv3 columns per TMEM load
+  static constexpr int kC1 = N1 / 4;                           // conv1' columns per epilogue warp
   static constexpr int kLag = 3;
   static constexpr size_t kSmemBytes = 1024 + kAStages * kAStage + (kW3Depth * kW3Q + kWDepth * kW1Q) + 4 * kCQuarter + kBiasBytes + kBarBytes;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
@@ -53,7 +56,7 @@ struct TailStreamCfg {
 };
 
 template <int K3C, int N1>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(TailStreamCfg<K3C, N1>::kThreads, 1)
 bneck_tail_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW3,
                          const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmR,
                          const __grid_constant__ CUtensorMap tmC, const TailStreamParams p) {
@@ -103,7 +106,7 @@ bneck_tail_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     for (int q = 0; q < 4; ++q) {
       mbar_init(bar_acc3 + 8 * q, 1);
       mbar_init(bar_res + 8 * q, 1);
-      mbar_init(bar_cready + 8 * q, Cfg::kEpiWarps);
+      mbar_init(bar_cready + 8 * q, 4);
       mbar_init(bar_cdone + 8 * q, 1);
     }
     for (int a = 0; a < 2; ++a) { mbar_init(bar_acc1f + 8 * a, 1); mbar_init(bar_acc1e + 8 * a, Cfg::kEpiWarps); }
@@ -244,10 +247,11 @@ bneck_tail_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int v = units > Cfg::kLag ? units - Cfg::kLag : 0; v < units; ++v) mma1(v);
   } else if (warp >= 4) {
-    // ============================ epilogue (warps 4..11) ============================
+    // ============================ epilogue (warps 4..19) ============================
+    constexpr int CP = Cfg::kCP, C1 = Cfg::kC1;
     const int lq = warp & 3;                                   // TMEM lane quarter
     const int row = lq * 32 + lane;
-    const int half = (warp - 4) >> 2;
+    const int part = (warp - 4) >> 2;                          // ring slot owned by this warp; conv1' column slice
     const uint32_t lane_addr = tmem_base + (uint32_t(lq * 32) << 16);
     auto epi1 = [&](int it) {                                  // conv1' of tile `it`: bias, ReLU, fp16, straight to global
       const int m0 = tile_m0(it);
@@ -255,52 +259,53 @@ bneck_tail_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       tcgen05_fence_after();
       const bool ok = m0 + row < p.M;
       __half* const dst = p.y1 + size_t(m0 + row) * N1;
+      const int col = part * C1;
+      uint32_t v[C1];
+      tmem_ld_32x32b<C1>(lane_addr + uint32_t(256 + (it & 1) * N1 + col), v);
+      tmem_ld_wait();
+      if (ok) {
 #pragma unroll
-      for (int c = 0; c < N1 / 64; ++c) {
-        const int col = half * (N1 / 2) + c * 32;
-        uint32_t v[32];
-        tmem_ld_32x32b<32>(lane_addr + uint32_t(256 + (it & 1) * N1 + col), v);
-        tmem_ld_wait();
-        if (ok) {
+        for (int i = 0; i < C1 / 8; ++i) {
+          uint32_t h[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint32_t h[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              h[j] = pack_half2(fmaxf(__uint_as_float(v[8 * i + 2 * j]) + sBias1[col + 8 * i + 2 * j], 0.f),
-                                fmaxf(__uint_as_float(v[8 * i + 2 * j + 1]) + sBias1[col + 8 * i + 2 * j + 1], 0.f));
-            *reinterpret_cast<uint4*>(dst + col + 8 * i) = make_uint4(h[0], h[1], h[2], h[3]);
-          }
+          for (int j = 0; j < 4; ++j)
+            h[j] = pack_half2(fmaxf(__uint_as_float(v[8 * i + 2 * j]) + sBias1[col + 8 * i + 2 * j], 0.f),
+                              fmaxf(__uint_as_float(v[8 * i + 2 * j + 1]) + sBias1[col + 8 * i + 2 * j + 1], 0.f));
+          *reinterpret_cast<uint4*>(dst + col + 8 * i) = make_uint4(h[0], h[1], h[2], h[3]);
         }
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc1e + 8 * (it & 1));
     };
-    int u = 0;
-    for (int it = 0; it < my_tiles; ++it) {
-      for (int q = 0; q < nq; ++q, ++u) {
-        if (q == nq / 2 && it > 0) epi1(it - 1);               // (its last conv1' MMA was issued kLag quarters into this tile)
-        const uint32_t par = uint32_t(u >> 2) & 1u;
-        const int col = q * 64 + half * 32;
-        mbar_wait(bar_acc3 + 8 * (u & 3), par);
-        tcgen05_fence_after();
-        uint32_t v[32];
-        tmem_ld_32x32b<32>(lane_addr + uint32_t((u & 3) * 64 + half * 32), v);
-        mbar_wait(bar_res + 8 * (u & 3), par);
-        const uint32_t qbase = sC + uint32_t(u & 3) * Cfg::kCQuarter;
-        uint4 r[4];
+    const uint32_t qbase = sC + uint32_t(part) * Cfg::kCQuarter;
+    const int total_units = my_tiles * nq;
+    int done_tile = -1;                                        // conv1' epilogues this warp has run: tiles 0 .. done_tile
+    for (int u = part; u < total_units; u += 4) {
+      const int it = u / nq, q = u - it * nq;
+      const uint32_t par = uint32_t(u >> 2) & 1u;
+      mbar_wait(bar_acc3 + 8 * part, par);
+      tcgen05_fence_after();
+      uint32_t v[2][CP];
+      tmem_ld_32x32b<CP>(lane_addr + uint32_t(part * 64), v[0]);
+      mbar_wait(bar_res + 8 * part, par);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t a = qbase + swizzle_off<128>(uint32_t(row), uint32_t(half * 4 + i));
+      for (int sub = 0; sub < 64 / CP; ++sub) {
+        const int col = q * 64 + sub * CP;
+        uint4 r[CP / 8];
+#pragma unroll
+        for (int i = 0; i < CP / 8; ++i) {
+          const uint32_t a = qbase + swizzle_off<128>(uint32_t(row), uint32_t(sub * (CP / 8) + i));
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[i].x), "=r"(r[i].y), "=r"(r[i].z), "=r"(r[i].w) : "r"(a));
         }
         tmem_ld_wait();
+        if (sub + 1 < 64 / CP) tmem_ld_32x32b<CP>(lane_addr + uint32_t(part * 64 + (sub + 1) * CP), v[(sub + 1) & 1]);   // next chunk in flight
+        const uint32_t (&vv)[CP] = v[sub & 1];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < CP / 8; ++i) {
           float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[8 * i + j]) + sBias3[col + 8 * i + j];
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(vv[8 * i + j]) + sBias3[col + 8 * i + j];
           const __half2* h = reinterpret_cast<const __half2*>(&r[i]);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -308,19 +313,21 @@ bneck_tail_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             f[2 * j] += r2.x;
             f[2 * j + 1] += r2.y;
           }
-          const uint32_t a = qbase + swizzle_off<128>(uint32_t(row), uint32_t(half * 4 + i));
+          const uint32_t a = qbase + swizzle_off<128>(uint32_t(row), uint32_t(sub * (CP / 8) + i));
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
                        "r"(pack_half2(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f))), "r"(pack_half2(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f))),
                        "r"(pack_half2(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f))), "r"(pack_half2(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f)))
                        : "memory");
         }
-        tcgen05_fence_before();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_cready + 8 * (u & 3));
       }
+      tcgen05_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_cready + 8 * part);
+      // conv1' of the previous tile: its last UMMA is issued kLag quarters into this tile, after units this warp has finished
+      if (it - 1 > done_tile) { epi1(it - 1); done_tile = it - 1; }
     }
-    if (my_tiles > 0) epi1(my_tiles - 1);
+    for (int it = done_tile + 1; it < my_tiles; ++it) epi1(it);
   }
 
   tcgen05_fence_before();
