@@ -388,7 +388,10 @@ def committed_traffic():
     """DRAM bytes of the tensor-core conv kernels of one B=256 step, from the newest committed ncu capture
     (profiles/*_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the step's launches)."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    import re
+    # encoder-step captures only (r1e_traffic.json, r2_traffic.json ...): the ViT / PPO-update captures share the schema
+    files = sorted(f for f in glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json"))
+                   if re.fullmatch(r"r\d+[a-z]?_traffic\.json", os.path.basename(f)))
     if not files:
         return None, None
     d = json.load(open(files[-1]))

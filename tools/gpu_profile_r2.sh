@@ -21,8 +21,9 @@ timeout 600 ncu --metrics $M --clock-control none -s $((3 * N)) -c $N --csv --lo
 timeout 600 ncu --metrics $M --clock-control none --csv --log-file gpurun_out/launches_ac_$TAG.csv python tools/profile_ac.py 128 60 > /dev/null 2>&1
 timeout 600 ncu --metrics $M --clock-control none --csv --log-file gpurun_out/launches_vit_$TAG.csv python tools/profile_vit.py 512 > /dev/null 2>&1
 F="--set full --clock-control none --import-source on"
-timeout 600 ncu $F -k regex:bneck_tail -s 3 -c 3 -o gpurun_out/prof_bneck_tail_$TAG -f $B > /dev/null 2>&1
-timeout 600 ncu $F -k regex:conv3x3_halo -s 30 -c 2 -o gpurun_out/prof_conv3x3_$TAG -f $B > /dev/null 2>&1
+timeout 600 ncu $F -k regex:bneck_tail -s 15 -c 5 -o gpurun_out/prof_bneck_tail_$TAG -f $B > /dev/null 2>&1
+timeout 600 ncu $F -k regex:conv3x3_halo -s 39 -c 4 -o gpurun_out/prof_conv3x3_$TAG -f $B > /dev/null 2>&1
+timeout 600 ncu $F -k regex:stem_conv1_rows -s 3 -c 1 -o gpurun_out/prof_stem_$TAG -f $B > /dev/null 2>&1
 timeout 600 ncu $F -k regex:gemm2sm -s 40 -c 3 -o gpurun_out/prof_gemm2sm_$TAG -f $B > /dev/null 2>&1
 timeout 600 ncu $F -k regex:conv_gemm -s 60 -c 2 -o gpurun_out/prof_conv_gemm_$TAG -f $B > /dev/null 2>&1
 timeout 600 ncu $F -k regex:"attention_tc|gemm2sm" -s 30 -c 5 -o gpurun_out/prof_vit_$TAG -f python tools/profile_vit.py 512 > /dev/null 2>&1
