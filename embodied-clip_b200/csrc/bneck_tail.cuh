@@ -293,9 +293,11 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         for (int i = 0; i < C1 / 8; ++i) {
           uint32_t h[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            h[j] = pack_half2(fmaxf(__uint_as_float(v[8 * i + 2 * j]) + sBias1[col + 8 * i + 2 * j], 0.f),
-                              fmaxf(__uint_as_float(v[8 * i + 2 * j + 1]) + sBias1[col + 8 * i + 2 * j + 1], 0.f));
+          for (int j = 0; j < 4; ++j) {
+            float f0 = __uint_as_float(v[8 * i + 2 * j]), f1 = __uint_as_float(v[8 * i + 2 * j + 1]);
+            add_f32x2(f0, f1, sBias1[col + 8 * i + 2 * j], sBias1[col + 8 * i + 2 * j + 1]);
+            h[j] = relu_pack_half2(f0, f1);
+          }
           *reinterpret_cast<uint4*>(dst + col + 8 * i) = make_uint4(h[0], h[1], h[2], h[3]);
         }
       }
@@ -333,20 +335,21 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         for (int i = 0; i < CP / 8; ++i) {
           float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(vv[8 * i + j]) + sBias3[col + 8 * i + j];
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(vv[8 * i + j]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) add_f32x2(f[2 * j], f[2 * j + 1], sBias3[col + 8 * i + 2 * j], sBias3[col + 8 * i + 2 * j + 1]);
           if (kRes) {
             const __half2* h = reinterpret_cast<const __half2*>(&r[i]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float2 r2 = __half22float2(h[j]);
-              f[2 * j] += r2.x;
-              f[2 * j + 1] += r2.y;
+              add_f32x2(f[2 * j], f[2 * j + 1], r2.x, r2.y);
             }
           }
           const uint32_t a = qbase + swizzle_off<128>(uint32_t(row), uint32_t(sub * (CP / 8) + i));
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
-                       "r"(pack_half2(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f))), "r"(pack_half2(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f))),
-                       "r"(pack_half2(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f))), "r"(pack_half2(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f)))
+                       "r"(relu_pack_half2(f[0], f[1])), "r"(relu_pack_half2(f[2], f[3])),
+                       "r"(relu_pack_half2(f[4], f[5])), "r"(relu_pack_half2(f[6], f[7]))
                        : "memory");
         }
       }
@@ -374,8 +377,7 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float2 f = __half22float2(h[e]);
-                  a[2 * e] += f.x;
-                  a[2 * e + 1] += f.y;
+                  add_f32x2(a[2 * e], a[2 * e + 1], f.x, f.y);
                 }
               }
               o = make_uint4(pack_half2(a[0] * .25f, a[1] * .25f), pack_half2(a[2] * .25f, a[3] * .25f),

@@ -196,7 +196,7 @@ static int launch_cfg(const GemmOp& op, cudaStream_t st) {
   if ((rc = make_map_2d(&tmB, op.wgt, op.w_rows, op.ldw, op.ldw, BK, BN))) return rc;
   p.num_n_blks = op.cout / BN;
   p.taps = op.taps;
-  p.kb_per_tap = op.c0 / BK;
+  p.kb_per_tap = (op.c0 + BK - 1) / BK;                        // (taps == 1 may end on a zero-filled partial box)
   p.kb_src0 = op.taps * p.kb_per_tap;
   p.kb_total = p.kb_src0 + op.c1 / BK;
   p.a0_box_bytes = uint32_t(p.box_w * p.box_h * p.box_n) * BK * 2;
@@ -277,7 +277,14 @@ int embclip::launch_gemm(const GemmOp& op, cudaStream_t st, int force_bn) {
         ((M + 255) / 256) * (op.cout / 256) >= num_sms() / 2)                       // enough pair tiles for every SM pair
       return op.residual ? launch_gemm2sm<256, true>(op, st) : launch_gemm2sm<256, false>(op, st);
   }
-  const int bk = (op.c0 % 64 == 0 && op.c1 % 64 == 0) ? 64 : 32;
+  int bk = (op.c0 % 64 == 0 && op.c1 % 64 == 0) ? 64 : 32;
+  // a long ragged K (the GRU input GEMM: K = 32 x 49 = 1568) still takes 64-wide k-blocks: the last box is half out of bounds in
+  // BOTH operands and TMA fills it with zeros.  Half the k-blocks of the BK = 32 path, which is what a few-CTA GEMM's time is
+  // made of (0.32 us per k-block per CTA, profiles/r2_launch_floor.txt).
+  static const bool ragged64 = getenv("EMBCLIP_NO_RAGGED_K64") == nullptr;
+  if (ragged64 && bk == 32 && op.taps == 1 && !op.a1 && !op.grp_n && op.c0 % 64 == 32 && op.c0 >= 256 &&
+      (op.a_cols == 0 || op.a_cols == op.c0) && op.ldw == op.c0)
+    bk = 64;
   int bn = force_bn ? force_bn : pick_bn(op.cout);
   if (op.grp_n && op.grp_n % bn) bn = op.grp_n % 64 == 0 ? 64 : 32;
   if (op.cout % bn) return fail(EMBCLIP_EINVAL, "cout %d not a multiple of tile N %d", op.cout, bn);

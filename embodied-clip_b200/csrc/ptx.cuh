@@ -244,5 +244,19 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// Packed fp32 pair add (FADD2: two IEEE adds per issue slot) and ReLU on the packed fp16 pair (HMNMX2; round-then-max equals
+// max-then-round, the rounding being monotonic with 0 exact; a tiny negative value may come out as -0 instead of +0: numerically
+// the same operand).  The epilogues of the memory-bound tails are issue-bound: these halve their add / max instruction count.
+__device__ __forceinline__ void add_f32x2(float& a0, float& a1, float b0, float b1) {
+  unsigned long long x, y;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(x) : "l"(x), "l"(y));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(x));
+}
+__device__ __forceinline__ uint32_t relu_pack_half2(float a, float b) {
+  const __half2 h = __hmax2(__floats2half2_rn(a, b), __float2half2_rn(0.f));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
 
 }  // namespace embclip
