@@ -164,6 +164,12 @@ struct HeadsParams {
   float* dlogits;            // [F][A]
   float* dvalues;            // [F]
   float* loss_out;           // [3]
+  // act(): CategoricalDistr(logits).sample() + log_prob(sample) (allenact distributions.py [UPSTREAM]) for every row in the same
+  // launch -- inverse-CDF over exp(logit - max) with the caller's
+  // uniforms, log-prob of the sampled action (one launch for the softmax -> multinomial -> log_softmax -> gather chain)
+  const float* uniforms;     // [F] or nullptr
+  long long* sampled;        // [F]
+  float* sampled_logp;       // [F]
 };
 
 __global__ void __launch_bounds__(256)
@@ -214,6 +220,28 @@ ac_heads_fwd_kernel(const HeadsParams p) {
 #pragma unroll
       for (int j = 0; j <= kMaxActions; ++j) if (j == p.A) v += acc[j];
       p.values[f] = v;
+      if (p.uniforms) {
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMaxActions; ++j) if (j < p.A) sum += __expf(lg[j] - mx);
+        const float target = p.uniforms[f] * sum;
+        float cdf = 0.f, lg_a = 0.f;
+        int a = -1, last = 0;
+#pragma unroll
+        for (int j = 0; j < kMaxActions; ++j) {
+          if (j < p.A) {
+            const float e = __expf(lg[j] - mx);
+            if (e > 0.f) last = j;
+            cdf += e;
+            if (a < 0 && cdf > target) a = j;
+          }
+        }
+        if (a < 0) a = last;                              // u * sum rounded up to the total: the last action with mass
+#pragma unroll
+        for (int j = 0; j < kMaxActions; ++j) if (j == a) lg_a = lg[j];
+        p.sampled[f] = a;
+        p.sampled_logp[f] = lg_a - mx - logf(sum);
+      }
       if (p.loss) {
         float se = 0.f;
 #pragma unroll
@@ -432,32 +460,5 @@ adam_clip_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// CategoricalDistr(logits).sample() + log_prob(sample) for one rollout step (allenact distributions.py [UPSTREAM]): one thread
-// per sampler, inverse CDF on softmax(logits) with a caller-supplied uniform u in [0, 1).  Replaces torch's
-// softmax -> multinomial -> log_softmax -> gather chain (8 launches) of the rollout loop.
-// ------------------------------------------------------------------------------------------------
-__global__ void ac_sample_kernel(const float* __restrict__ logits, const float* __restrict__ uniforms, long long* __restrict__ actions,
-                                 float* __restrict__ log_probs, int N, int A) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  const float* lg = logits + (size_t)n * A;
-  float mx = -INFINITY;
-  for (int j = 0; j < A; ++j) mx = fmaxf(mx, lg[j]);
-  float sum = 0.f;
-  for (int j = 0; j < A; ++j) sum += __expf(lg[j] - mx);
-  const float target = uniforms[n] * sum;
-  float cdf = 0.f;
-  int a = -1, last = 0;
-  for (int j = 0; j < A; ++j) {
-    const float e = __expf(lg[j] - mx);
-    if (e > 0.f) last = j;
-    cdf += e;
-    if (a < 0 && cdf > target) a = j;
-  }
-  if (a < 0) a = last;                                    // u * sum rounded up to the total: the last action with mass
-  actions[n] = a;
-  log_probs[n] = lg[a] - mx - logf(sum);
-}
 
 }  // namespace embclip

@@ -193,11 +193,16 @@ int launch_gru_forward(GruFwdParams p, cudaStream_t st) {
   if (p.H % 64 || p.H <= 0) return fail(EMBCLIP_EINVAL, "gru: hidden size must be a multiple of 64");
   if (p.N <= 0) return fail(EMBCLIP_EINVAL, "gru: no samplers");
   GruClusterGeom cg;
-  if (gru_cluster_geometry(gru_cluster_forward_kernel, p.N, p.H, gru_cluster_fwd_smem(p.H, kGcMaxNS), &cg)) {
+  GruGeom g;
+  // a single step (act) has no recurrence to keep on chip: staging 192 KB of weights per CTA for one use costs more than the
+  // cooperative kernel's plain pass (measured 3.6 us per rollout step at 60 samplers)
+  int coop_groups = num_sms() / (p.H / kGruUB);
+  if (coop_groups > kGruMaxGroups) coop_groups = kGruMaxGroups;
+  const bool one_step = p.T == 1 && (p.N + kGruNS - 1) / kGruNS <= coop_groups;
+  if (!one_step && gru_cluster_geometry(gru_cluster_forward_kernel, p.N, p.H, gru_cluster_fwd_smem(p.H, kGcMaxNS), &cg)) {
     p.groups = cg.groups; p.ns = cg.ns;
     return launch_gru_cluster(gru_cluster_forward_kernel, p, cg, gru_cluster_fwd_smem(p.H, cg.nsp), st);
   }
-  GruGeom g;
   int rc;
   if ((rc = gru_geometry(p.N, p.H, &g))) return rc;
   p.groups = g.groups; p.ns = g.ns;
@@ -485,9 +490,11 @@ extern "C" int embclip_ac_pack_features(embclip_ac_t h, const float* feats_nchw,
 
 // params_version != 0: the caller vouches that equal versions mean equal parameter values, so the forward-only fp16 layouts
 // already sitting in this workspace (same block shape) are reused instead of re-packed (rollout steps between two updates).
+struct ActSample { const float* uniforms; long long* actions; float* log_probs; };
 static int ac_forward_impl(embclip_ac_t h, const float* params, uint64_t params_version, const void* feats_f16, const long long* goals,
                            const float* masks, const float* h0, int T, int N, float* logits, float* values, float* h_last,
-                           void* workspace, uint64_t workspace_bytes, int save_for_backward, void* stream) {
+                           void* workspace, uint64_t workspace_bytes, int save_for_backward, void* stream,
+                           const ActSample* sample = nullptr) {
   int rc;
   if ((rc = check_block(h, T, N, workspace, workspace_bytes))) return rc;
   if (!params || !feats_f16 || !goals || !masks || !h0 || !logits || !values) return fail(EMBCLIP_EINVAL, "ac_forward: null pointer");
@@ -539,17 +546,21 @@ static int ac_forward_impl(embclip_ac_t h, const float* params, uint64_t params_
   GruFwdParams gp;
   memset(&gp, 0, sizeof gp);
   gp.T = T; gp.N = N; gp.H = H; gp.gi = w.GI; gp.w_hh = P(h, params, P_WHH); gp.b_hh = P(h, params, P_BHH); gp.h0 = h0;
-  gp.masks = masks; gp.out = w.Hout;
+  // one rollout step (act): the step's output IS the new memory -- written in place, no copy launch
+  const bool direct_out = T == 1 && !save_for_backward && h_last && h_last != h0;
+  gp.masks = masks; gp.out = direct_out ? h_last : w.Hout;
   gp.h_init = c.trainable_masked_hidden_state ? P(h, params, P_HINIT) : nullptr;
   if (save_for_backward) { gp.r = w.R; gp.z = w.Z; gp.n = w.Nn; gp.hn = w.HN; }
   gp.bar = w.scratch32;
   if ((rc = launch_gru_forward(gp, st))) return rc;
-  if (h_last) CUDA_TRY(cudaMemcpyAsync(h_last, w.Hout + (size_t)(T - 1) * N * H, sizeof(float) * N * H, cudaMemcpyDeviceToDevice, st));
+  if (h_last && !direct_out)
+    CUDA_TRY(cudaMemcpyAsync(h_last, w.Hout + (size_t)(T - 1) * N * H, sizeof(float) * N * H, cudaMemcpyDeviceToDevice, st));
 
   HeadsParams hp;
   memset(&hp, 0, sizeof hp);
-  hp.h = w.Hout; hp.w_actor = P(h, params, P_AW); hp.b_actor = P(h, params, P_AB); hp.w_critic = P(h, params, P_CW);
+  hp.h = gp.out; hp.w_actor = P(h, params, P_AW); hp.b_actor = P(h, params, P_AB); hp.w_critic = P(h, params, P_CW);
   hp.b_critic = P(h, params, P_CB); hp.logits = logits; hp.values = values; hp.F = F; hp.H = H; hp.A = c.num_actions;
+  if (sample) { hp.uniforms = sample->uniforms; hp.sampled = sample->actions; hp.sampled_logp = sample->log_probs; }
   const size_t hsmem = sizeof(float) * (size_t)(c.num_actions + 1) * H;
   { const int rc_ = ensure_smem((const void*)ac_heads_fwd_kernel, (size_t)(hsmem)); if (rc_) return rc_; }
   ac_heads_fwd_kernel<<<blocks_for(F, 8, 4), 256, hsmem, st>>>(hp);
@@ -571,12 +582,10 @@ extern "C" int embclip_ac_act(embclip_ac_t h, const float* params, uint64_t para
                               void* workspace, uint64_t workspace_bytes, void* stream) {
   EMBCLIP_TRACE();
   if (!uniforms || !actions || !action_log_probs || !h_out || !logits) return fail(EMBCLIP_EINVAL, "ac_act: null pointer");
-  int rc = ac_forward_impl(h, params, params_version, feats_f16, goals, masks, h0, 1, N, logits, values, h_out, workspace,
-                           workspace_bytes, 0, stream);
-  if (rc) return rc;
-  ac_sample_kernel<<<blocks_for(N, 128), 128, 0, (cudaStream_t)stream>>>(logits, uniforms, actions, action_log_probs, N, h->cfg.num_actions);
-  CUDA_TRY(cudaGetLastError());
-  return 0;
+  // sampling rides in the heads launch
+  const ActSample sample{uniforms, actions, action_log_probs};
+  return ac_forward_impl(h, params, params_version, feats_f16, goals, masks, h0, 1, N, logits, values, h_out, workspace,
+                         workspace_bytes, 0, stream, &sample);
 }
 
 extern "C" int embclip_ac_ppo_loss(embclip_ac_t h, const float* params, int T, int N, const long long* actions,
