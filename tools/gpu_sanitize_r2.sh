@@ -9,7 +9,7 @@ run() {  # tool, tag, pytest args...
   echo "[$tool $tag] exit $? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' gpurun_out/sanitize_${tool}_${tag}.log | tr '\n' ' ')"
 }
 run memcheck prims tests/test_primitives_gpu.py -k "gemm_epilogues or gemm_cta_pair_epilogues or gemm_k_concat or gemm_residual_wide_tile or conv3x3 or stem_conv1 or avgpool2"
-run memcheck tail tests/test_primitives_gpu.py -k "bneck_tail and not 148"
+run memcheck tail tests/test_primitives_gpu.py -k "bneck_tail and not 148 and not 160"
 run memcheck rn50 tests/test_rn50_gpu.py -k "golden or uint8"
 run memcheck imagenet tests/test_imagenet_gpu.py
 run memcheck act tests/test_actor_critic_gpu.py -k "act_step or encode_rows or harness_packed"
@@ -18,4 +18,6 @@ run memcheck storage tests/test_storage.py
 run memcheck vit tests/test_vit_gpu.py -k "zero_shot or text_features"
 run racecheck gru tests/test_actor_critic_gpu.py -k "(gru_forward_backward_vs_torch and (5-7-128 or 3-33-512)) or trainable"
 run racecheck res tests/test_primitives_gpu.py -k "gemm_epilogues or gemm_residual_wide_tile"
+run racecheck tailpool tests/test_primitives_gpu.py -k "bneck_tail_pool and (1-2-56 or 3-8-32)"
+run racecheck stem tests/test_rn50_gpu.py -k "uint8"
 run synccheck vit tests/test_vit_gpu.py -k "text_features"
