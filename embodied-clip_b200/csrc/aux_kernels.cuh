@@ -783,7 +783,7 @@ attnpool_tc_kernel(const __grid_constant__ CUtensorMap tmQT, const __grid_consta
   const int tile = blockIdx.x;
   const int rq0 = tile * 128;                      // first (image, head) row
   const int rt0 = tile * 4 * p.L;                  // first token row
-  const int nkb = p.C / 64, nchunks = p.C / 128;
+  const int nkb = p.C / 64;
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQT); tma_prefetch_desc(&tmTokK); tma_prefetch_desc(&tmTokMN);
@@ -885,12 +885,16 @@ attnpool_tc_kernel(const __grid_constant__ CUtensorMap tmQT, const __grid_consta
   tcgen05_fence_before();
   __syncthreads();                                 // P complete; phase-1 stages are dead (their MMAs retired before bar_s)
 
-  // ---------------- phase 3: XBAR chunks of 128 channels
+  // ---------------- phase 3: XBAR chunks of 128 channels.  gridDim.y CTAs share a tile: each repeats phases 1-2 (11 of the
+  // kernel's 60 us) and takes a contiguous slice of the channel chunks, so a small batch still fills the SMs (`c` below is the
+  // LOCAL chunk index: buffers and phases follow it, channel offsets follow c0 + c)
+  const int c0 = int(blockIdx.y) * (p.C / 128) / int(gridDim.y);
+  const int nchunks = (int(blockIdx.y) + 1) * (p.C / 128) / int(gridDim.y) - c0;
   auto load_t = [&](int c) {
     const uint32_t bar = bar_tfull + 8 * (c & 1), dst = sT + uint32_t(c & 1) * 65536u;
     mbar_arrive_expect_tx(bar, 65536);
-    tma_load_2d(&tmTokMN, bar, dst, c * 128, rt0);
-    tma_load_2d(&tmTokMN, bar, dst + 32768, c * 128 + 64, rt0);
+    tma_load_2d(&tmTokMN, bar, dst, (c0 + c) * 128, rt0);
+    tma_load_2d(&tmTokMN, bar, dst + 32768, (c0 + c) * 128 + 64, rt0);
   };
   if (tid == 0) { load_t(0); if (nchunks > 1) load_t(1); }
   for (int c = 0; c <= nchunks; ++c) {
@@ -911,7 +915,7 @@ attnpool_tc_kernel(const __grid_constant__ CUtensorMap tmQT, const __grid_consta
       mbar_wait(bar_o + 8 * (e & 1), uint32_t(e >> 1) & 1u);
       tcgen05_fence_after();
       if (tid == 0 && e + 2 < nchunks) load_t(e + 2);          // its token tile is free again
-      __half* orow = p.xbar + (size_t)(rq0 + r) * p.C + (size_t)e * 128;
+      __half* orow = p.xbar + (size_t)(rq0 + r) * p.C + (size_t)(c0 + e) * 128;
 #pragma unroll 1
       for (int q4 = 0; q4 < 4; ++q4) {
         uint32_t v[32];

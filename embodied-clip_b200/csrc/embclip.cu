@@ -1180,7 +1180,11 @@ static int run_op(embclip_rn50* m, const Op& op, const std::vector<uint64_t>& of
         if ((rc = make_map_2d(&tmn, act_ptr(op.in1), B * m->tokens, m->embed, m->embed, 64, 256))) return rc;
         AttnPoolTcParams ap;
         ap.B = B; ap.heads = m->cfg.heads; ap.L = m->tokens; ap.C = m->embed; ap.xbar = (__half*)act_ptr(op.out);
-        CUDA_TRY(launch_pdl(attnpool_tc_kernel, dim3((B + 3) / 4), dim3(128), (size_t)kApSmem, st, tq, tk, tmn, ap));
+        // channel-chunk split: the largest power of two that still gives every CTA an SM (B = 256: 64 tiles x 2; B = 8: 2 x 16)
+        const int tiles = (B + 3) / 4, nch = m->embed / 128;
+        int split = 1;
+        while (split * 2 <= nch && nch % (split * 2) == 0 && tiles * split * 2 <= num_sms()) split *= 2;
+        CUDA_TRY(launch_pdl(attnpool_tc_kernel, dim3(tiles, split), dim3(128), (size_t)kApSmem, st, tq, tk, tmn, ap));
         return 0;
       }
       constexpr int HG = 8;
