@@ -407,8 +407,8 @@ static int launch_conv3x3_halo(const Conv3Op& op, cudaStream_t st) {
   int bn = op.N % 128 == 0 ? 128 : (op.N % 64 == 0 ? 64 : 32);
   if (env_bn && op.N % env_bn == 0 && env_bn >= 128 && op.N % 128 == 0) bn = env_bn;
   int ms = bn == 256 ? 1 : (bn == 128 ? 2 : 4);
-  if (env_ms && env_ms * bn * 2 <= 512) ms = env_ms;
   C3Geom g;
+  if (env_ms && env_ms * bn * 2 <= 512 && c3_geometry(op.B, op.H, op.W, env_ms, op.pool != 0, &g)) ms = env_ms;   // (a hint: shapes it does not fit keep the default)
   const int ms0 = ms;
   for (;; ms >>= 1) {
     if (ms < 1) {
