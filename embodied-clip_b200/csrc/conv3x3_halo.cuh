@@ -43,6 +43,7 @@ struct Conv3Params {
   int relu;
   int N;                       // Cout
   int reverse;                 // 1: walk the tiles last-to-first (snake order across layers)
+  int resident;                // 1: one N block, one chunk, n_b == 9: the nine weight tiles are loaded ONCE per CTA and stay (stem, layer 1)
   int pool;                    // 1: write avgpool2(relu(conv)) [B, H/2, W/2, N] instead of the full-resolution map;
                                // 2: write relu(conv)[:, ::2, ::2] -- a STRIDE-2 3x3 conv (torchvision Bottleneck.conv2), same epilogue
   const float* bias;
@@ -122,6 +123,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        if (p.resident && t != int(blockIdx.x)) break;         // every tile of this CTA uses the same nine weight tiles
         const int n_blk = (p.reverse ? num_tiles - 1 - t : t) % p.num_n_blks;
         for (int c = 0; c < p.chunks; ++c) {
           for (int tap = 0; tap < 9; ++tap) {
@@ -173,7 +175,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // one issue round = one kernel row (3 taps): their weight stages are polled by three lanes at once and
         // the 3 * MS * KC/16 MMAs go out back to back, so barrier / elect latency is paid once per 3 taps
         for (int kh = 0; kh < 3; ++kh) {
-          ring_wait(bar_bfull, stage, bphase, 3, p.n_b);
+          // resident weights: only the CTA's first tile waits for them (and nothing is ever handed back to the producer)
+          if (!(p.resident && t != int(blockIdx.x))) ring_wait(bar_bfull, stage, bphase, 3, p.n_b);
           tcgen05_fence_after();
           const uint32_t a_row = plane_lo + uint32_t(kh * p.Wp) * (SWZ / 16);
           const uint32_t first = uint32_t((c | kh) != 0);
@@ -191,7 +194,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   umma_f16_ss(d_tmem + uint32_t(s * BN), desc64(a_lo + uint32_t(s * 128 * SWZ / 16 + 2 * k), dhi),
                               desc64(b_lo + uint32_t(2 * k), dhi), idesc, (kw | k) == 0 ? first : 1u);
               }
-              umma_commit(bar_bempty + 8 * st);
+              if (!p.resident) umma_commit(bar_bempty + 8 * st);
             }
           }
           __syncwarp();

@@ -375,6 +375,12 @@ static int launch_c3_cfg(const Conv3Op& op, const C3Geom& g, cudaStream_t st) {
     n_b = int((budget - uint32_t(n_a) * plane_bytes) / kBBytes);
   }
   if (n_b > 12) n_b = 12;
+  // Small convs (stem conv2 / conv3, layer-1 conv2: one chunk, one N block, 18 .. 72 KB of weights): every tile of a CTA reads the
+  // SAME nine weight tiles, so they are loaded once and stay; the MMA warp then issues a tile's 9 taps without a barrier round per
+  // kernel row (at N = 32 a weight stage feeds only 128 cycles of UMMAs: the rounds, not the traffic, were the cost)
+  static const bool resident_ok = getenv("EMBCLIP_C3_NO_RESIDENT") == nullptr;
+  const bool resident = resident_ok && chunks == 1 && op.N == BN && uint32_t(n_a) * plane_bytes + 9u * kBBytes <= budget;
+  if (resident) n_b = 9;
   const size_t smem = 1024 + size_t(n_a) * plane_bytes + size_t(n_b) * kBBytes + kC3BarBytes + stage_bytes;
   { const int rc_ = ensure_smem((const void*)conv3x3_halo_kernel<BN, MS, KC, kPool>, (size_t)(smem)); if (rc_) return rc_; }
   CUtensorMap tmA, tmB;
@@ -386,7 +392,7 @@ static int launch_c3_cfg(const Conv3Op& op, const C3Geom& g, cudaStream_t st) {
   p.num_m_tiles = g.tiles; p.num_n_blks = op.N / BN;
   p.strips_per_image = g.strips; p.R = g.R; p.G = g.G; p.BHo = g.BHo;
   p.H = op.H; p.W = op.W; p.Wp = g.Wp; p.B = op.B; p.C = op.C; p.chunks = chunks;
-  p.n_a = n_a; p.n_b = n_b;
+  p.n_a = n_a; p.n_b = n_b; p.resident = resident ? 1 : 0;
   p.plane_bytes = plane_bytes; p.plane_tx_bytes = g.rows_tma * SWZ;
   p.plane_rows_tma = g.rows_tma; p.plane_rows_alloc = plane_bytes / SWZ;
   p.relu = op.relu; p.N = op.N; p.pool = op.pool; p.reverse = op.reverse;
