@@ -54,7 +54,8 @@ constexpr int kC3Threads = 384;
 constexpr int kC3EpiWarps = 8;
 constexpr int kC3EpiThreads = kC3EpiWarps * 32;
 constexpr int kC3MaxA = 4, kC3MaxB = 16;
-constexpr int kC3BarBytes = 512;
+constexpr int kC3BiasBytes = kC3EpiWarps * 128 * 4;            // a private bias slice per epilogue warp (<= 128 columns)
+constexpr int kC3BarBytes = 512 + kC3BiasBytes;               // barriers + TMEM slot, then the bias slices
 
 template <int BN, int MS, int KC, bool kPool>
 __global__ void __launch_bounds__(kC3Threads, 1)
@@ -238,11 +239,21 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     int acc = 0;
     uint32_t acc_phase = 0;
+    // this warp's bias columns live in a private shared-memory slice, refilled only when the N block changes and BEFORE the
+    // accumulator wait (the global-load latency used to sit inside every column chunk of every tile)
+    float* const bias_w = reinterpret_cast<float*>(gen_base + (sBar - smem_base) + 512) + (warp - 4) * 128;
+    int bias_blk = -1;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int n_blk, img0, h0;
       tile_coords(t, n_blk, img0, h0);
       const int n0 = n_blk * BN;
       __half* const tile_out = p.out + (size_t(img0) * p.H + h0) * p.W * p.N + n0;
+      if (n_blk != bias_blk) {
+        __syncwarp();                                          // the previous tile's reads of the slice are done
+        for (int i = lane; i < kColsPerWarp; i += 32) bias_w[i] = p.bias ? __ldg(p.bias + n0 + col_base + i) : 0.f;
+        __syncwarp();
+        bias_blk = n_blk;
+      }
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -251,7 +262,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float bv[CH];
 #pragma unroll
         for (int i = 0; i < CH / 4; ++i) {
-          const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col) + i) : make_float4(0, 0, 0, 0);
+          const float4 b4 = reinterpret_cast<const float4*>(bias_w + c * CH)[i];
           bv[4 * i] = b4.x; bv[4 * i + 1] = b4.y; bv[4 * i + 2] = b4.z; bv[4 * i + 3] = b4.w;
         }
 #pragma unroll
