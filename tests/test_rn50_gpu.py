@@ -146,6 +146,32 @@ def test_rn50_uint8_frames(encoder, rn50_visual):
         encoder(torch.zeros(2, 224, 224, 3, device="cuda", dtype=torch.int32))
 
 
+def test_profile_lists_every_launch_for_both_frame_dtypes(encoder):
+    """embclip_rn50_profile / _profile_u8: one (name, ms) per launch of the forward, same op list for fp32 and raw uint8 frames
+    (the uint8 entry exists because the fp32 one would read a uint8 buffer as floats), and the profiled pass leaves the same
+    outputs as a plain forward."""
+    g = torch.Generator().manual_seed(11)
+    u8 = torch.randint(0, 256, (2, 224, 224, 3), generator=g, dtype=torch.uint8).cuda()
+    mean, std = torch.tensor(encoder.CLIP_RGB_MEANS), torch.tensor(encoder.CLIP_RGB_STDS)
+    f32 = ((u8.cpu().float() / 255.0 - mean) / std).cuda()
+    heads = ("trunk", "avgpool", "attnpool")
+    ops_f = encoder.profile(f32, heads)
+    ops_u = encoder.profile(u8, heads)
+    torch.cuda.synchronize()
+    assert [n for n, _ in ops_f] == [n for n, _ in ops_u]
+    assert len(ops_f) == encoder.launches_per_forward(heads)
+    assert all(0.0 < ms < 50.0 for _, ms in ops_f + ops_u)
+    names = [n for n, _ in ops_f]
+    assert names[0] == "stem.conv1" and "layer4.2.conv3" in names and "attnpool.c" in names
+    assert "layer2.0.xpool" not in names          # written by layer1.2's fused tail (pooled-output variant), not a launch
+    ref = {k: v.clone() for k, v in encoder(u8, want=heads).items()}
+    encoder.profile(u8, heads)
+    out = encoder(u8, want=heads)
+    torch.cuda.synchronize()
+    for k in heads:
+        assert torch.equal(out[k], ref[k]), k
+
+
 def _heavy_tailed_oracle(seed: int, calibrated: bool):
     """Weight sets with heavy-tailed per-channel BatchNorm statistics (VERDICT r1 "numerics margin").
 
