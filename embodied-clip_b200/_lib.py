@@ -59,6 +59,7 @@ SIGNATURES = {
     "embclip_rn50_profile": (_I, [_VP, _FP, _I, _FP, _FP, _FP, _VP, _U64, _VP, _VP, _VP, _I]),
     "embclip_rn50_profile_u8": (_I, [_VP, _VP, C.POINTER(C.c_float), C.POINTER(C.c_float), _I, _FP, _FP, _FP, _VP, _U64, _VP, _VP, _VP, _I]),
     "embclip_rn50_launches_per_forward": (_I, [_VP, _I, _I, _I]),
+    "embclip_rn50_encode_rows_f16": (_I, [_VP, _VP, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), _I, _VP, _VP, _U64, _VP]),
     "embclip_rn50_export_rows_f16": (_I, [_VP, _I, _VP, _U64, _VP, _VP]),
     "embclip_gemm_f16": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "embclip_gemm_grouped_f16": (_I, [_VP, _I, _VP, _I, _I, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP]),

@@ -1104,7 +1104,7 @@ extern "C" int embclip_rn50_act_info(embclip_rn50_t h, int batch, int index, emb
   return 0;
 }
 
-struct FramesIn { const void* ptr; int u8; float norm[6]; };
+struct FramesIn { const void* ptr; int u8; float norm[6]; void* rows_f16 = nullptr; };   // rows_f16: see embclip_rn50_encode_rows_f16
 static int run_op(embclip_rn50* m, const Op& op, const std::vector<uint64_t>& offs, const FramesIn& frames, int B,
                   float* o_nchw, float* o_avg, float* o_attn, uint8_t* ws, cudaStream_t st) {
   auto act_ptr = [&](int id) -> void* { return id >= 0 ? (void*)(ws + offs[id]) : nullptr; };
@@ -1165,6 +1165,9 @@ static int run_op(embclip_rn50* m, const Op& op, const std::vector<uint64_t>& of
       g.residual = act_ptr(op.res);
       g.out = op.out == -4 ? (void*)o_attn : act_ptr(op.out);
       g.cout = op.cout; g.relu = op.relu; g.out_f32 = op.out_f32;
+      // rows-only forward: the last conv rounds its fp32 result to fp16 in its own epilogue and stores the policy's pixel rows
+      // (the fp32 NHWC tensor is not written: no head reads it in this mode)
+      if (frames.rows_f16 && op.out == m->act_trunk_f32) { g.out = frames.rows_f16; g.out_f32 = 0; }
       g.grp_n = op.grp_n; g.grp_a_koff = op.grp_a_koff; g.grp_b_koff = op.grp_b_koff; g.grp_b_nmod = op.grp_b_nmod;
       g.reverse = op.reverse;
       return launch_gemm(g, st, op.force_bn);
@@ -1344,6 +1347,24 @@ extern "C" int embclip_rn50_profile_u8(embclip_rn50_t h, const uint8_t* frames_n
   }
   return forward_impl(h, in, batch, out_trunk_nchw, out_avgpool, out_attnpool, workspace, workspace_bytes,
                       (cudaStream_t)stream, op_ms, names, max_ops);
+}
+extern "C" int embclip_rn50_encode_rows_f16(embclip_rn50_t h, const void* frames_nhwc, int frames_are_u8, const float* mean3, const float* std3,
+                                            int batch, void* out_rows_f16, void* workspace, uint64_t workspace_bytes, void* stream) {
+  EMBCLIP_TRACE();
+  if (!out_rows_f16) return fail(EMBCLIP_EINVAL, "encode_rows: null output");
+  if (reinterpret_cast<uintptr_t>(out_rows_f16) % 16) return fail(EMBCLIP_EINVAL, "encode_rows: output must be 16-B aligned");
+  FramesIn in{frames_nhwc, frames_are_u8 ? 1 : 0, {1, 1, 1, 0, 0, 0}};
+  if (frames_are_u8) {
+    if (!mean3 || !std3) return fail(EMBCLIP_EINVAL, "encode_rows: mean / std required for uint8 frames");
+    for (int c = 0; c < 3; ++c) {
+      if (!(std3[c] > 0.f)) return fail(EMBCLIP_EINVAL, "encode_rows: std must be positive");
+      in.norm[c] = 1.f / (255.f * std3[c]);
+      in.norm[3 + c] = -mean3[c] / std3[c];
+    }
+  }
+  in.rows_f16 = out_rows_f16;
+  const int rc = forward_impl(h, in, batch, nullptr, nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream, nullptr, nullptr, 0);
+  return rc < 0 ? rc : 0;
 }
 extern "C" int embclip_rn50_export_rows_f16(embclip_rn50_t h, int batch, const void* workspace, uint64_t workspace_bytes,
                                             void* out_rows_f16, void* stream) {

@@ -171,11 +171,14 @@ class ClipRN50Encoder:
             raise ValueError(f"out must be a contiguous fp16 tensor of {rows} x {self.embed} elements on {self.device}")
         if B == 0:
             return out
-        self.forward(frames, want=())
         ws = self._workspace(B)
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            _lib.check(self.lib.embclip_rn50_export_rows_f16(self._h, B, ws.data_ptr(), ws.numel(), out.data_ptr(), stream))
+            u8 = frames.dtype == torch.uint8
+            mean = (C.c_float * 3)(*self.CLIP_RGB_MEANS) if u8 else None
+            std = (C.c_float * 3)(*self.CLIP_RGB_STDS) if u8 else None
+            _lib.check(self.lib.embclip_rn50_encode_rows_f16(self._h, frames.data_ptr(), int(u8), mean, std, B, out.data_ptr(),
+                                                             ws.data_ptr(), ws.numel(), stream))
         return out
 
     def profile(self, frames: torch.Tensor, want: Iterable[str] = ("trunk",)) -> List[Tuple[str, float]]:

@@ -110,6 +110,13 @@ int embclip_rn50_profile(embclip_rn50_t h, const float* frames_nhwc, int batch, 
 int embclip_rn50_profile_u8(embclip_rn50_t h, const uint8_t* frames_nhwc_u8, const float* mean3, const float* std3, int batch,
                             float* out_trunk_nchw, float* out_avgpool, float* out_attnpool, void* workspace,
                             uint64_t workspace_bytes, void* stream, float* op_ms, char* names, int max_ops);
+/* Trunk forward whose ONLY result is the actor-critic path's input: fp16 NHWC pixel rows [batch * fres * fres, embed]
+ * (the layout of embclip_ac_pack_features, bit-identical to packing the fp32 NCHW trunk output).  The last conv rounds to fp16
+ * in its own epilogue: no fp32 trunk tensor, no cast launch.  frames_are_u8 = 0: fp32 NHWC normalised frames (mean3 / std3
+ * ignored); 1: raw uint8 NHWC frames, normalised in the stem kernel.  Replaces ClipResNetEmbedder.forward (trunk only)
+ * + ResnetTensorNavActorCritic's view of the features for a rollout loop that keeps its storage on the device. */
+int embclip_rn50_encode_rows_f16(embclip_rn50_t h, const void* frames_nhwc, int frames_are_u8, const float* mean3, const float* std3,
+                                 int batch, void* out_rows_f16, void* workspace, uint64_t workspace_bytes, void* stream);
 /* fp16 copy of the trunk output of the LAST forward on this workspace, as NHWC pixel rows [batch * fres * fres, embed] -- the
  * layout the actor-critic path consumes (embclip_ac_pack_features output), bit-identical to packing the fp32 NCHW trunk
  * output.  Lets a rollout loop skip the fp32 NCHW round trip. */
