@@ -47,7 +47,7 @@ def zeroshot(clip_vit):
     return ClipZeroShot(clip_vit.state_dict(), "cuda:0")
 
 
-@pytest.mark.parametrize("batch", [1, 3])
+@pytest.mark.parametrize("batch", [1, 3, 64])          # 64 distinct frames = BASELINE config 5's per-GPU size at 8 GPUs
 def test_vit_image_features_vs_oracle(zeroshot, clip_vit, batch):
     frames = synthetic_frames(batch, seed=20 + batch)
     with torch.no_grad():
