@@ -286,6 +286,14 @@ int embclip::launch_gemm(const GemmOp& op, cudaStream_t st, int force_bn) {
       (op.a_cols == 0 || op.a_cols == op.c0) && op.ldw == op.c0)
     bk = 64;
   int bn = force_bn ? force_bn : pick_bn(op.cout);
+  {
+    // few-row GEMMs (a rollout step at 8 samplers: layers 3-4 and the actor-critic's pointwise convs) take 64-wide N tiles: twice
+    // the CTAs and more pipeline stages per CTA.  Measured at 8 frames: 0.570 -> 0.566 ms per rollout step; 32-wide tiles and
+    // a higher row threshold are slower (0.586 ms; 1.191 -> 1.237 ms at 60 frames with the threshold at 16 K rows)
+    static const int small_bn = getenv("EMBCLIP_SMALLM_BN") ? atoi(getenv("EMBCLIP_SMALLM_BN")) : 64;
+    static const int small_m = getenv("EMBCLIP_SMALLM_ROWS") ? atoi(getenv("EMBCLIP_SMALLM_ROWS")) : 2048;
+    if (small_bn && !force_bn && !op.grp_n && (long long)op.n * op.h * op.w <= small_m && bn > small_bn && op.cout % small_bn == 0) bn = small_bn;
+  }
   if (op.grp_n && op.grp_n % bn) bn = op.grp_n % 64 == 0 ? 64 : 32;
   if (op.cout % bn) return fail(EMBCLIP_EINVAL, "cout %d not a multiple of tile N %d", op.cout, bn);
   const bool res = op.residual != nullptr;
